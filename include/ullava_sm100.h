@@ -1,0 +1,236 @@
+/*
+ * ullava_sm100.h -- C ABI of libullava_sm100.so, the B200 (sm_100a) implementation of the
+ * u-LLaVA data-parallel inference hot path.
+ *
+ * The reference (OPPOMKLab/u-LLaVA) has no FFI: its boundary is the Python nn.Module API of
+ * models/ullava_core.py, models/ullava.py and models/segment_anything.
+ * The host-side mirror of that API lives in u-llava_b200/models/ and calls ONLY the entry
+ * points declared here (through ctypes, see u-llava_b200/native.py and INTEGRATION.md).
+ * Each entry point cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, integer shapes, a cudaStream_t passed as void*;
+ *     no torch / C++ types cross the boundary, no exception crosses it;
+ *   - every function returns 0 on success and a negative ullava_status otherwise; the message
+ *     is available from ullava_last_error() (thread local);
+ *   - the library never allocates or frees caller-visible memory: outputs, KV caches and the
+ *     scratch workspace are allocated by the caller (PyTorch caching allocator) and passed in;
+ *   - all kernels are enqueued on the given stream and are CUDA-graph capturable
+ *     (no synchronisation, no allocation inside);
+ *   - "dtype" is the 16-bit storage type of activations and weights: ULLAVA_BF16 or ULLAVA_F16;
+ *     accumulation, softmax, LayerNorm/RMSNorm statistics and RoPE are fp32.
+ */
+#ifndef ULLAVA_SM100_H_
+#define ULLAVA_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ULLAVA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ULLAVA_API __attribute__((visibility("default")))
+#else
+#define ULLAVA_API
+#endif
+
+typedef struct ullava_ctx ullava_ctx;
+
+enum ullava_status {
+  ULLAVA_OK = 0,
+  ULLAVA_ERR_BAD_ARG = -1,
+  ULLAVA_ERR_UNSUPPORTED = -2,
+  ULLAVA_ERR_CUDA = -3,
+  ULLAVA_ERR_ARCH = -4,
+  ULLAVA_ERR_WORKSPACE = -5
+};
+
+enum ullava_dtype { ULLAVA_BF16 = 0, ULLAVA_F16 = 1, ULLAVA_F32 = 2 };
+
+/* GEMM epilogues (applied as  D = act(A*B^T + bias) + residual) */
+enum ullava_epilogue {
+  ULLAVA_EPI_NONE = 0,
+  ULLAVA_EPI_RELU = 1,       /* models/ullava.py:86-101, segment_anything/modeling/transformer.py (MLPBlock, ReLU) */
+  ULLAVA_EPI_GELU = 2,       /* erf GELU: models/ullava_core.py:121-126 (mlp2x projector) */
+  ULLAVA_EPI_QUICK_GELU = 3, /* x*sigmoid(1.702x): CLIP MLP, hf:models/clip/modeling_clip.py:339-351 */
+  ULLAVA_EPI_SILU_MUL = 4    /* silu(gate)*up on gate/up rows interleaved in blocks of 16:
+                                LLaMA MLP, hf:models/llama/modeling_llama.py:171-184 */
+};
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+ULLAVA_API int ullava_abi_version(void);
+ULLAVA_API const char* ullava_last_error(void);
+/* Creates a per-device context (device must be compute capability 10.x). */
+ULLAVA_API int ullava_create(int device, ullava_ctx** out);
+ULLAVA_API int ullava_destroy(ullava_ctx* ctx);
+/* Registers caller-owned scratch memory (split-K partials, attention scratch). 256 B aligned. */
+ULLAVA_API int ullava_set_workspace(ullava_ctx* ctx, void* ptr, size_t bytes);
+/* Number of kernels this context has enqueued so far (bench.py's gpu_launches). */
+ULLAVA_API int64_t ullava_launch_count(ullava_ctx* ctx);
+
+/* ---- GEMM: D[M,N] = act(A[M,K] * B[N,K]^T + bias[N]) + residual[M,N] ------------------
+ * Replaces torch.nn.Linear at every call site of the path (CLIP / LLaMA / projector / lm_head /
+ * seg & det projectors).  A, B: 16-bit row-major, lda/ldb in elements (multiples of 8).
+ * D: 16-bit (out_f32 = 0) or fp32 (out_f32 = 1).  With ULLAVA_EPI_SILU_MUL, D has N/2 columns. */
+typedef struct ullava_gemm_args {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* D; int64_t ldd;
+  const void* bias;              /* [N] 16-bit or NULL */
+  const void* residual; int64_t ldr; /* 16-bit, layout of D, or NULL */
+  int32_t M, N, K;
+  int32_t dtype;                 /* ullava_dtype of A, B, bias, residual */
+  int32_t out_f32;
+  int32_t epilogue;              /* ullava_epilogue */
+  int32_t force_bn;              /* 0 = auto; else tile N in {16,32,64,128,256} (tests/tuning) */
+  int32_t force_splits;          /* 0 = auto; else split-K factor */
+  int32_t no_swap;               /* 1 = never use the small-M swap-AB path */
+} ullava_gemm_args;
+ULLAVA_API int ullava_gemm(ullava_ctx* ctx, const ullava_gemm_args* args, void* stream);
+
+/* ---- normalisation ---------------------------------------------------------------------
+ * LayerNorm over the last dim (fp32 statistics): CLIP pre_layrnorm / layer_norm1/2
+ * (hf:models/clip/modeling_clip.py:354-385,677), SAM TwoWayTransformer norms
+ * (segment_anything/modeling/transformer.py:151-182), LayerNorm2d of the mask head (common.py:31-43,
+ * channels-last rows).  act: ULLAVA_EPI_NONE or ULLAVA_EPI_GELU (fused activation).  y may alias x. */
+ULLAVA_API int ullava_layernorm(ullava_ctx* ctx, const void* x, int64_t ldx, const void* weight, const void* bias, void* y,
+                     int64_t ldy, int32_t rows, int32_t cols, float eps, int32_t act, int32_t dtype, void* stream);
+/* LlamaRMSNorm (hf:models/llama/modeling_llama.py:52-69): y = w * (x * rsqrt(mean(x^2) + eps)),
+ * x up-cast to fp32, normalised value rounded to the 16-bit dtype BEFORE the multiply by w. */
+ULLAVA_API int ullava_rmsnorm(ullava_ctx* ctx, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int32_t rows,
+                   int32_t cols, float eps, int32_t dtype, void* stream);
+
+/* ---- attention -------------------------------------------------------------------------
+ * Flash-style softmax(Q K^T * scale) V with fp32 online softmax.  Q/K/V are strided views
+ * [batch, seq, heads, head_dim] given by (batch stride, row stride, head stride) in elements, so
+ * the packed QKV GEMM output or a KV cache can be consumed in place.
+ * Replaces CLIPAttention (hf:models/clip/modeling_clip.py:282-336, non causal, hd 64) and
+ * LlamaAttention eager (hf:models/llama/modeling_llama.py:199-291, causal, hd 128).
+ * causal: query i (absolute position q_pos0 + i) sees keys j <= q_pos0 + i. */
+typedef struct ullava_attn_args {
+  const void* q; int64_t q_bs, q_rs, q_hs;
+  const void* k; int64_t k_bs, k_rs, k_hs;
+  const void* v; int64_t v_bs, v_rs, v_hs;
+  void* o; int64_t o_bs, o_rs, o_hs;
+  int32_t batch, heads, seq_q, seq_k, head_dim;
+  int32_t causal, q_pos0;
+  float scale;
+  int32_t dtype;
+} ullava_attn_args;
+ULLAVA_API int ullava_attention(ullava_ctx* ctx, const ullava_attn_args* args, void* stream);
+
+/* Single-query (decode) attention against a KV cache [batch, heads, max_seq, head_dim]:
+ * LlamaAttention with past_key_values, one new token per sample.  ctx_len keys are attended. */
+ULLAVA_API int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q_bs, const void* k_cache, const void* v_cache,
+                            int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
+                            int32_t head_dim, int32_t ctx_len, float scale, int32_t dtype, void* stream);
+
+/* RoPE (rotate-half, hf:models/llama/modeling_llama.py:74-168) applied to the q and k thirds of a
+ * packed QKV buffer [rows, 3*heads*head_dim]; rotated k and the untouched v are scattered into the
+ * KV cache [batch, heads, max_seq, head_dim] at position pos0 + (row % seq); rotated q is written
+ * back in place.  cos_table / sin_table: fp32 [max_pos, head_dim/2] (LlamaRotaryEmbedding, fp32). */
+ULLAVA_API int ullava_rope_kvcache(ullava_ctx* ctx, void* qkv, int64_t ld_qkv, void* k_cache, void* v_cache, int64_t cache_bs,
+                        int64_t cache_hs, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, int32_t pos0,
+                        const float* cos_table, const float* sin_table, int32_t dtype, void* stream);
+
+/* ---- glue kernels ------------------------------------------------------------------------ */
+/* CLIP patchify as im2col (hf:models/clip/modeling_clip.py:148-154,209-210): pixels [B,3,H,W] ->
+ * patches [B*gh*gw, k_pad] with column order (c, ky, kx) matching Conv2d.weight.view(out, -1);
+ * columns >= 3*patch*patch are zero. */
+ULLAVA_API int ullava_vit_im2col(ullava_ctx* ctx, const void* pixels, void* out, int32_t batch, int32_t img, int32_t patch,
+                      int32_t k_pad, int32_t dtype, void* stream);
+/* CLIP embeddings (hf:...modeling_clip.py:212-218): out[b,0]=cls+pos[0]; out[b,1+p]=patch[b,p]+pos[1+p]. */
+ULLAVA_API int ullava_vit_assemble(ullava_ctx* ctx, const void* patch_embeds, const void* cls, const void* pos, void* out,
+                        int32_t batch, int32_t n_patches, int32_t dim, int32_t dtype, void* stream);
+/* Token-embedding gather (models/ullava_core.py:191): out[r] = table[ids[r]]. */
+ULLAVA_API int ullava_embed_gather(ullava_ctx* ctx, const int64_t* ids, const void* table, void* out, int32_t rows, int32_t dim,
+                        int32_t vocab, int32_t dtype, void* stream);
+/* Image-feature splice (models/ullava_core.py:222-246): for each sample b overwrite rows
+ * [start[b]+1, start[b]+1+n_patch) of embeds [B,L,dim] with feats [B,n_patch,dim]; start[b] < 0 = skip. */
+ULLAVA_API int ullava_splice_rows(ullava_ctx* ctx, void* embeds, const void* feats, const int32_t* start, int32_t batch,
+                       int32_t seq, int32_t n_patch, int32_t dim, int32_t dtype, void* stream);
+/* Strided row copy dst[r] = src[r] for 16-bit matrices (drop-CLS, hidden-state accumulation). */
+ULLAVA_API int ullava_copy_rows(ullava_ctx* ctx, const void* src, int64_t src_bs, int64_t src_rs, void* dst, int64_t dst_bs,
+                     int64_t dst_rs, int32_t batch, int32_t rows, int32_t cols, int32_t dtype, void* stream);
+/* Greedy token: out[r] = argmax_c logits[r, c] over fp32 logits (first index on ties, like torch.argmax). */
+ULLAVA_API int ullava_argmax(ullava_ctx* ctx, const float* logits, int64_t ld, int64_t* out, int32_t rows, int32_t cols,
+                  void* stream);
+
+/* ---- SAM mask decoder ----------------------------------------------------------------------
+ * Everything after the image encoder for n prompts of one image:
+ * PromptEncoder(text_embeds) (segment_anything/modeling/prompt_encoder.py:140-186),
+ * MaskDecoder.predict_masks + TwoWayTransformer (mask_decoder.py:116-164, transformer.py:62-242),
+ * mask slice 0 (multimask_output=False, mask_decoder.py:108-111).
+ * Weights are passed as a table of device pointers in the order documented in
+ * u-llava_b200/models/segment_anything/native_decoder.py (SAM_DECODER_WEIGHT_ORDER). */
+typedef struct ullava_sam_decoder_args {
+  const void* const* weights;   /* host array of device pointers, 16-bit, order fixed (ULLAVA_SAM_N_WEIGHTS) */
+  int32_t n_weights;
+  const void* image_embeddings; /* [n_images, 256, 64, 64] 16-bit (SAM image encoder output, NCHW) */
+  const int32_t* prompt_image;  /* device int32 [n_prompts]: image index of every prompt */
+  const void* image_pe;         /* [256, 64, 64] 16-bit dense positional encoding (get_dense_pe) */
+  const void* text_embeds;      /* [n_prompts, 256] 16-bit ([SEG] embeddings after seg_projector) */
+  int32_t n_prompts;
+  void* low_res_masks;          /* out [n_prompts, 4, 256, 256] 16-bit (all mask tokens; caller slices 0:1) */
+  void* iou_pred;               /* out [n_prompts, 4] 16-bit or NULL */
+  void* scratch; size_t scratch_bytes; /* caller-owned, >= ullava_sam_mask_decoder_scratch_bytes(n_prompts) */
+  int32_t dtype;
+} ullava_sam_decoder_args;
+#define ULLAVA_SAM_N_WEIGHTS 121
+ULLAVA_API int ullava_sam_mask_decoder(ullava_ctx* ctx, const ullava_sam_decoder_args* args, void* stream);
+ULLAVA_API size_t ullava_sam_mask_decoder_scratch_bytes(int32_t n_prompts);
+
+/* Sam.postprocess_masks (segment_anything/modeling/sam.py:137-172): fp32 bilinear low_res->img_size
+ * (align_corners=False), crop [:in_h,:in_w], bilinear -> (out_h,out_w); fused, no img_size^2 buffer.
+ * masks: n masks of [low_res,low_res] 16-bit, mask_stride elements apart; out: [n,out_h,out_w] fp32.
+ * packed_bits (optional): [n, ceil(out_h*out_w/32)] uint32, bit = (logit > 0), for the eval gather. */
+ULLAVA_API int ullava_sam_postprocess(ullava_ctx* ctx, const void* masks, int64_t mask_stride, float* out, uint32_t* packed_bits,
+                           int32_t n, int32_t low_res, int32_t img_size, int32_t in_h, int32_t in_w, int32_t out_h,
+                           int32_t out_w, int32_t dtype, void* stream);
+
+/* ---- fused model-level entry points (layer loops run in C++, one call per stage) ----------- */
+/* CLIP ViT (encode_image, models/ullava_core.py:146-158): pixel_values -> hidden_states[n_layers_used]
+ * without CLS.  Weight table order: see u-llava_b200/models/native_layout.py (VIT_WEIGHT_ORDER). */
+typedef struct ullava_vit_args {
+  const void* const* weights; int32_t n_weights;
+  const void* pixels;      /* [B,3,img,img] 16-bit */
+  void* out;               /* [B, n_patches, hidden] 16-bit (CLS dropped) */
+  void* scratch; size_t scratch_bytes;
+  int32_t batch, img, patch, hidden, heads, ffn, layers_used, k_pad;
+  int32_t act;             /* ullava_epilogue of the MLP: QUICK_GELU (openai CLIP) or GELU */
+  float eps;
+  int32_t dtype;
+} ullava_vit_args;
+ULLAVA_API int ullava_vit_forward(ullava_ctx* ctx, const ullava_vit_args* args, void* stream);
+ULLAVA_API size_t ullava_vit_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32_t hidden, int32_t ffn, int32_t k_pad);
+
+/* LLaMA decoder stack (LlamaModel.forward, hf:models/llama/modeling_llama.py:355-424) on a batch of
+ * equal-length sequences: hidden [B*S, H] (in place) at absolute positions pos0..pos0+S-1, appending
+ * K/V to the caches.  S == 1 is the decode step (swap-AB GEMMs + single-query attention).
+ * After the call `hidden` holds the output of the LAST layer (pre final norm) and, if final_out is
+ * not NULL, final_out holds final RMSNorm(hidden).  all_hidden (optional) receives the input of every
+ * layer ([layers][B*S][H]) for output_hidden_states=True. */
+typedef struct ullava_llama_args {
+  const void* const* weights; int32_t n_weights;   /* per layer: ln1, wqkv, wo, ln2, wgu(packed), wdown; then final norm */
+  void* hidden;            /* [B*S, H] 16-bit, in/out */
+  void* final_out;         /* [B*S, H] 16-bit or NULL */
+  void* all_hidden;        /* [layers, B*S, H] 16-bit or NULL */
+  void* k_cache; void* v_cache;  /* [layers, B, heads, max_seq, hd] 16-bit */
+  void* scratch; size_t scratch_bytes;
+  int32_t batch, seq, pos0, max_seq;
+  int32_t layers, hidden_size, heads, head_dim, ffn;
+  float eps;
+  const float* rope_cos; const float* rope_sin; /* fp32 [max_seq, head_dim/2] */
+  int32_t dtype;
+} ullava_llama_args;
+ULLAVA_API int ullava_llama_forward(ullava_ctx* ctx, const ullava_llama_args* args, void* stream);
+ULLAVA_API size_t ullava_llama_scratch_bytes(int32_t rows, int32_t hidden_size, int32_t ffn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULLAVA_SM100_H_ */

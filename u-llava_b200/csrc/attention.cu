@@ -1,0 +1,473 @@
+// Attention kernels of the u-LLaVA hot path.
+//
+//   attention_run        : flash-style softmax(Q K^T * scale) V, fp32 online softmax, non-causal
+//                          (CLIP ViT, hd 64, S = 577; hf:models/clip/modeling_clip.py:282-336) and
+//                          causal (LLaMA prefill, hd 128, S = 608; hf:models/llama/modeling_llama.py:199-291).
+//   attention_decode_run : single-query attention against the KV cache (LLaMA decode step).
+//
+// Attention is ~1-3 % of the path's FLOPs, so round 1 keeps it on the
+// warp-level tensor-core path (mma.sync.m16n8k16 + ldmatrix + cp.async double buffering): K/V tiles
+// are read from HBM/L2 exactly once per 64-row query block, nothing of size S x S is materialised.
+// The tcgen05/TMEM version (S in TMEM, P fed back as the A operand) is the planned follow-up.
+#include "common.cuh"
+#include "ullava_internal.h"
+
+namespace ullava {
+
+// ---- small PTX helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ---- flash forward ------------------------------------------------------------------------------
+static constexpr int FA_BM = 64;   // query rows per CTA (4 warps x 16)
+static constexpr int FA_BN = 64;   // keys per tile
+static constexpr int FA_THREADS = 128;
+
+struct FlashParams {
+  const void* q; int64_t q_bs, q_rs, q_hs;
+  const void* k; int64_t k_bs, k_rs, k_hs;
+  const void* v; int64_t v_bs, v_rs, v_hs;
+  void* o; int64_t o_bs, o_rs, o_hs;
+  int seq_q, seq_k, causal, q_pos0;
+  float scale_log2;  // scale * log2(e)
+};
+
+// shared tile [rows][HD] 16-bit with a 16-byte-chunk XOR swizzle (conflict-free ldmatrix)
+template <int HD>
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
+  constexpr int CPR = HD / 8;                    // 16-byte chunks per row
+  constexpr int MASK = CPR >= 8 ? 7 : CPR - 1;   // XOR only within the row's own chunks
+  return static_cast<uint32_t>(row * (HD * 2) + (((chunk & ~MASK) | ((chunk ^ row) & MASK)) << 4));
+}
+
+template <typename T, int HD>
+__device__ __forceinline__ void load_tile(uint32_t smem_base, const T* g, int64_t row_stride, int row0, int nrows_valid,
+                                          int tid) {
+  constexpr int CPR = HD / 8;  // 16-byte chunks per row
+  for (int i = tid; i < FA_BN * CPR; i += FA_THREADS) {
+    const int r = i / CPR, c = i - r * CPR;
+    const bool ok = (row0 + r) < nrows_valid;
+    const T* src = g + static_cast<int64_t>(ok ? (row0 + r) : 0) * row_stride + c * 8;
+    cp_async16(smem_base + sw_off<HD>(r, c), src, ok);
+  }
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(FA_THREADS)
+flash_fwd_kernel(const FlashParams p) {
+  extern __shared__ __align__(128) uint8_t fa_smem[];
+  constexpr int TILE_BYTES = FA_BN * HD * 2;
+  const uint32_t sQ = smem_u32(fa_smem);
+  const uint32_t sK = sQ + TILE_BYTES;            // 2 buffers
+  const uint32_t sV = sK + 2 * TILE_BYTES;        // 2 buffers
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * FA_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const T* qg = static_cast<const T*>(p.q) + b * p.q_bs + h * p.q_hs;
+  const T* kg = static_cast<const T*>(p.k) + b * p.k_bs + h * p.k_hs;
+  const T* vg = static_cast<const T*>(p.v) + b * p.v_bs + h * p.v_hs;
+  T* og = static_cast<T*>(p.o) + b * p.o_bs + h * p.o_hs;
+
+  int k_end = p.seq_k;
+  if (p.causal) k_end = min(k_end, p.q_pos0 + m0 + FA_BM);
+  const int n_tiles = (k_end + FA_BN - 1) / FA_BN;
+
+  // prologue: Q tile + first K/V tile
+  load_tile<T, HD>(sQ, qg, p.q_rs, m0, p.seq_q, tid);
+  load_tile<T, HD>(sK, kg, p.k_rs, 0, p.seq_k, tid);
+  load_tile<T, HD>(sV, vg, p.v_rs, 0, p.seq_k, tid);
+  cp_async_commit();
+
+  constexpr int KS = HD / 16;  // k-steps of QK^T
+  uint32_t qf[KS][4];
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  const int g = lane >> 2, tq = lane & 3;
+  const int qrow0 = m0 + warp * 16 + g;  // this thread's rows: qrow0 and qrow0 + 8
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < n_tiles) {
+      load_tile<T, HD>(sK + (buf ^ 1) * TILE_BYTES, kg, p.k_rs, (t + 1) * FA_BN, p.seq_k, tid);
+      load_tile<T, HD>(sV + (buf ^ 1) * TILE_BYTES, vg, p.v_rs, (t + 1) * FA_BN, p.seq_k, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    if (t == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int chunk = ks * 2 + (lane >> 4);
+        ldsm_x4(sQ + sw_off<HD>(row, chunk), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+
+    // ---- S = Q K^T (16 x 64 per warp) ----
+    float s[FA_BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < FA_BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    const uint32_t kb = sK + buf * TILE_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int nb = 0; nb < FA_BN / 16; ++nb) {
+        uint32_t r0, r1, r2, r3;
+        const int row = nb * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int chunk = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(kb + sw_off<HD>(row, chunk), r0, r1, r2, r3);
+        mma16816<T>(s[nb * 2], qf[ks], r0, r1);
+        mma16816<T>(s[nb * 2 + 1], qf[ks], r2, r3);
+      }
+    }
+
+    // ---- mask + online softmax ----
+    const int key0 = t * FA_BN;
+    const bool need_mask = (key0 + FA_BN > p.seq_k) || (p.causal && (key0 + FA_BN - 1 > p.q_pos0 + m0 + warp * 16));
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nb = 0; nb < FA_BN / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float val = s[nb][e] * p.scale_log2;
+        if (need_mask) {
+          const int key = key0 + nb * 8 + tq * 2 + (e & 1);
+          const int qr = qrow0 + (e >> 1) * 8;
+          if (key >= p.seq_k || (p.causal && key > p.q_pos0 + qr)) val = -INFINITY;
+        }
+        s[nb][e] = val;
+        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_run[r], mx[r]);
+      // fully masked so far: keep everything at zero without producing NaN from (-inf) - (-inf)
+      const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+      corr[r] = exp2f(m_run[r] - msafe);
+      m_run[r] = mnew[r];
+      mnew[r] = msafe;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[FA_BN / 16][4];
+#pragma unroll
+    for (int nb = 0; nb < FA_BN / 8; ++nb) {
+      const float p0 = exp2f(s[nb][0] - mnew[0]);
+      const float p1 = exp2f(s[nb][1] - mnew[0]);
+      const float p2 = exp2f(s[nb][2] - mnew[1]);
+      const float p3 = exp2f(s[nb][3] - mnew[1]);
+      // round P to the 16-bit dtype first so that the row sum matches what the PV MMA consumes
+      const uint32_t lo = pack2<T>(p0, p1), hi = pack2<T>(p2, p3);
+      const float2 flo = unpack2<T>(lo), fhi = unpack2<T>(hi);
+      rs[0] += flo.x + flo.y;
+      rs[1] += fhi.x + fhi.y;
+      pf[nb >> 1][(nb & 1) * 2 + 0] = lo;
+      pf[nb >> 1][(nb & 1) * 2 + 1] = hi;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o_acc[i][0] *= corr[0];
+      o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1];
+      o_acc[i][3] *= corr[1];
+    }
+
+    // ---- O += P V ----
+    const uint32_t vb = sV + buf * TILE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < FA_BN / 16; ++kk) {
+#pragma unroll
+      for (int db = 0; db < HD / 16; ++db) {
+        uint32_t r0, r1, r2, r3;
+        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int chunk = db * 2 + (lane >> 4);
+        ldsm_x4_t(vb + sw_off<HD>(row, chunk), r0, r1, r2, r3);
+        mma16816<T>(o_acc[db * 2], pf[kk], r0, r1);
+        mma16816<T>(o_acc[db * 2 + 1], pf[kk], r2, r3);
+      }
+    }
+    __syncthreads();  // everyone done with buffer `buf` before it is refilled (iteration t+1 prefetches into it)
+  }
+
+  // ---- finalise: O / l ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    const int col = i * 8 + tq * 2;
+    if (qrow0 < p.seq_q)
+      *reinterpret_cast<uint32_t*>(og + static_cast<int64_t>(qrow0) * p.o_rs + col) =
+          pack2<T>(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+    if (qrow0 + 8 < p.seq_q)
+      *reinterpret_cast<uint32_t*>(og + static_cast<int64_t>(qrow0 + 8) * p.o_rs + col) =
+          pack2<T>(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+  }
+}
+
+template <typename T, int HD>
+static int flash_launch(const FlashParams& p, int batch, int heads, cudaStream_t stream) {
+  constexpr int smem = 5 * FA_BN * HD * 2;
+  auto kern = flash_fwd_kernel<T, HD>;
+  static bool configured = false;
+  if (!configured) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.seq_q + FA_BM - 1) / FA_BM, heads, batch);
+  kern<<<grid, FA_THREADS, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "flash_fwd launch");
+}
+
+int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream) {
+  ULLAVA_REQUIRE(a.q && a.k && a.v && a.o, "attention: null pointer");
+  ULLAVA_REQUIRE(a.batch >= 0 && a.heads > 0 && a.seq_q >= 0 && a.seq_k > 0, "attention: bad shape");
+  const int64_t strides[] = {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs};
+  for (int64_t s : strides) ULLAVA_REQUIRE(s % 8 == 0, "attention: strides must be multiples of 8 elements");
+  ULLAVA_REQUIRE(((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) |
+                   reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.o)) & 15) == 0,
+                 "attention: pointers must be 16-byte aligned");
+  if (a.batch == 0 || a.seq_q == 0) return OK;
+  FlashParams p;
+  p.q = a.q; p.q_bs = a.q_bs; p.q_rs = a.q_rs; p.q_hs = a.q_hs;
+  p.k = a.k; p.k_bs = a.k_bs; p.k_rs = a.k_rs; p.k_hs = a.k_hs;
+  p.v = a.v; p.v_bs = a.v_bs; p.v_rs = a.v_rs; p.v_hs = a.v_hs;
+  p.o = a.o; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
+  p.seq_q = a.seq_q; p.seq_k = a.seq_k; p.causal = a.causal; p.q_pos0 = a.q_pos0;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  int st;
+  if (a.dtype == DT_BF16) {
+    if (a.head_dim == 64) st = flash_launch<__nv_bfloat16, 64>(p, a.batch, a.heads, stream);
+    else if (a.head_dim == 128) st = flash_launch<__nv_bfloat16, 128>(p, a.batch, a.heads, stream);
+    else if (a.head_dim == 32) st = flash_launch<__nv_bfloat16, 32>(p, a.batch, a.heads, stream);
+    else if (a.head_dim == 16) st = flash_launch<__nv_bfloat16, 16>(p, a.batch, a.heads, stream);
+    else { set_last_error("attention: head_dim %d not compiled (16/32/64/128)", a.head_dim); return ERR_UNSUPPORTED; }
+  } else if (a.dtype == DT_F16) {
+    if (a.head_dim == 64) st = flash_launch<__half, 64>(p, a.batch, a.heads, stream);
+    else if (a.head_dim == 128) st = flash_launch<__half, 128>(p, a.batch, a.heads, stream);
+    else if (a.head_dim == 32) st = flash_launch<__half, 32>(p, a.batch, a.heads, stream);
+    else if (a.head_dim == 16) st = flash_launch<__half, 16>(p, a.batch, a.heads, stream);
+    else { set_last_error("attention: head_dim %d not compiled (16/32/64/128)", a.head_dim); return ERR_UNSUPPORTED; }
+  } else {
+    set_last_error("attention: unsupported dtype %d", a.dtype);
+    return ERR_UNSUPPORTED;
+  }
+  if (st == OK) ctx->launches++;
+  return st;
+}
+
+// ---- decode attention --------------------------------------------------------------------------
+// One CTA per (head, sample).  Phase 1: scores (LPK lanes per key, 16 elements per lane) into shared
+// memory; phase 2: block softmax; phase 3: P V with 16-byte V loads, 128/(HD/8) key groups reduced
+// through shared memory.  HBM-bound: K and V are each read exactly once.
+static constexpr int DEC_THREADS = 128;
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(DEC_THREADS)
+attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ kc, const T* __restrict__ vc,
+                   int64_t cache_bs, int64_t cache_hs, T* __restrict__ o, int64_t o_bs, int ctx_len,
+                   float scale_log2) {
+  extern __shared__ float dec_smem[];   // [ctx_len] scores, then [groups][HD] partial outputs
+  __shared__ float red[DEC_THREADS / 32];
+  __shared__ float bcast[2];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* qp = q + b * q_bs + h * HD;
+  const T* kp = kc + b * cache_bs + h * cache_hs;
+  const T* vp = vc + b * cache_bs + h * cache_hs;
+
+  constexpr int LPK = HD / 16;             // lanes per key
+  constexpr int KPW = 32 / LPK;            // keys per warp iteration
+  const int sub = lane % LPK, kin = lane / LPK;
+  float qf[16];
+  {
+    const uint4 a = *reinterpret_cast<const uint4*>(qp + sub * 16);
+    const uint4 c = *reinterpret_cast<const uint4*>(qp + sub * 16 + 8);
+    const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 f = unpack2<T>(u[e]);
+      qf[2 * e] = f.x;
+      qf[2 * e + 1] = f.y;
+    }
+  }
+  float lmax = -INFINITY;
+  for (int j0 = warp * KPW; j0 < ctx_len; j0 += (DEC_THREADS / 32) * KPW) {
+    const int j = j0 + kin;
+    float acc = 0.f;
+    if (j < ctx_len) {
+      const T* kr = kp + static_cast<int64_t>(j) * HD + sub * 16;
+      const uint4 a = *reinterpret_cast<const uint4*>(kr);
+      const uint4 c = *reinterpret_cast<const uint4*>(kr + 8);
+      const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 f = unpack2<T>(u[e]);
+        acc += f.x * qf[2 * e] + f.y * qf[2 * e + 1];
+      }
+    }
+#pragma unroll
+    for (int off = LPK / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    acc *= scale_log2;
+    if (j < ctx_len) {
+      if (sub == 0) dec_smem[j] = acc;
+      lmax = fmaxf(lmax, acc);
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+    for (int i = 1; i < DEC_THREADS / 32; ++i) m = fmaxf(m, red[i]);
+    bcast[0] = m;
+  }
+  __syncthreads();
+  const float m = bcast[0];
+  float lsum = 0.f;
+  for (int j = tid; j < ctx_len; j += DEC_THREADS) {
+    // P rounded to the 16-bit dtype like the eager reference (softmax in fp32, cast, then P V)
+    const float pj = exp2f(dec_smem[j] - m);
+    lsum += pj;
+    dec_smem[j] = pj;
+  }
+  lsum = warp_sum(lsum);
+  __syncthreads();
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < DEC_THREADS / 32; ++i) s += red[i];
+    bcast[1] = 1.f / s;
+  }
+  __syncthreads();
+  const float inv = bcast[1];
+
+  constexpr int TPR = HD / 8;              // threads per V row
+  constexpr int GROUPS = DEC_THREADS / TPR;
+  const int grp = tid / TPR, dv = (tid % TPR) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = grp; j < ctx_len; j += GROUPS) {
+    const float pj = T16<T>::to_f(T16<T>::from_f(dec_smem[j] * inv));
+    const uint4 a = *reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(j) * HD + dv);
+    const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack2<T>(u[e]);
+      acc[2 * e] += pj * f.x;
+      acc[2 * e + 1] += pj * f.y;
+    }
+  }
+  __syncthreads();  // scores no longer needed: reuse shared memory for the cross-group reduction
+  float* part = dec_smem;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[grp * HD + dv + e] = acc[e];
+  __syncthreads();
+  for (int d = tid; d < HD; d += DEC_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int gI = 0; gI < GROUPS; ++gI) s += part[gI * HD + d];
+    o[b * o_bs + h * HD + d] = T16<T>::from_f(s);
+  }
+}
+
+template <typename T, int HD>
+static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
+                         int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
+                         cudaStream_t stream) {
+  constexpr int GROUPS = DEC_THREADS / (HD / 8);
+  size_t smem = sizeof(float) * static_cast<size_t>(ctx_len > GROUPS * HD ? ctx_len : GROUPS * HD);
+  auto kern = attn_decode_kernel<T, HD>;
+  if (smem > 48 * 1024) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  dim3 grid(heads, batch);
+  kern<<<grid, DEC_THREADS, smem, stream>>>(static_cast<const T*>(q), q_bs, static_cast<const T*>(kc),
+                                            static_cast<const T*>(vc), cache_bs, cache_hs, static_cast<T*>(o), o_bs,
+                                            ctx_len, scale * 1.4426950408889634f);
+  return check_cuda(cudaGetLastError(), "attn_decode launch");
+}
+
+int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
+                         int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
+                         float scale, int dtype, cudaStream_t stream) {
+  ULLAVA_REQUIRE(q && kc && vc && o, "attention_decode: null pointer");
+  ULLAVA_REQUIRE(ctx_len > 0 && ctx_len <= 16384, "attention_decode: ctx_len %d out of range", ctx_len);
+  ULLAVA_REQUIRE(q_bs % 8 == 0 && cache_bs % 8 == 0 && cache_hs % 8 == 0, "attention_decode: bad strides");
+  if (batch == 0) return OK;
+  int st;
+#define ULLAVA_DEC(TT, HDIM) \
+  st = decode_launch<TT, HDIM>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream)
+  if (dtype == DT_BF16) {
+    if (head_dim == 128) ULLAVA_DEC(__nv_bfloat16, 128);
+    else if (head_dim == 64) ULLAVA_DEC(__nv_bfloat16, 64);
+    else if (head_dim == 32) ULLAVA_DEC(__nv_bfloat16, 32);
+    else if (head_dim == 16) ULLAVA_DEC(__nv_bfloat16, 16);
+    else { set_last_error("attention_decode: head_dim %d not compiled", head_dim); return ERR_UNSUPPORTED; }
+  } else if (dtype == DT_F16) {
+    if (head_dim == 128) ULLAVA_DEC(__half, 128);
+    else if (head_dim == 64) ULLAVA_DEC(__half, 64);
+    else if (head_dim == 32) ULLAVA_DEC(__half, 32);
+    else if (head_dim == 16) ULLAVA_DEC(__half, 16);
+    else { set_last_error("attention_decode: head_dim %d not compiled", head_dim); return ERR_UNSUPPORTED; }
+  } else {
+    set_last_error("attention_decode: unsupported dtype");
+    return ERR_UNSUPPORTED;
+  }
+#undef ULLAVA_DEC
+  if (st == OK) ctx->launches++;
+  return st;
+}
+
+}  // namespace ullava

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libullava_sm100.so in-tree (next to this script) for sm_100a only.
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+SRCS="runtime.cu gemm_sm100.cu norm.cu attention.cu elementwise.cu sam_decoder.cu models.cu capi.cu"
+mkdir -p build
+pids=()
+for f in $SRCS; do
+  o=build/${f%.cu}.o
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ullava_internal.h -nt "$o" ] || [ ../../include/ullava_sm100.h -nt "$o" ]; then
+    $NVCC $FLAGS -c "$f" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+OBJS=$(for f in $SRCS; do echo build/${f%.cu}.o; done)
+$NVCC -shared -o libullava_sm100.so $OBJS -Xcompiler -fPIC -cudart static
+echo "built $(pwd)/libullava_sm100.so"

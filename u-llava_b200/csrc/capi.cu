@@ -1,0 +1,124 @@
+// extern "C" surface of libullava_sm100.so (declared in include/ullava_sm100.h).
+// Thin argument checks + dispatch; no exception crosses this boundary.
+#include "common.cuh"
+#include "ullava_internal.h"
+
+using namespace ullava;
+
+#define CTX_CHECK(name)                              \
+  if (!ctx) {                                        \
+    set_last_error(name ": ctx is NULL");            \
+    return ERR_BAD_ARG;                              \
+  }
+
+extern "C" {
+
+int ullava_layernorm(ullava_ctx* ctx, const void* x, int64_t ldx, const void* weight, const void* bias, void* y,
+                     int64_t ldy, int32_t rows, int32_t cols, float eps, int32_t act, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_layernorm");
+  return layernorm_run(ctx, x, ldx, weight, bias, y, ldy, rows, cols, eps, act, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_rmsnorm(ullava_ctx* ctx, const void* x, int64_t ldx, const void* weight, void* y, int64_t ldy, int32_t rows,
+                   int32_t cols, float eps, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_rmsnorm");
+  return rmsnorm_run(ctx, x, ldx, weight, y, ldy, rows, cols, eps, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_attention(ullava_ctx* ctx, const ullava_attn_args* args, void* stream) {
+  CTX_CHECK("ullava_attention");
+  if (!args) { set_last_error("ullava_attention: args is NULL"); return ERR_BAD_ARG; }
+  return attention_run(ctx, *args, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q_bs, const void* k_cache, const void* v_cache,
+                            int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
+                            int32_t head_dim, int32_t ctx_len, float scale, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_attention_decode");
+  return attention_decode_run(ctx, q, q_bs, k_cache, v_cache, cache_bs, cache_hs, o, o_bs, batch, heads, head_dim,
+                              ctx_len, scale, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_rope_kvcache(ullava_ctx* ctx, void* qkv, int64_t ld_qkv, void* k_cache, void* v_cache, int64_t cache_bs,
+                        int64_t cache_hs, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim, int32_t pos0,
+                        const float* cos_table, const float* sin_table, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_rope_kvcache");
+  return rope_kvcache_run(ctx, qkv, ld_qkv, k_cache, v_cache, cache_bs, cache_hs, batch, seq, heads, head_dim, pos0,
+                          cos_table, sin_table, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_vit_im2col(ullava_ctx* ctx, const void* pixels, void* out, int32_t batch, int32_t img, int32_t patch,
+                      int32_t k_pad, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_vit_im2col");
+  return vit_im2col_run(ctx, pixels, out, batch, img, patch, k_pad, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_vit_assemble(ullava_ctx* ctx, const void* patch_embeds, const void* cls, const void* pos, void* out,
+                        int32_t batch, int32_t n_patches, int32_t dim, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_vit_assemble");
+  return vit_assemble_run(ctx, patch_embeds, cls, pos, out, batch, n_patches, dim, dtype,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int ullava_embed_gather(ullava_ctx* ctx, const int64_t* ids, const void* table, void* out, int32_t rows, int32_t dim,
+                        int32_t vocab, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_embed_gather");
+  return embed_gather_run(ctx, ids, table, out, rows, dim, vocab, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_splice_rows(ullava_ctx* ctx, void* embeds, const void* feats, const int32_t* start, int32_t batch,
+                       int32_t seq, int32_t n_patch, int32_t dim, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_splice_rows");
+  return splice_rows_run(ctx, embeds, feats, start, batch, seq, n_patch, dim, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_copy_rows(ullava_ctx* ctx, const void* src, int64_t src_bs, int64_t src_rs, void* dst, int64_t dst_bs,
+                     int64_t dst_rs, int32_t batch, int32_t rows, int32_t cols, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_copy_rows");
+  return copy_rows_run(ctx, src, src_bs, src_rs, dst, dst_bs, dst_rs, batch, rows, cols, dtype,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int ullava_argmax(ullava_ctx* ctx, const float* logits, int64_t ld, int64_t* out, int32_t rows, int32_t cols,
+                  void* stream) {
+  CTX_CHECK("ullava_argmax");
+  return argmax_run(ctx, logits, ld, out, rows, cols, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_sam_mask_decoder(ullava_ctx* ctx, const ullava_sam_decoder_args* args, void* stream) {
+  CTX_CHECK("ullava_sam_mask_decoder");
+  if (!args) { set_last_error("ullava_sam_mask_decoder: args is NULL"); return ERR_BAD_ARG; }
+  return sam_mask_decoder_run(ctx, *args, static_cast<cudaStream_t>(stream));
+}
+
+size_t ullava_sam_mask_decoder_scratch_bytes(int32_t n_prompts) { return sam_mask_decoder_scratch(n_prompts); }
+
+int ullava_sam_postprocess(ullava_ctx* ctx, const void* masks, int64_t mask_stride, float* out, uint32_t* packed_bits,
+                           int32_t n, int32_t low_res, int32_t img_size, int32_t in_h, int32_t in_w, int32_t out_h,
+                           int32_t out_w, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_sam_postprocess");
+  return sam_postprocess_run(ctx, masks, mask_stride, out, packed_bits, n, low_res, img_size, in_h, in_w, out_h, out_w,
+                             dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_vit_forward(ullava_ctx* ctx, const ullava_vit_args* args, void* stream) {
+  CTX_CHECK("ullava_vit_forward");
+  if (!args) { set_last_error("ullava_vit_forward: args is NULL"); return ERR_BAD_ARG; }
+  return vit_forward_run(ctx, *args, static_cast<cudaStream_t>(stream));
+}
+
+size_t ullava_vit_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32_t hidden, int32_t ffn, int32_t k_pad) {
+  return vit_scratch(batch, img, patch, hidden, ffn, k_pad);
+}
+
+int ullava_llama_forward(ullava_ctx* ctx, const ullava_llama_args* args, void* stream) {
+  CTX_CHECK("ullava_llama_forward");
+  if (!args) { set_last_error("ullava_llama_forward: args is NULL"); return ERR_BAD_ARG; }
+  return llama_forward_run(ctx, *args, static_cast<cudaStream_t>(stream));
+}
+
+size_t ullava_llama_scratch_bytes(int32_t rows, int32_t hidden_size, int32_t ffn) {
+  return llama_scratch(rows, hidden_size, ffn);
+}
+
+}  // extern "C"

@@ -1,0 +1,622 @@
+// tcgen05 GEMM for the u-LLaVA hot path:  D[M,N] = epi(A[M,K] * B[N,K]^T)
+//
+// Replaces every nn.Linear on the path (reference call sites: CLIP q/k/v/out/fc1/fc2
+// hf:models/clip/modeling_clip.py:282-351, LLaMA q/k/v/o/gate/up/down
+// hf:models/llama/modeling_llama.py:171-291, projector models/ullava_core.py:117-129,228,
+// lm_head models/ullava_core.py:325, seg/det projectors models/ullava.py:83-132).
+//
+// Design (B200, sm_100a):
+//   * persistent CTAs (one per SM), static tile scheduler with M-grouped rasterisation so
+//     that the CTAs of one wave share A/B tiles through the 126 MB L2;
+//   * warp-specialised: warp0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, K-major
+//     64-element slabs), warp1 = single-thread tcgen05.mma issuer, warp2 = TMEM allocator,
+//     warps4-7 = epilogue (tcgen05.ld -> registers -> fused bias/activation/residual -> global);
+//   * 128 x BN fp32 accumulator lives in TMEM, double buffered (2*BN columns) so the epilogue
+//     of tile i overlaps the MMAs of tile i+1;
+//   * STAGES-deep shared-memory ring guarded by full/empty mbarriers; tcgen05.commit releases a
+//     slot when the MMAs that read it have retired;
+//   * small-M (decode) products run "swap-AB": the weight matrix is the 128-row operand and the
+//     (padded) batch is the UMMA N (16/32), with split-K so that >=148 CTAs stream weights from
+//     HBM; partials go to an fp32 workspace and splitk_reduce_kernel applies the epilogue.
+#include "common.cuh"
+#include "ullava_internal.h"
+
+namespace ullava {
+
+static constexpr int BM = 128;       // UMMA M (rows of A per tile)
+static constexpr int BK = 64;        // 64 x 16-bit = 128 B = one SWIZZLE_128B row
+static constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
+static constexpr int GROUP_M = 8;    // rasterisation group
+static constexpr int kGemmThreads = 256;
+static constexpr int kEpiWarp0 = 4;  // first epilogue warp
+
+struct GemmKernelParams {
+  void* D;
+  int64_t ldd;
+  const void* bias;
+  const void* residual;
+  int64_t ldr;
+  int M, N, K;
+  int epilogue;
+  int out_f32;
+  int num_m, num_n;   // tile counts
+  int kb_total;       // ceil(K / 64)
+  int kb_per_split;   // k-blocks handled by one split
+  int splits;         // >1: D is an fp32 workspace [splits][M][N], epilogue deferred
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& split, int& m_blk, int& n_blk) {
+  const int per_split = num_m * num_n;
+  split = t / per_split;
+  int r = t - split * per_split;
+  const int group = GROUP_M * num_n;
+  const int g = r / group;
+  const int first_m = g * GROUP_M;
+  const int gm = min(num_m - first_m, GROUP_M);
+  r -= g * group;
+  m_blk = first_m + r % gm;
+  n_blk = r / gm;
+}
+
+__device__ __forceinline__ float apply_act(float v, int epi) {
+  switch (epi) {
+    case EPI_RELU: return fmaxf(v, 0.f);
+    case EPI_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case EPI_QUICK_GELU: return v / (1.f + __expf(-1.702f * v));
+    default: return v;
+  }
+}
+
+template <typename T, int CH>
+__device__ __forceinline__ void epilogue_store(float (&v)[CH], const GemmKernelParams& p, const T* bias, const T* resid,
+                                               bool split_mode, int split, int row, int n0) {
+
+        if (split_mode) {
+          float* out = reinterpret_cast<float*>(p.D) + (static_cast<int64_t>(split) * p.M + row) * p.N + n0;
+          if (n0 + CH <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < CH; ++i)
+              if (n0 + i < p.N) out[i] = v[i];
+          }
+          return;
+        }
+
+        const bool full_chunk = (n0 + CH <= p.N);
+        if (bias != nullptr) {
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              uint4 b = *reinterpret_cast<const uint4*>(bias + n0 + i);
+              float2 f;
+              f = unpack2<T>(b.x); v[i] += f.x; v[i + 1] += f.y;
+              f = unpack2<T>(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+              f = unpack2<T>(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+              f = unpack2<T>(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (n0 + i < p.N) v[i] += T16<T>::to_f(bias[n0 + i]);
+          }
+        }
+
+        if (p.epilogue == EPI_SILU_MUL) {
+          // weight rows are packed so that every 32-column chunk holds 16 gate columns followed by
+          // the 16 matching up columns; output has N/2 columns.
+          if constexpr (CH == 32) {
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float g = v[i];
+              o[i] = (g / (1.f + __expf(-g))) * v[16 + i];
+            }
+            const int on0 = n0 >> 1;
+            if (p.out_f32) {
+              float* out = reinterpret_cast<float*>(p.D) + static_cast<int64_t>(row) * p.ldd + on0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) out[i] = o[i];
+            } else {
+              T* out = reinterpret_cast<T*>(p.D) + static_cast<int64_t>(row) * p.ldd + on0;
+              if (resid != nullptr) {
+                const T* rr = resid + static_cast<int64_t>(row) * p.ldr + on0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] += T16<T>::to_f(rr[i]);
+              }
+              if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                  uint4 w;
+                  w.x = pack2<T>(o[i], o[i + 1]);
+                  w.y = pack2<T>(o[i + 2], o[i + 3]);
+                  w.z = pack2<T>(o[i + 4], o[i + 5]);
+                  w.w = pack2<T>(o[i + 6], o[i + 7]);
+                  *reinterpret_cast<uint4*>(out + i) = w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) out[i] = T16<T>::from_f(o[i]);
+              }
+            }
+          }
+          return;
+        }
+
+        if (p.epilogue != EPI_NONE) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = apply_act(v[i], p.epilogue);
+        }
+
+        if (resid != nullptr) {
+          const T* rr = resid + static_cast<int64_t>(row) * p.ldr + n0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              uint4 b = *reinterpret_cast<const uint4*>(rr + i);
+              float2 f;
+              f = unpack2<T>(b.x); v[i] += f.x; v[i + 1] += f.y;
+              f = unpack2<T>(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+              f = unpack2<T>(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+              f = unpack2<T>(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (n0 + i < p.N) v[i] += T16<T>::to_f(rr[i]);
+          }
+        }
+
+        if (p.out_f32) {
+          float* out = reinterpret_cast<float*>(p.D) + static_cast<int64_t>(row) * p.ldd + n0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (n0 + i < p.N) out[i] = v[i];
+          }
+        } else {
+          T* out = reinterpret_cast<T*>(p.D) + static_cast<int64_t>(row) * p.ldd + n0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              uint4 w;
+              w.x = pack2<T>(v[i], v[i + 1]);
+              w.y = pack2<T>(v[i + 2], v[i + 3]);
+              w.z = pack2<T>(v[i + 4], v[i + 5]);
+              w.w = pack2<T>(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(out + i) = w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (n0 + i < p.N) out[i] = T16<T>::from_f(v[i]);
+          }
+        }
+      }
+
+template <typename T, int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKernelParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_f16(T16<T>::kUmmaFormat, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m * p.num_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4 * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_ptr, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int split, m_blk, n_blk;
+        tile_coords(t, p.num_m, p.num_n, split, m_blk, n_blk);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int split, m_blk, n_blk;
+        tile_coords(t, p.num_m, p.num_n, split, m_blk, n_blk);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t a_desc = make_kmajor_sw128_desc(sa);
+          const uint64_t b_desc = make_kmajor_sw128_desc(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_f16<1>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<1>(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit<1>(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* resid = reinterpret_cast<const T*>(p.residual);
+    const bool split_mode = p.splits > 1;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int split, m_blk, n_blk;
+      tile_coords(t, p.num_m, p.num_n, split, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
+#pragma unroll 1
+      for (int c = 0; c < BN / CH; ++c) {
+        float v[CH];
+        if constexpr (CH == 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x16(taddr + c * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        const int n0 = n_blk * BN + c * CH;
+        if (row_ok && n0 < p.N) epilogue_store<T, CH>(v, p, bias, resid, split_mode, split, row, n0);
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Split-K reduce + epilogue.  partial: fp32 [splits][R][C].
+//   transpose == 0: out[r][c]   (R = M rows, C = N cols)
+//   transpose == 1: out[c][r]   (swap-AB: R = weight rows (N_out), C = padded batch; out is [batch][N_out])
+// bias is indexed by the output column, residual has the output's layout.
+// One block handles a 32 (r) x 32 (c) patch.
+// -----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int R, int C, int c_valid, void* __restrict__ out,
+                     int64_t ldo, const T* __restrict__ bias, const T* __restrict__ resid, int64_t ldr, int epilogue,
+                     int out_f32, int transpose) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;  // 0..7
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int r = r0 + rr, c = c0 + tx;
+    float s = 0.f;
+    if (r < R && c < C) {
+      const float* ptr = partial + static_cast<int64_t>(r) * C + c;
+      for (int k = 0; k < splits; ++k) s += ptr[static_cast<int64_t>(k) * R * C];
+    }
+    tile[rr][tx] = s;
+  }
+  __syncthreads();
+  if (!transpose) {
+    // out[r][c]; threads along c
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int r = r0 + rr;
+      if (r >= R) continue;
+      if (epilogue == EPI_SILU_MUL) {
+        // chunk of 32 columns = 16 gate + 16 up -> 16 outputs
+        if (tx < 16) {
+          const int c = c0 + tx;
+          if (c < c_valid) {
+            const float g = tile[rr][tx], u = tile[rr][tx + 16];
+            float o = (g / (1.f + __expf(-g))) * u;
+            const int oc = (c0 >> 1) + tx;
+            if (resid) o += T16<T>::to_f(resid[static_cast<int64_t>(r) * ldr + oc]);
+            if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(r) * ldo + oc] = o;
+            else reinterpret_cast<T*>(out)[static_cast<int64_t>(r) * ldo + oc] = T16<T>::from_f(o);
+          }
+        }
+        continue;
+      }
+      const int c = c0 + tx;
+      if (c >= c_valid) continue;
+      float v = tile[rr][tx];
+      if (bias) v += T16<T>::to_f(bias[c]);
+      v = apply_act(v, epilogue);
+      if (resid) v += T16<T>::to_f(resid[static_cast<int64_t>(r) * ldr + c]);
+      if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(r) * ldo + c] = v;
+      else reinterpret_cast<T*>(out)[static_cast<int64_t>(r) * ldo + c] = T16<T>::from_f(v);
+    }
+  } else {
+    // out[c][r]; threads along r (the contiguous output dimension)
+    for (int cc = ty; cc < 32; cc += 8) {
+      const int c = c0 + cc;
+      if (c >= c_valid) continue;
+      if (epilogue == EPI_SILU_MUL) {
+        if (tx < 16) {
+          const int r = r0 + tx;  // gate row; up row = r + 16 (same 32-row chunk)
+          if (r < R) {
+            const float g = tile[tx][cc], u = tile[tx + 16][cc];
+            float o = (g / (1.f + __expf(-g))) * u;
+            const int orow = (r0 >> 1) + tx;
+            if (resid) o += T16<T>::to_f(resid[static_cast<int64_t>(c) * ldr + orow]);
+            if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(c) * ldo + orow] = o;
+            else reinterpret_cast<T*>(out)[static_cast<int64_t>(c) * ldo + orow] = T16<T>::from_f(o);
+          }
+        }
+        continue;
+      }
+      const int r = r0 + tx;
+      if (r >= R) continue;
+      float v = tile[tx][cc];
+      if (bias) v += T16<T>::to_f(bias[r]);
+      v = apply_act(v, epilogue);
+      if (resid) v += T16<T>::to_f(resid[static_cast<int64_t>(c) * ldr + r]);
+      if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(c) * ldo + r] = v;
+      else reinterpret_cast<T*>(out)[static_cast<int64_t>(c) * ldo + r] = T16<T>::from_f(v);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Host side
+// -----------------------------------------------------------------------------
+template <typename T, int BN, int STAGES>
+static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+                          cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  auto kern = gemm_tcgen05_kernel<T, BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, p);
+  return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
+}
+
+template <typename T>
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+                     cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_variant<T, 256, 4>(ta, tb, p, grid, stream);
+    case 128: return launch_variant<T, 128, 6>(ta, tb, p, grid, stream);
+    case 64: return launch_variant<T, 64, 8>(ta, tb, p, grid, stream);
+    case 32: return launch_variant<T, 32, 8>(ta, tb, p, grid, stream);
+    case 16: return launch_variant<T, 16, 8>(ta, tb, p, grid, stream);
+    default: set_last_error("gemm: unsupported BN %d", bn); return ERR_UNSUPPORTED;
+  }
+}
+
+static int pick_bn_large(int N) {
+  if (N > 128) return 256;
+  if (N > 64) return 128;
+  if (N > 32) return 64;
+  if (N > 16) return 32;
+  return 16;
+}
+
+int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
+  ULLAVA_REQUIRE(a.A && a.B && a.D, "gemm: null operand");
+  ULLAVA_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  ULLAVA_REQUIRE(a.dtype == DT_BF16 || a.dtype == DT_F16, "gemm: dtype must be bf16/f16");
+  ULLAVA_REQUIRE((a.lda % 8) == 0 && (a.ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16 B stride)");
+  ULLAVA_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+                 "gemm: A/B must be 16-byte aligned");
+  ULLAVA_REQUIRE(a.lda >= a.K && a.ldb >= a.K, "gemm: leading dimension smaller than K");
+  if (a.epilogue == EPI_SILU_MUL) ULLAVA_REQUIRE((a.N % 32) == 0, "gemm: SILU_MUL needs N %% 32 == 0");
+
+  const int kb_total = (a.K + BK - 1) / BK;
+  const int sms = ctx->sm_count;
+
+  // Small-M products: swap operands so the weight matrix feeds the 128-row side.
+  const bool swap = (a.M <= 32) && (a.N >= 128) && !a.no_swap;
+  GemmKernelParams p{};
+  p.kb_total = kb_total;
+  p.epilogue = a.epilogue;
+  p.out_f32 = a.out_f32;
+  p.bias = a.bias;
+  p.residual = a.residual;
+  p.ldr = a.ldr;
+  CUtensorMap ta, tb;
+
+  if (!swap) {
+    const int bn = a.force_bn ? a.force_bn : pick_bn_large(a.N);
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.num_m = (a.M + BM - 1) / BM;
+    p.num_n = (a.N + bn - 1) / bn;
+    int splits = a.force_splits > 0 ? a.force_splits : 1;
+    if (splits > kb_total) splits = kb_total;
+    p.kb_per_split = (kb_total + splits - 1) / splits;
+    splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = splits;
+    int st = encode_tmap_2d(&ta, a.A, 2, a.K, a.M, a.lda * 2, BK, BM, true);
+    if (st) return st;
+    st = encode_tmap_2d(&tb, a.B, 2, a.K, a.N, a.ldb * 2, BK, bn, true);
+    if (st) return st;
+    if (splits > 1) {
+      const size_t need = static_cast<size_t>(splits) * a.M * a.N * sizeof(float);
+      if (need > ctx->workspace_bytes) {
+        set_last_error("gemm: split-K workspace too small (%zu > %zu)", need, ctx->workspace_bytes);
+        return ERR_WORKSPACE;
+      }
+      p.D = ctx->workspace; p.ldd = a.N;
+    } else {
+      p.D = a.D; p.ldd = a.ldd;
+    }
+    const int tiles = p.num_m * p.num_n * splits;
+    const int grid = tiles < sms ? tiles : sms;
+    st = (a.dtype == DT_BF16) ? launch_bn<__nv_bfloat16>(bn, ta, tb, p, grid, stream)
+                              : launch_bn<__half>(bn, ta, tb, p, grid, stream);
+    if (st) return st;
+    if (splits > 1) {
+      dim3 g((a.M + 31) / 32, (a.N + 31) / 32);
+      if (a.dtype == DT_BF16)
+        splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(
+            reinterpret_cast<const float*>(ctx->workspace), splits, a.M, a.N, a.N, a.D, a.ldd,
+            reinterpret_cast<const __nv_bfloat16*>(a.bias), reinterpret_cast<const __nv_bfloat16*>(a.residual), a.ldr,
+            a.epilogue, a.out_f32, 0);
+      else
+        splitk_reduce_kernel<__half><<<g, 256, 0, stream>>>(
+            reinterpret_cast<const float*>(ctx->workspace), splits, a.M, a.N, a.N, a.D, a.ldd,
+            reinterpret_cast<const __half*>(a.bias), reinterpret_cast<const __half*>(a.residual), a.ldr, a.epilogue,
+            a.out_f32, 0);
+      ctx->launches += 2;
+      return check_cuda(cudaGetLastError(), "splitk_reduce launch");
+    }
+    ctx->launches += 1;
+    return OK;
+  }
+
+  // ---- swap-AB path: kernel computes P[N_out][Bpad] = W[N_out,K] * X[Bpad,K]^T ----
+  const int bn = a.M <= 16 ? 16 : 32;
+  p.M = a.N;   // weight rows
+  p.N = bn;    // padded batch (TMA zero-fills rows >= a.M of X)
+  p.K = a.K;
+  p.num_m = (a.N + BM - 1) / BM;
+  p.num_n = 1;
+  int splits;
+  if (a.force_splits > 0) {
+    splits = a.force_splits;
+  } else {
+    const int target = 2 * sms;
+    splits = (target + p.num_m - 1) / p.num_m;
+    const int max_splits = kb_total / 4 > 0 ? kb_total / 4 : 1;  // keep >= 4 k-blocks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > kb_total) splits = kb_total;
+  p.kb_per_split = (kb_total + splits - 1) / splits;
+  splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  // force the workspace path even with one split: the reduce kernel performs the transpose + epilogue
+  p.splits = splits;
+  const size_t need = static_cast<size_t>(splits) * a.N * bn * sizeof(float);
+  if (need > ctx->workspace_bytes) {
+    set_last_error("gemm(swap): workspace too small (%zu > %zu)", need, ctx->workspace_bytes);
+    return ERR_WORKSPACE;
+  }
+  p.D = ctx->workspace;
+  p.ldd = bn;
+  p.bias = nullptr; p.residual = nullptr; p.epilogue = EPI_NONE; p.out_f32 = 1;
+  int st = encode_tmap_2d(&ta, a.B, 2, a.K, a.N, a.ldb * 2, BK, BM, true);
+  if (st) return st;
+  st = encode_tmap_2d(&tb, a.A, 2, a.K, a.M, a.lda * 2, BK, bn, true);
+  if (st) return st;
+  const int tiles = p.num_m * splits;
+  const int grid = tiles < sms ? tiles : sms;
+  // with splits == 1 the kernel takes its plain fp32 store path, which has the same [N_out][bn] layout
+  st = (a.dtype == DT_BF16) ? launch_bn<__nv_bfloat16>(bn, ta, tb, p, grid, stream)
+                            : launch_bn<__half>(bn, ta, tb, p, grid, stream);
+  if (st) return st;
+  dim3 g((a.N + 31) / 32, (bn + 31) / 32);
+  if (a.dtype == DT_BF16)
+    splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(
+        reinterpret_cast<const float*>(ctx->workspace), splits, a.N, bn, a.M, a.D, a.ldd,
+        reinterpret_cast<const __nv_bfloat16*>(a.bias), reinterpret_cast<const __nv_bfloat16*>(a.residual), a.ldr,
+        a.epilogue, a.out_f32, 1);
+  else
+    splitk_reduce_kernel<__half><<<g, 256, 0, stream>>>(
+        reinterpret_cast<const float*>(ctx->workspace), splits, a.N, bn, a.M, a.D, a.ldd,
+        reinterpret_cast<const __half*>(a.bias), reinterpret_cast<const __half*>(a.residual), a.ldr, a.epilogue,
+        a.out_f32, 1);
+  ctx->launches += 2;
+  return check_cuda(cudaGetLastError(), "splitk_reduce(swap) launch");
+}
+
+}  // namespace ullava

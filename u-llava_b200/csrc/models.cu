@@ -1,0 +1,185 @@
+// Stage-level entry points: the layer loops of the CLIP ViT, the LLaMA decoder stack and the SAM
+// mask decoder run here in C++ (one ctypes call per stage, ~2 us per kernel launch instead of a
+// Python round trip per op).  Every kernel they enqueue is one of the hand-written sm_100a kernels
+// of this library; nothing here calls cuBLAS/cuDNN/torch.
+#include <algorithm>
+
+#include "common.cuh"
+#include "ullava_internal.h"
+
+namespace ullava {
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Arena {
+  uint8_t* base;
+  size_t cap, off = 0;
+  bool ok = true;
+  Arena(void* p, size_t bytes) : base(static_cast<uint8_t*>(p)), cap(bytes) {}
+  void* take(size_t bytes) {
+    const size_t o = align_up(off);
+    if (o + bytes > cap) { ok = false; return nullptr; }
+    off = o + bytes;
+    return base + o;
+  }
+};
+
+static int gemm(Context* ctx, cudaStream_t s, int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
+                int64_t ldd, int M, int N, int K, const void* bias = nullptr, int epi = EPI_NONE,
+                const void* resid = nullptr, int64_t ldr = 0, int out_f32 = 0) {
+  GemmArgs a{};
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.D = D; a.ldd = ldd;
+  a.bias = bias; a.residual = resid; a.ldr = ldr;
+  a.M = M; a.N = N; a.K = K; a.dtype = dtype; a.out_f32 = out_f32; a.epilogue = epi;
+  return gemm_run(ctx, a, s);
+}
+
+#define RUN(expr)              \
+  do {                         \
+    int _st = (expr);          \
+    if (_st != OK) return _st; \
+  } while (0)
+
+// =================================================================================================
+// CLIP ViT  (UllavaCoreForCausalLM.encode_image, models/ullava_core.py:146-158;
+//            CLIPVisionTransformer hf:models/clip/modeling_clip.py:138-218,282-385,647-690)
+// weights: 0 patch_w[hidden,k_pad] 1 cls[hidden] 2 pos[np+1,hidden] 3 pre_ln_w 4 pre_ln_b, then per layer
+//          ln1_w ln1_b wqkv[3h,h] bqkv[3h] wo[h,h] bo ln2_w ln2_b w1[ffn,h] b1 w2[h,ffn] b2   (12 per layer)
+// =================================================================================================
+size_t vit_scratch(int batch, int img, int patch, int hidden, int ffn, int k_pad) {
+  const size_t g = img / patch, np = g * g, rows = static_cast<size_t>(batch) * (np + 1);
+  size_t t = 0;
+  t += align_up(static_cast<size_t>(batch) * np * k_pad * 2);      // im2col
+  t += align_up(static_cast<size_t>(batch) * np * hidden * 2);     // patch embeds
+  t += 2 * align_up(rows * hidden * 2);                            // x, xn
+  t += align_up(rows * 3 * hidden * 2);                            // qkv
+  t += align_up(rows * hidden * 2);                                // attn
+  t += align_up(rows * ffn * 2);                                   // mlp act
+  return t + 4096;
+}
+
+int vit_forward_run(Context* ctx, const ullava_vit_args& a, cudaStream_t s) {
+  ULLAVA_REQUIRE(a.weights && a.pixels && a.out && a.scratch, "vit_forward: null pointer");
+  ULLAVA_REQUIRE(a.n_weights == 5 + 12 * a.layers_used, "vit_forward: expected %d weights, got %d",
+                 5 + 12 * a.layers_used, a.n_weights);
+  ULLAVA_REQUIRE(a.hidden % a.heads == 0, "vit_forward: hidden %% heads != 0");
+  const int g = a.img / a.patch, np = g * g, T = np + 1;
+  const int rows = a.batch * T, H = a.hidden, hd = H / a.heads;
+  if (a.batch == 0) return OK;
+  Arena ar(a.scratch, a.scratch_bytes);
+  void* col = ar.take(static_cast<size_t>(a.batch) * np * a.k_pad * 2);
+  void* pe = ar.take(static_cast<size_t>(a.batch) * np * H * 2);
+  void* x = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* xn = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* qkv = ar.take(static_cast<size_t>(rows) * 3 * H * 2);
+  void* att = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* act = ar.take(static_cast<size_t>(rows) * a.ffn * 2);
+  if (!ar.ok) { set_last_error("vit_forward: scratch too small (%zu bytes)", a.scratch_bytes); return ERR_WORKSPACE; }
+  const void* const* W = a.weights;
+  const int dt = a.dtype;
+
+  RUN(vit_im2col_run(ctx, a.pixels, col, a.batch, a.img, a.patch, a.k_pad, dt, s));
+  RUN(gemm(ctx, s, dt, col, a.k_pad, W[0], a.k_pad, pe, H, a.batch * np, H, a.k_pad));
+  RUN(vit_assemble_run(ctx, pe, W[1], W[2], x, a.batch, np, H, dt, s));
+  RUN(layernorm_run(ctx, x, H, W[3], W[4], x, H, rows, H, a.eps, EPI_NONE, dt, s));
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < a.layers_used; ++l) {
+    const void* const* L = W + 5 + 12 * l;
+    RUN(layernorm_run(ctx, x, H, L[0], L[1], xn, H, rows, H, a.eps, EPI_NONE, dt, s));
+    RUN(gemm(ctx, s, dt, xn, H, L[2], H, qkv, 3 * H, rows, 3 * H, H, L[3]));
+    AttnArgs at{};
+    const uint16_t* q16 = static_cast<const uint16_t*>(qkv);
+    at.q = q16; at.k = q16 + H; at.v = q16 + 2 * H; at.o = att;
+    at.q_bs = at.k_bs = at.v_bs = static_cast<int64_t>(T) * 3 * H;
+    at.q_rs = at.k_rs = at.v_rs = 3 * H;
+    at.q_hs = at.k_hs = at.v_hs = hd;
+    at.o_bs = static_cast<int64_t>(T) * H; at.o_rs = H; at.o_hs = hd;
+    at.batch = a.batch; at.heads = a.heads; at.seq_q = T; at.seq_k = T; at.head_dim = hd;
+    at.causal = 0; at.q_pos0 = 0; at.scale = scale; at.dtype = dt;
+    RUN(attention_run(ctx, at, s));
+    RUN(gemm(ctx, s, dt, att, H, L[4], H, x, H, rows, H, H, L[5], EPI_NONE, x, H));
+    RUN(layernorm_run(ctx, x, H, L[6], L[7], xn, H, rows, H, a.eps, EPI_NONE, dt, s));
+    RUN(gemm(ctx, s, dt, xn, H, L[8], H, act, a.ffn, rows, a.ffn, H, L[9], a.act));
+    RUN(gemm(ctx, s, dt, act, a.ffn, L[10], a.ffn, x, H, rows, H, a.ffn, L[11], EPI_NONE, x, H));
+  }
+  // drop CLS: out[b, p] = x[b, 1 + p]
+  RUN(copy_rows_run(ctx, static_cast<const uint16_t*>(x) + H, static_cast<int64_t>(T) * H, H, a.out,
+                    static_cast<int64_t>(np) * H, H, a.batch, np, H, dt, s));
+  return OK;
+}
+
+// =================================================================================================
+// LLaMA decoder stack (LlamaModel.forward hf:models/llama/modeling_llama.py:355-424; layer :292-333)
+// weights: per layer  ln1[H] wqkv[3H,H] wo[H,H] ln2[H] wgu[2F,H] (gate/up interleaved by 16) wdown[H,F]; then final norm[H]
+// =================================================================================================
+size_t llama_scratch(int rows, int hidden, int ffn) {
+  size_t t = 0;
+  t += align_up(static_cast<size_t>(rows) * hidden * 2);       // xn
+  t += align_up(static_cast<size_t>(rows) * 3 * hidden * 2);   // qkv
+  t += align_up(static_cast<size_t>(rows) * hidden * 2);       // attn
+  t += align_up(static_cast<size_t>(rows) * ffn * 2);          // act
+  return t + 4096;
+}
+
+int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s) {
+  ULLAVA_REQUIRE(a.weights && a.hidden && a.k_cache && a.v_cache && a.scratch && a.rope_cos && a.rope_sin,
+                 "llama_forward: null pointer");
+  ULLAVA_REQUIRE(a.n_weights == 6 * a.layers + 1, "llama_forward: expected %d weights, got %d", 6 * a.layers + 1,
+                 a.n_weights);
+  ULLAVA_REQUIRE(a.hidden_size == a.heads * a.head_dim, "llama_forward: hidden != heads*head_dim");
+  ULLAVA_REQUIRE(a.pos0 >= 0 && a.pos0 + a.seq <= a.max_seq, "llama_forward: positions %d..%d exceed the KV cache (%d)",
+                 a.pos0, a.pos0 + a.seq, a.max_seq);
+  ULLAVA_REQUIRE(a.ffn % 16 == 0, "llama_forward: ffn must be a multiple of 16");
+  const int rows = a.batch * a.seq, H = a.hidden_size, F = a.ffn, hd = a.head_dim;
+  if (rows == 0) return OK;
+  Arena ar(a.scratch, a.scratch_bytes);
+  void* xn = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* qkv = ar.take(static_cast<size_t>(rows) * 3 * H * 2);
+  void* att = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* act = ar.take(static_cast<size_t>(rows) * F * 2);
+  if (!ar.ok) { set_last_error("llama_forward: scratch too small (%zu bytes)", a.scratch_bytes); return ERR_WORKSPACE; }
+  const int dt = a.dtype;
+  const int64_t cache_hs = static_cast<int64_t>(a.max_seq) * hd;
+  const int64_t cache_bs = cache_hs * a.heads;
+  const int64_t layer_stride = cache_bs * a.batch;  // elements
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  uint16_t* kc0 = static_cast<uint16_t*>(a.k_cache);
+  uint16_t* vc0 = static_cast<uint16_t*>(a.v_cache);
+
+  for (int l = 0; l < a.layers; ++l) {
+    const void* const* L = a.weights + 6 * l;
+    uint16_t* kc = kc0 + l * layer_stride;
+    uint16_t* vc = vc0 + l * layer_stride;
+    if (a.all_hidden) {
+      RUN(copy_rows_run(ctx, a.hidden, 0, H, static_cast<uint16_t*>(a.all_hidden) + static_cast<int64_t>(l) * rows * H,
+                        0, H, 1, rows, H, dt, s));
+    }
+    RUN(rmsnorm_run(ctx, a.hidden, H, L[0], xn, H, rows, H, a.eps, dt, s));
+    RUN(gemm(ctx, s, dt, xn, H, L[1], H, qkv, 3 * H, rows, 3 * H, H));
+    RUN(rope_kvcache_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, a.batch, a.seq, a.heads, hd, a.pos0, a.rope_cos,
+                         a.rope_sin, dt, s));
+    if (a.seq == 1) {
+      RUN(attention_decode_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, att, H, a.batch, a.heads, hd, a.pos0 + 1,
+                               scale, dt, s));
+    } else {
+      AttnArgs at{};
+      at.q = qkv; at.q_bs = static_cast<int64_t>(a.seq) * 3 * H; at.q_rs = 3 * H; at.q_hs = hd;
+      at.k = kc; at.k_bs = cache_bs; at.k_rs = hd; at.k_hs = cache_hs;
+      at.v = vc; at.v_bs = cache_bs; at.v_rs = hd; at.v_hs = cache_hs;
+      at.o = att; at.o_bs = static_cast<int64_t>(a.seq) * H; at.o_rs = H; at.o_hs = hd;
+      at.batch = a.batch; at.heads = a.heads; at.seq_q = a.seq; at.seq_k = a.pos0 + a.seq; at.head_dim = hd;
+      at.causal = 1; at.q_pos0 = a.pos0; at.scale = scale; at.dtype = dt;
+      RUN(attention_run(ctx, at, s));
+    }
+    RUN(gemm(ctx, s, dt, att, H, L[2], H, a.hidden, H, rows, H, H, nullptr, EPI_NONE, a.hidden, H));
+    RUN(rmsnorm_run(ctx, a.hidden, H, L[3], xn, H, rows, H, a.eps, dt, s));
+    RUN(gemm(ctx, s, dt, xn, H, L[4], H, act, F, rows, 2 * F, H, nullptr, EPI_SILU_MUL));
+    RUN(gemm(ctx, s, dt, act, F, L[5], F, a.hidden, H, rows, H, F, nullptr, EPI_NONE, a.hidden, H));
+  }
+  if (a.final_out) {
+    RUN(rmsnorm_run(ctx, a.hidden, H, a.weights[6 * a.layers], a.final_out, H, rows, H, a.eps, dt, s));
+  }
+  return OK;
+}
+
+}  // namespace ullava

@@ -1,0 +1,74 @@
+// Internal C++ declarations shared by the .cu translation units of libullava_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/ullava_sm100.h"
+
+struct ullava_ctx {
+  int device = 0;
+  int sm_count = 148;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  int64_t launches = 0;
+};
+
+namespace ullava {
+
+using Context = ::ullava_ctx;
+using GemmArgs = ::ullava_gemm_args;
+using AttnArgs = ::ullava_attn_args;
+
+enum Epilogue : int {
+  EPI_NONE = ULLAVA_EPI_NONE,
+  EPI_RELU = ULLAVA_EPI_RELU,
+  EPI_GELU = ULLAVA_EPI_GELU,
+  EPI_QUICK_GELU = ULLAVA_EPI_QUICK_GELU,
+  EPI_SILU_MUL = ULLAVA_EPI_SILU_MUL,
+};
+
+// gemm_sm100.cu
+int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream);
+
+// norm.cu
+int layernorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+                  int rows, int cols, float eps, int act, int dtype, cudaStream_t stream);
+int rmsnorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols,
+                float eps, int dtype, cudaStream_t stream);
+
+// attention.cu
+int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream);
+int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
+                         int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
+                         float scale, int dtype, cudaStream_t stream);
+
+// elementwise.cu
+int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld_qkv, void* kc, void* vc, int64_t cache_bs, int64_t cache_hs,
+                     int batch, int seq, int heads, int head_dim, int pos0, const float* cos_t, const float* sin_t,
+                     int dtype, cudaStream_t stream);
+int vit_im2col_run(Context* ctx, const void* pixels, void* out, int batch, int img, int patch, int k_pad, int dtype,
+                   cudaStream_t stream);
+int vit_assemble_run(Context* ctx, const void* pe, const void* cls, const void* pos, void* out, int batch, int np,
+                     int dim, int dtype, cudaStream_t stream);
+int embed_gather_run(Context* ctx, const int64_t* ids, const void* table, void* out, int rows, int dim, int vocab,
+                     int dtype, cudaStream_t stream);
+int splice_rows_run(Context* ctx, void* embeds, const void* feats, const int32_t* start, int batch, int seq,
+                    int n_patch, int dim, int dtype, cudaStream_t stream);
+int copy_rows_run(Context* ctx, const void* src, int64_t sbs, int64_t srs, void* dst, int64_t dbs, int64_t drs,
+                  int batch, int rows, int cols, int dtype, cudaStream_t stream);
+int argmax_run(Context* ctx, const float* logits, int64_t ld, int64_t* out, int rows, int cols, cudaStream_t stream);
+
+// sam_decoder.cu
+int sam_mask_decoder_run(Context* ctx, const ullava_sam_decoder_args& a, cudaStream_t stream);
+size_t sam_mask_decoder_scratch(int n);
+int sam_postprocess_run(Context* ctx, const void* masks, int64_t mask_stride, float* out, uint32_t* bits, int n,
+                        int low_res, int img_size,
+                        int in_h, int in_w, int out_h, int out_w, int dtype, cudaStream_t stream);
+
+// models.cu
+int vit_forward_run(Context* ctx, const ullava_vit_args& a, cudaStream_t stream);
+size_t vit_scratch(int batch, int img, int patch, int hidden, int ffn, int k_pad);
+int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t stream);
+size_t llama_scratch(int rows, int hidden, int ffn);
+
+}  // namespace ullava

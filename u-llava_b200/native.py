@@ -1,0 +1,397 @@
+"""ctypes binding of libullava_sm100.so (C ABI declared in include/ullava_sm100.h).
+
+This module is the ONLY place where the host-side mirror of the reference API
+(u-llava_b200/models/*) touches native code.  PyTorch is used for device memory and
+streams only: every wrapper passes raw device pointers + shapes to the C ABI.
+
+There is no CPU or torch fallback: if the shared library is missing or the device is
+not sm_100, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libullava_sm100.so")
+
+BF16, F16, F32 = 0, 1, 2
+EPI_NONE, EPI_RELU, EPI_GELU, EPI_QUICK_GELU, EPI_SILU_MUL = 0, 1, 2, 3, 4
+SAM_N_WEIGHTS = 121
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", _vp), ("lda", _i64), ("B", _vp), ("ldb", _i64), ("D", _vp), ("ldd", _i64),
+                ("bias", _vp), ("residual", _vp), ("ldr", _i64),
+                ("M", _i32), ("N", _i32), ("K", _i32), ("dtype", _i32), ("out_f32", _i32),
+                ("epilogue", _i32), ("force_bn", _i32), ("force_splits", _i32), ("no_swap", _i32)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("q", _vp), ("q_bs", _i64), ("q_rs", _i64), ("q_hs", _i64),
+                ("k", _vp), ("k_bs", _i64), ("k_rs", _i64), ("k_hs", _i64),
+                ("v", _vp), ("v_bs", _i64), ("v_rs", _i64), ("v_hs", _i64),
+                ("o", _vp), ("o_bs", _i64), ("o_rs", _i64), ("o_hs", _i64),
+                ("batch", _i32), ("heads", _i32), ("seq_q", _i32), ("seq_k", _i32), ("head_dim", _i32),
+                ("causal", _i32), ("q_pos0", _i32), ("scale", _f32), ("dtype", _i32)]
+
+
+class SamDecoderArgs(C.Structure):
+    _fields_ = [("weights", C.POINTER(_vp)), ("n_weights", _i32),
+                ("image_embeddings", _vp), ("prompt_image", _vp), ("image_pe", _vp), ("text_embeds", _vp),
+                ("n_prompts", _i32), ("low_res_masks", _vp), ("iou_pred", _vp),
+                ("scratch", _vp), ("scratch_bytes", _sz), ("dtype", _i32)]
+
+
+class VitArgs(C.Structure):
+    _fields_ = [("weights", C.POINTER(_vp)), ("n_weights", _i32), ("pixels", _vp), ("out", _vp),
+                ("scratch", _vp), ("scratch_bytes", _sz),
+                ("batch", _i32), ("img", _i32), ("patch", _i32), ("hidden", _i32), ("heads", _i32),
+                ("ffn", _i32), ("layers_used", _i32), ("k_pad", _i32), ("act", _i32), ("eps", _f32),
+                ("dtype", _i32)]
+
+
+class LlamaArgs(C.Structure):
+    _fields_ = [("weights", C.POINTER(_vp)), ("n_weights", _i32), ("hidden", _vp), ("final_out", _vp),
+                ("all_hidden", _vp), ("k_cache", _vp), ("v_cache", _vp), ("scratch", _vp), ("scratch_bytes", _sz),
+                ("batch", _i32), ("seq", _i32), ("pos0", _i32), ("max_seq", _i32),
+                ("layers", _i32), ("hidden_size", _i32), ("heads", _i32), ("head_dim", _i32), ("ffn", _i32),
+                ("eps", _f32), ("rope_cos", _vp), ("rope_sin", _vp), ("dtype", _i32)]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/ullava_sm100.h
+_SIGNATURES = {
+    "ullava_abi_version": (_i32, []),
+    "ullava_last_error": (C.c_char_p, []),
+    "ullava_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "ullava_destroy": (_i32, [_vp]),
+    "ullava_set_workspace": (_i32, [_vp, _vp, _sz]),
+    "ullava_launch_count": (_i64, [_vp]),
+    "ullava_gemm": (_i32, [_vp, C.POINTER(GemmArgs), _vp]),
+    "ullava_layernorm": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _i32, _i32, _vp]),
+    "ullava_rmsnorm": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _f32, _i32, _vp]),
+    "ullava_attention": (_i32, [_vp, C.POINTER(AttnArgs), _vp]),
+    "ullava_attention_decode": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32,
+                                       _f32, _i32, _vp]),
+    "ullava_rope_kvcache": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
+                                   _i32, _vp]),
+    "ullava_vit_im2col": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "ullava_vit_assemble": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ullava_embed_gather": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ullava_splice_rows": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "ullava_copy_rows": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "ullava_argmax": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp]),
+    "ullava_sam_mask_decoder": (_i32, [_vp, C.POINTER(SamDecoderArgs), _vp]),
+    "ullava_sam_mask_decoder_scratch_bytes": (_sz, [_i32]),
+    "ullava_sam_postprocess": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                      _vp]),
+    "ullava_vit_forward": (_i32, [_vp, C.POINTER(VitArgs), _vp]),
+    "ullava_vit_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "ullava_llama_forward": (_i32, [_vp, C.POINTER(LlamaArgs), _vp]),
+    "ullava_llama_scratch_bytes": (_sz, [_i32, _i32, _i32]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def build_library(force: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/libullava_sm100.so (nvcc, sm_100a only)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.run(["bash", script], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def load_library():
+    """dlopen the C ABI; raises (never falls back) when it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / torch fallback for the u-LLaVA sm_100a path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.ullava_abi_version() != 1:
+            raise RuntimeError("libullava_sm100.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def exported_symbols() -> Sequence[str]:
+    return tuple(_SIGNATURES.keys())
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return BF16
+    if dt == torch.float16:
+        return F16
+    raise TypeError(f"the sm_100a path stores activations/weights in bf16 or fp16, got {dt}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Context:
+    """Per-device handle (ullava_create).  Owns a torch-allocated scratch workspace."""
+
+    _by_device = {}
+
+    def __init__(self, device: int, workspace_bytes: int = 256 << 20):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeError("CUDA device required: the u-LLaVA B200 path has no CPU fallback")
+        h = _vp()
+        st = self.lib.ullava_create(int(device), C.byref(h))
+        if st != 0:
+            raise NativeError(f"ullava_create failed ({st}): {self.lib.ullava_last_error().decode()}")
+        self.handle = h
+        self.device = torch.device("cuda", device)
+        self.workspace = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+        self._chk(self.lib.ullava_set_workspace(self.handle, self.workspace.data_ptr(), workspace_bytes))
+
+    @classmethod
+    def get(cls, device=None) -> "Context":
+        if device is None:
+            device = torch.cuda.current_device()
+        if isinstance(device, torch.device):
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        ctx = cls._by_device.get(device)
+        if ctx is None:
+            ctx = cls(device)
+            cls._by_device[device] = ctx
+        return ctx
+
+    def _chk(self, st: int):
+        if st != 0:
+            raise NativeError(f"libullava_sm100 error {st}: {self.lib.ullava_last_error().decode()}")
+
+    def launch_count(self) -> int:
+        return int(self.lib.ullava_launch_count(self.handle))
+
+    # ---- primitives ------------------------------------------------------------------
+    def gemm(self, a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, epilogue=EPI_NONE, out=None,
+             out_f32=False, force_bn=0, force_splits=0, no_swap=False) -> torch.Tensor:
+        """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual   (nn.Linear semantics)."""
+        assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+        assert a.stride(1) == 1 and w.stride(1) == 1
+        M, K = a.shape
+        N = w.shape[0]
+        n_out = N // 2 if epilogue == EPI_SILU_MUL else N
+        if out is None:
+            out = torch.empty((M, n_out), dtype=torch.float32 if out_f32 else a.dtype, device=a.device)
+        assert out.stride(1) == 1
+        g = GemmArgs()
+        g.A, g.lda, g.B, g.ldb = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0)
+        g.D, g.ldd = out.data_ptr(), out.stride(0)
+        g.bias = _ptr(bias)
+        g.residual = _ptr(residual)
+        g.ldr = residual.stride(0) if residual is not None else 0
+        g.M, g.N, g.K = M, N, K
+        g.dtype = dtype_code(a.dtype)
+        g.out_f32 = 1 if out.dtype == torch.float32 else 0
+        g.epilogue, g.force_bn, g.force_splits, g.no_swap = epilogue, force_bn, force_splits, int(no_swap)
+        self._chk(self.lib.ullava_gemm(self.handle, C.byref(g), _stream()))
+        return out
+
+    def layernorm(self, x, weight, bias, eps, act=EPI_NONE, out=None):
+        x2 = x.reshape(-1, x.shape[-1])
+        if out is None:
+            out = torch.empty_like(x2)
+        o2 = out.reshape(-1, x.shape[-1])
+        self._chk(self.lib.ullava_layernorm(self.handle, x2.data_ptr(), x2.stride(0), weight.data_ptr(),
+                                            bias.data_ptr(), o2.data_ptr(), o2.stride(0), x2.shape[0], x2.shape[1],
+                                            float(eps), act, dtype_code(x.dtype), _stream()))
+        return out.reshape(x.shape)
+
+    def rmsnorm(self, x, weight, eps, out=None):
+        x2 = x.reshape(-1, x.shape[-1])
+        if out is None:
+            out = torch.empty_like(x2)
+        o2 = out.reshape(-1, x.shape[-1])
+        self._chk(self.lib.ullava_rmsnorm(self.handle, x2.data_ptr(), x2.stride(0), weight.data_ptr(), o2.data_ptr(),
+                                          o2.stride(0), x2.shape[0], x2.shape[1], float(eps), dtype_code(x.dtype),
+                                          _stream()))
+        return out.reshape(x.shape)
+
+    def attention(self, q, k, v, causal=False, q_pos0=0, scale=None, out=None):
+        """q,k,v: [B, S, H, D] views (last dim contiguous); returns [B, Sq, H, D]."""
+        B, Sq, H, D = q.shape
+        Sk = k.shape[1]
+        if out is None:
+            out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
+        a = AttnArgs()
+        for name, t in (("q", q), ("k", k), ("v", v), ("o", out)):
+            assert t.stride(3) == 1
+            setattr(a, name, t.data_ptr())
+            setattr(a, name + "_bs", t.stride(0))
+            setattr(a, name + "_rs", t.stride(1))
+            setattr(a, name + "_hs", t.stride(2))
+        a.batch, a.heads, a.seq_q, a.seq_k, a.head_dim = B, H, Sq, Sk, D
+        a.causal, a.q_pos0 = int(causal), int(q_pos0)
+        a.scale = float(scale if scale is not None else D ** -0.5)
+        a.dtype = dtype_code(q.dtype)
+        self._chk(self.lib.ullava_attention(self.handle, C.byref(a), _stream()))
+        return out
+
+    def attention_decode(self, q, k_cache, v_cache, ctx_len, scale=None, out=None):
+        """q: [B, H*D] (row stride arbitrary); caches: [B, H, max_seq, D]; returns [B, H*D]."""
+        B, H, _, D = k_cache.shape
+        if out is None:
+            out = torch.empty((B, H * D), dtype=q.dtype, device=q.device)
+        self._chk(self.lib.ullava_attention_decode(
+            self.handle, q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0),
+            k_cache.stride(1), out.data_ptr(), out.stride(0), B, H, D, int(ctx_len),
+            float(scale if scale is not None else D ** -0.5), dtype_code(q.dtype), _stream()))
+        return out
+
+    def rope_kvcache(self, qkv, k_cache, v_cache, batch, seq, pos0, cos, sin):
+        B, H, _, D = k_cache.shape
+        self._chk(self.lib.ullava_rope_kvcache(
+            self.handle, qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0),
+            k_cache.stride(1), batch, seq, H, D, int(pos0), cos.data_ptr(), sin.data_ptr(), dtype_code(qkv.dtype),
+            _stream()))
+
+    def vit_im2col(self, pixels, patch, k_pad):
+        B, _, img, _ = pixels.shape
+        g = img // patch
+        out = torch.empty((B * g * g, k_pad), dtype=pixels.dtype, device=pixels.device)
+        self._chk(self.lib.ullava_vit_im2col(self.handle, pixels.data_ptr(), out.data_ptr(), B, img, patch, k_pad,
+                                             dtype_code(pixels.dtype), _stream()))
+        return out
+
+    def vit_assemble(self, patch_embeds, cls, pos, batch):
+        n_p = patch_embeds.shape[0] // batch
+        dim = patch_embeds.shape[1]
+        out = torch.empty((batch, n_p + 1, dim), dtype=patch_embeds.dtype, device=patch_embeds.device)
+        self._chk(self.lib.ullava_vit_assemble(self.handle, patch_embeds.data_ptr(), cls.data_ptr(), pos.data_ptr(),
+                                               out.data_ptr(), batch, n_p, dim, dtype_code(out.dtype), _stream()))
+        return out
+
+    def embed_gather(self, ids, table, out=None):
+        rows = ids.numel()
+        dim = table.shape[1]
+        if out is None:
+            out = torch.empty((rows, dim), dtype=table.dtype, device=table.device)
+        ids = ids.reshape(-1).contiguous()
+        assert ids.dtype == torch.int64
+        self._chk(self.lib.ullava_embed_gather(self.handle, ids.data_ptr(), table.data_ptr(), out.data_ptr(), rows,
+                                               dim, table.shape[0], dtype_code(table.dtype), _stream()))
+        return out
+
+    def splice_rows(self, embeds, feats, start):
+        B, L, dim = embeds.shape
+        n_patch = feats.shape[1]
+        assert start.dtype == torch.int32 and start.is_cuda
+        self._chk(self.lib.ullava_splice_rows(self.handle, embeds.data_ptr(), feats.data_ptr(), start.data_ptr(), B, L,
+                                              n_patch, dim, dtype_code(embeds.dtype), _stream()))
+
+    def copy_rows(self, src, dst, batch, rows, cols, src_bs, src_rs, dst_bs, dst_rs):
+        self._chk(self.lib.ullava_copy_rows(self.handle, src.data_ptr(), src_bs, src_rs, dst.data_ptr(), dst_bs,
+                                            dst_rs, batch, rows, cols, dtype_code(src.dtype), _stream()))
+
+    def argmax(self, logits, out=None):
+        rows, cols = logits.shape
+        assert logits.dtype == torch.float32 and logits.stride(1) == 1
+        if out is None:
+            out = torch.empty((rows,), dtype=torch.int64, device=logits.device)
+        self._chk(self.lib.ullava_argmax(self.handle, logits.data_ptr(), logits.stride(0), out.data_ptr(), rows, cols,
+                                         _stream()))
+        return out
+
+    # ---- stage-level --------------------------------------------------------------------
+    @staticmethod
+    def pointer_table(tensors: Sequence[torch.Tensor]):
+        arr = (_vp * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = t.data_ptr()
+        return arr
+
+    def sam_mask_decoder(self, weight_table, n_weights, image_embeddings, prompt_image, image_pe, text_embeds,
+                         want_iou=True):
+        n = text_embeds.shape[0]
+        dt = text_embeds.dtype
+        dev = text_embeds.device
+        masks = torch.empty((n, 4, 256, 256), dtype=dt, device=dev)
+        iou = torch.empty((n, 4), dtype=dt, device=dev) if want_iou else None
+        sb = int(self.lib.ullava_sam_mask_decoder_scratch_bytes(n))
+        scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+        a = SamDecoderArgs()
+        a.weights, a.n_weights = weight_table, n_weights
+        a.image_embeddings, a.prompt_image = image_embeddings.data_ptr(), prompt_image.data_ptr()
+        a.image_pe, a.text_embeds, a.n_prompts = image_pe.data_ptr(), text_embeds.data_ptr(), n
+        a.low_res_masks, a.iou_pred = masks.data_ptr(), _ptr(iou)
+        a.scratch, a.scratch_bytes, a.dtype = scratch.data_ptr(), sb, dtype_code(dt)
+        self._chk(self.lib.ullava_sam_mask_decoder(self.handle, C.byref(a), _stream()))
+        return masks, iou
+
+    def sam_postprocess(self, masks, mask_stride, n, low_res, img_size, input_size, original_size, pack_bits=False):
+        out_h, out_w = int(original_size[0]), int(original_size[1])
+        out = torch.empty((n, out_h, out_w), dtype=torch.float32, device=masks.device)
+        bits = None
+        if pack_bits:
+            bits = torch.zeros((n, (out_h * out_w + 31) // 32), dtype=torch.int32, device=masks.device)
+        self._chk(self.lib.ullava_sam_postprocess(self.handle, masks.data_ptr(), int(mask_stride), out.data_ptr(),
+                                                  _ptr(bits), n, low_res, img_size, int(input_size[0]),
+                                                  int(input_size[1]), out_h, out_w, dtype_code(masks.dtype),
+                                                  _stream()))
+        return out, bits
+
+    def vit_forward(self, weight_table, n_weights, pixels, cfg: dict, scratch=None):
+        B = pixels.shape[0]
+        g = cfg["img"] // cfg["patch"]
+        out = torch.empty((B, g * g, cfg["hidden"]), dtype=pixels.dtype, device=pixels.device)
+        sb = int(self.lib.ullava_vit_scratch_bytes(B, cfg["img"], cfg["patch"], cfg["hidden"], cfg["ffn"],
+                                                   cfg["k_pad"]))
+        if scratch is None or scratch.numel() < sb:
+            scratch = torch.empty(sb, dtype=torch.uint8, device=pixels.device)
+        a = VitArgs()
+        a.weights, a.n_weights, a.pixels, a.out = weight_table, n_weights, pixels.data_ptr(), out.data_ptr()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        a.batch, a.img, a.patch, a.hidden, a.heads = B, cfg["img"], cfg["patch"], cfg["hidden"], cfg["heads"]
+        a.ffn, a.layers_used, a.k_pad, a.act, a.eps = cfg["ffn"], cfg["layers_used"], cfg["k_pad"], cfg["act"], cfg["eps"]
+        a.dtype = dtype_code(pixels.dtype)
+        self._chk(self.lib.ullava_vit_forward(self.handle, C.byref(a), _stream()))
+        return out
+
+    def llama_forward(self, weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq, pos0, cfg: dict,
+                      rope_cos, rope_sin, final_out=None, all_hidden=None):
+        a = LlamaArgs()
+        a.weights, a.n_weights = weight_table, n_weights
+        a.hidden, a.final_out, a.all_hidden = hidden.data_ptr(), _ptr(final_out), _ptr(all_hidden)
+        a.k_cache, a.v_cache = k_cache.data_ptr(), v_cache.data_ptr()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        a.batch, a.seq, a.pos0, a.max_seq = batch, seq, pos0, k_cache.shape[3]
+        a.layers, a.hidden_size, a.heads, a.head_dim, a.ffn = (cfg["layers"], cfg["hidden"], cfg["heads"],
+                                                               cfg["head_dim"], cfg["ffn"])
+        a.eps = cfg["eps"]
+        a.rope_cos, a.rope_sin = rope_cos.data_ptr(), rope_sin.data_ptr()
+        a.dtype = dtype_code(hidden.dtype)
+        self._chk(self.lib.ullava_llama_forward(self.handle, C.byref(a), _stream()))
+
+    def llama_scratch_bytes(self, rows, hidden, ffn) -> int:
+        return int(self.lib.ullava_llama_scratch_bytes(rows, hidden, ffn))
