@@ -12,6 +12,7 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (sm_100a); run with -m gpu")
+    config.addinivalue_line("markers", "slow: CPU test that takes more than ~10 s")
 
 
 def pytest_collection_modifyitems(config, items):

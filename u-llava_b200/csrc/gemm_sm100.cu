@@ -72,7 +72,7 @@ __device__ __forceinline__ float apply_act(float v, int epi) {
   switch (epi) {
     case EPI_RELU: return fmaxf(v, 0.f);
     case EPI_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-    case EPI_QUICK_GELU: return v / (1.f + __expf(-1.702f * v));
+    case EPI_QUICK_GELU: return __fdividef(v, 1.f + __expf(fminf(-1.702f * v, 80.f)));  // MUFU.EX2 + MUFU.RCP
     default: return v;
   }
 }
@@ -120,7 +120,7 @@ __device__ __forceinline__ void epilogue_store(float (&v)[CH], const GemmKernelP
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float g = v[i];
-              o[i] = (g / (1.f + __expf(-g))) * v[16 + i];
+              o[i] = __fdividef(g, 1.f + __expf(fminf(-g, 80.f))) * v[16 + i];
             }
             const int on0 = n0 >> 1;
             if (p.out_f32) {
@@ -405,7 +405,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int R, int C
           const int c = c0 + tx;
           if (c < c_valid) {
             const float g = tile[rr][tx], u = tile[rr][tx + 16];
-            float o = (g / (1.f + __expf(-g))) * u;
+            float o = __fdividef(g, 1.f + __expf(fminf(-g, 80.f))) * u;
             const int oc = (c0 >> 1) + tx;
             if (resid) o += T16<T>::to_f(resid[static_cast<int64_t>(r) * ldr + oc]);
             if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(r) * ldo + oc] = o;
@@ -433,7 +433,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int R, int C
           const int r = r0 + tx;  // gate row; up row = r + 16 (same 32-row chunk)
           if (r < R) {
             const float g = tile[tx][cc], u = tile[tx + 16][cc];
-            float o = (g / (1.f + __expf(-g))) * u;
+            float o = __fdividef(g, 1.f + __expf(fminf(-g, 80.f))) * u;
             const int orow = (r0 >> 1) + tx;
             if (resid) o += T16<T>::to_f(resid[static_cast<int64_t>(c) * ldr + orow]);
             if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(c) * ldo + orow] = o;

@@ -1,0 +1,202 @@
+"""Host-side glue between the reference-shaped nn.Module tree and libullava_sm100.so.
+
+The nn.Modules (LlamaModel, CLIPVisionModel, nn.Linear ...) are *parameter containers* that keep
+the reference's attribute tree / state_dict keys / from_pretrained format; their forward() is never
+called.  This module packs their parameters once into the layouts the kernels want (fused QKV,
+gate/up interleaved by 16 rows, zero-padded im2col patch weight), keeps pointer tables for the C ABI
+and owns the caller-side buffers (KV cache, activations, scratch).
+
+Everything here is host logic + pointer plumbing; all arithmetic happens in the C ABI calls.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+try:  # importable both as models.engine (drop-in layout) and standalone
+    import native
+except ImportError:  # pragma: no cover
+    from .. import native  # type: ignore
+
+
+def _sig(params) -> Tuple:
+    return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """[F,K],[F,K] -> [2F,K] where every 32-row chunk = 16 gate rows followed by the 16 matching up rows
+    (layout consumed by the SILU_MUL GEMM epilogue)."""
+    F_, K = gate.shape
+    assert F_ % 16 == 0
+    return torch.stack([gate.view(F_ // 16, 16, K), up.view(F_ // 16, 16, K)], dim=1).reshape(2 * F_, K).contiguous()
+
+
+class KVCache:
+    """KV cache owned by the caller side: k, v [layers, B, heads, max_seq, head_dim]; `length` tokens valid.
+    Returned as `past_key_values` by UllavaCoreForCausalLM.forward(use_cache=True)."""
+
+    def __init__(self, layers, batch, heads, max_seq, head_dim, dtype, device):
+        self.k = torch.empty((layers, batch, heads, max_seq, head_dim), dtype=dtype, device=device)
+        self.v = torch.empty_like(self.k)
+        self.length = 0
+        self.max_seq = max_seq
+        self.batch = batch
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self.length
+
+    def __len__(self):
+        return self.k.shape[0]
+
+    def __bool__(self):
+        return True
+
+    def to_legacy(self):
+        """Tuple of (k, v) [B, heads, length, hd] per layer, HF legacy format (views)."""
+        return tuple((self.k[l, :, :, : self.length], self.v[l, :, :, : self.length]) for l in range(self.k.shape[0]))
+
+
+class VisionTower:
+    """CLIP ViT weights packed for ullava_vit_forward."""
+
+    def __init__(self, vision_encoder, hidden_layer: int):
+        self.module = vision_encoder
+        self.hidden_layer = hidden_layer
+        self._sig = None
+
+    def _pack(self):
+        vm = self.module.vision_model
+        cfg = self.module.config
+        n_layers = cfg.num_hidden_layers
+        idx = self.hidden_layer if self.hidden_layer >= 0 else n_layers + 1 + self.hidden_layer
+        if not (0 <= idx <= n_layers):
+            raise ValueError(f"vision_hidden_layer {self.hidden_layer} out of range for {n_layers} layers")
+        act = {"quick_gelu": native.EPI_QUICK_GELU, "gelu": native.EPI_GELU}.get(cfg.hidden_act)
+        if act is None:
+            raise NotImplementedError(f"CLIP hidden_act {cfg.hidden_act!r}")
+        pw = vm.embeddings.patch_embedding.weight
+        H = pw.shape[0]
+        k = pw[0].numel()
+        k_pad = (k + 63) // 64 * 64
+        wp = torch.zeros((H, k_pad), dtype=pw.dtype, device=pw.device)
+        wp[:, :k] = pw.detach().reshape(H, k)
+        tensors = [wp, vm.embeddings.class_embedding.detach().contiguous(),
+                   vm.embeddings.position_embedding.weight.detach().contiguous(),
+                   vm.pre_layrnorm.weight.detach(), vm.pre_layrnorm.bias.detach()]
+        for l in range(idx):
+            lay = vm.encoder.layers[l]
+            a = lay.self_attn
+            tensors += [lay.layer_norm1.weight.detach(), lay.layer_norm1.bias.detach(),
+                        torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).detach().contiguous(),
+                        torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0).detach().contiguous(),
+                        a.out_proj.weight.detach().contiguous(), a.out_proj.bias.detach(),
+                        lay.layer_norm2.weight.detach(), lay.layer_norm2.bias.detach(),
+                        lay.mlp.fc1.weight.detach().contiguous(), lay.mlp.fc1.bias.detach(),
+                        lay.mlp.fc2.weight.detach().contiguous(), lay.mlp.fc2.bias.detach()]
+        self.tensors = tensors  # keep alive
+        self.table = native.Context.pointer_table(tensors)
+        self.cfg = dict(img=cfg.image_size, patch=cfg.patch_size, hidden=H, heads=cfg.num_attention_heads,
+                        ffn=cfg.intermediate_size, layers_used=idx, k_pad=k_pad, act=act,
+                        eps=float(cfg.layer_norm_eps))
+
+    def ensure(self):
+        sig = _sig(self.module.parameters())
+        if sig != self._sig:
+            self._pack()
+            self._sig = sig
+
+    def __call__(self, ctx: "native.Context", pixels: torch.Tensor) -> torch.Tensor:
+        self.ensure()
+        dt = self.tensors[0].dtype
+        pixels = pixels.to(dt).contiguous()
+        if pixels.shape[-1] != self.cfg["img"] or pixels.shape[-2] != self.cfg["img"]:
+            raise ValueError(f"Input image size ({pixels.shape[-2]}*{pixels.shape[-1]}) doesn't match model "
+                             f"({self.cfg['img']}*{self.cfg['img']}).")
+        return ctx.vit_forward(self.table, len(self.tensors), pixels, self.cfg)
+
+
+class LlamaStack:
+    """LLaMA decoder weights packed for ullava_llama_forward + lm_head / embedding plumbing."""
+
+    def __init__(self, llama_model, lm_head):
+        self.model = llama_model
+        self.lm_head = lm_head
+        self._sig = None
+        self._scratch = None
+        self._rope = None
+
+    def _pack(self):
+        cfg = self.model.config
+        heads = cfg.num_attention_heads
+        kvh = getattr(cfg, "num_key_value_heads", heads) or heads
+        if kvh != heads:
+            raise NotImplementedError("grouped-query attention is outside the u-LLaVA (LLaMA-7B) path")
+        if getattr(cfg, "attention_bias", False) or getattr(cfg, "mlp_bias", False):
+            raise NotImplementedError("LLaMA with biases is outside the u-LLaVA path")
+        tensors = []
+        for lay in self.model.layers:
+            a, m = lay.self_attn, lay.mlp
+            tensors += [lay.input_layernorm.weight.detach(),
+                        torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).detach().contiguous(),
+                        a.o_proj.weight.detach().contiguous(),
+                        lay.post_attention_layernorm.weight.detach(),
+                        interleave_gate_up(m.gate_proj.weight.detach(), m.up_proj.weight.detach()),
+                        m.down_proj.weight.detach().contiguous()]
+        tensors.append(self.model.norm.weight.detach())
+        self.tensors = tensors
+        self.table = native.Context.pointer_table(tensors)
+        H = cfg.hidden_size
+        self.cfg = dict(layers=len(self.model.layers), hidden=H, heads=heads, head_dim=H // heads,
+                        ffn=cfg.intermediate_size, eps=float(cfg.rms_norm_eps))
+        rp = getattr(cfg, "rope_parameters", None) or {}
+        self.theta = float(rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0)))
+        if rp.get("rope_type", "default") != "default":
+            raise NotImplementedError("only default RoPE is on the u-LLaVA path")
+        self.dtype = tensors[1].dtype
+        self.device = tensors[1].device
+        self._rope = None
+
+    def ensure(self):
+        sig = _sig(list(self.model.parameters()) + list(self.lm_head.parameters()))
+        if sig != self._sig:
+            self._pack()
+            self._sig = sig
+
+    def rope_tables(self, max_pos: int):
+        if self._rope is None or self._rope[0].shape[0] < max_pos:
+            hd = self.cfg["head_dim"]
+            n = max(max_pos, 2048)
+            # LlamaRotaryEmbedding (hf:models/llama/modeling_llama.py:74-135), fp32 on the host side
+            inv = 1.0 / (self.theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+            fr = torch.arange(n, dtype=torch.float32)[:, None] * inv[None, :]
+            self._rope = (fr.cos().to(self.device).contiguous(), fr.sin().to(self.device).contiguous())
+        return self._rope
+
+    def new_cache(self, batch: int, max_seq: int) -> KVCache:
+        self.ensure()
+        c = self.cfg
+        return KVCache(c["layers"], batch, c["heads"], max_seq, c["head_dim"], self.dtype, self.device)
+
+    def scratch(self, ctx, rows: int) -> torch.Tensor:
+        need = ctx.llama_scratch_bytes(rows, self.cfg["hidden"], self.cfg["ffn"])
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != self.device:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    def run(self, ctx, hidden: torch.Tensor, cache: KVCache, batch: int, seq: int, want_all_hidden=False):
+        """hidden [batch*seq, H] is updated in place to the last layer's output; returns
+        (final_norm_out [batch*seq, H], all_hidden [layers, batch*seq, H] or None)."""
+        self.ensure()
+        pos0 = cache.length
+        if pos0 + seq > cache.max_seq:
+            raise ValueError(f"KV cache too small: {pos0}+{seq} > {cache.max_seq}")
+        cos, sin = self.rope_tables(cache.max_seq)
+        final = torch.empty_like(hidden)
+        allh = None
+        if want_all_hidden:
+            allh = torch.empty((self.cfg["layers"],) + tuple(hidden.shape), dtype=hidden.dtype, device=hidden.device)
+        ctx.llama_forward(self.table, len(self.tensors), hidden, cache.k, cache.v, self.scratch(ctx, batch * seq),
+                          batch, seq, pos0, self.cfg, cos, sin, final_out=final, all_hidden=allh)
+        cache.length = pos0 + seq
+        return final, allh

@@ -1,0 +1,392 @@
+"""B200-native u-LLaVA core: CLIP ViT -> projector -> LLaMA, behind the reference's module API.
+
+Mirrors /root/reference/models/ullava_core.py (class names, constructor, attribute tree, state_dict
+keys, forward/generate signatures and return containers) so that inference_ullava_core.py and
+UllavaForCausalLM use it unchanged.  The HuggingFace modules instantiated here hold parameters only:
+every forward pass goes through libullava_sm100.so (see engine.py / native.py).  There is no torch
+fallback: without a CUDA sm_100 device the forward raises.
+
+Reference behaviour kept (file:line in /root/reference):
+  * encode_image selects hidden_states[vision_hidden_layer] and drops CLS      (models/ullava_core.py:146-158)
+  * image features are projected and spliced after <img_beg>                  (:182-277)
+  * start/end token count assertion                                           (:209-211)
+  * a [B,1] input_ids call with past_key_values is a decode step (no vision)  (:188-189)
+  * forward returns CausalLMOutputWithPast(loss, logits, past_key_values, hidden_states, attentions) (:279-355)
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+from transformers import (AutoConfig, AutoModelForCausalLM, CLIPVisionConfig, CLIPVisionModel, LlamaConfig,
+                          LlamaForCausalLM, LlamaModel)
+from transformers.modeling_outputs import CausalLMOutputWithPast
+
+try:
+    from utils.registry import registry  # present when dropped into the reference tree
+except Exception:  # standalone use
+    class _Registry:
+        mapping = {"model_name_mapping": {}}
+
+        @classmethod
+        def register_model(cls, name):
+            def wrap(model_cls):
+                cls.mapping["model_name_mapping"][name] = model_cls
+                return model_cls
+            return wrap
+
+    registry = _Registry()
+
+import native
+from .engine import KVCache, LlamaStack, VisionTower
+
+
+class UllavaCoreConfig(LlamaConfig):
+    model_type = "ullava_core"
+    is_composition = True
+
+    def __init__(self, vision_config=None, vision_hidden_layer=-1, projector_type='mlp',
+                 projector_from_scratch=True, mm_token_ids=None, **kwargs):
+        super().__init__(**kwargs)
+        self.vision_hidden_layer = vision_hidden_layer
+        self.mm_token_ids = mm_token_ids
+        self.projector_type = projector_type
+        self.projector_from_scratch = projector_from_scratch
+        if isinstance(vision_config, CLIPVisionConfig):
+            vision_config = vision_config.to_dict()
+        self.vision_config = CLIPVisionConfig(**vision_config) if vision_config else {}
+
+    def to_dict(self):
+        output = copy.deepcopy(self.__dict__)
+        output["vision_config"] = self.vision_config.to_dict() if self.vision_config else {}
+        output["model_type"] = self.__class__.model_type
+        return output
+
+
+class GenerateOutput(dict):
+    """Minimal stand-in for transformers' GenerateDecoderOnlyOutput: attribute + key access."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+@registry.register_model('ullava_core')
+class UllavaCoreForCausalLM(LlamaForCausalLM):
+    config_class = UllavaCoreConfig
+
+    def __init__(self, config: UllavaCoreConfig):
+        super(LlamaForCausalLM, self).__init__(config)
+        self.config = config
+        self.model = LlamaModel(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.vision_encoder = CLIPVisionModel(config.vision_config)
+        self.vision_projector = self.build_vision_projector(config.vision_config.hidden_size, config.hidden_size,
+                                                            config.projector_type)
+        self.vision_hidden_layer = config.vision_hidden_layer
+        self.projector_from_scratch = config.projector_from_scratch
+        self.mm_token_ids = config.mm_token_ids
+        self.post_init()
+        self._tower = None
+        self._stack = None
+
+    @staticmethod
+    def build_vision_projector(in_dim, hidden_dim, name='mlp'):
+        if name == 'mlp':
+            return nn.Linear(in_dim, hidden_dim)
+        if name == 'mlp2x':
+            return nn.Sequential(nn.Linear(in_dim, hidden_dim), nn.GELU(), nn.Linear(hidden_dim, hidden_dim))
+        raise NotImplementedError
+
+    def get_input_embeddings(self) -> nn.Module:
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self) -> nn.Module:
+        return self.lm_head
+
+    def init_mm_tokens(self, tokenizer, mm_tokens):
+        mm_token_ids = {k: tokenizer.convert_tokens_to_ids(v) for k, v in mm_tokens.items()}
+        self.config.mm_token_ids = mm_token_ids
+        self.mm_token_ids = self.config.mm_token_ids
+
+    # ---- native plumbing -------------------------------------------------------------------
+    def _ctx(self) -> "native.Context":
+        dev = self.lm_head.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("UllavaCoreForCausalLM (B200 build) runs on a CUDA sm_100 device only; "
+                               "call .cuda() first -- there is no CPU fallback")
+        return native.Context.get(dev)
+
+    def _engine(self):
+        if self._tower is None or self._tower.module is not self.vision_encoder or \
+                self._tower.hidden_layer != self.vision_hidden_layer:
+            self._tower = VisionTower(self.vision_encoder, self.vision_hidden_layer)
+        if self._stack is None or self._stack.model is not self.model or self._stack.lm_head is not self.lm_head:
+            self._stack = LlamaStack(self.model, self.lm_head)
+        return self._tower, self._stack
+
+    def _project(self, ctx, feats2d: torch.Tensor) -> torch.Tensor:
+        vp = self.vision_projector
+        if isinstance(vp, nn.Linear):
+            return ctx.gemm(feats2d, vp.weight.detach(), bias=vp.bias.detach())
+        h = ctx.gemm(feats2d, vp[0].weight.detach(), bias=vp[0].bias.detach(), epilogue=native.EPI_GELU)
+        return ctx.gemm(h, vp[2].weight.detach(), bias=vp[2].bias.detach())
+
+    def encode_image(self, image_tensors):
+        """[bs,3,H,W] -> [bs, num_patches, vision_hidden] (CLS removed)."""
+        with torch.no_grad():
+            tower, _ = self._engine()
+            return tower(self._ctx(), image_tensors)
+
+    def encode_video(self, video_clip_tensors):
+        """[bs, C, T, H, W] -> temporal+spatial pooled features [bs, T + num_patches, hidden]
+        (reference :160-180).  The frames go through the native ViT; the two mean-poolings are glue."""
+        bs, c, t, h, w = video_clip_tensors.shape
+        frames = video_clip_tensors.permute(0, 2, 1, 3, 4).reshape(bs * t, c, h, w)
+        feats = self.encode_image(frames).view(bs, t, -1, self.vision_encoder.config.hidden_size)
+        spatial = feats.float().mean(dim=1).to(feats.dtype)
+        temporal = feats.float().mean(dim=2).to(feats.dtype)
+        return torch.cat([temporal, spatial], dim=1)
+
+    def embed_images_videos(self, input_ids=None, images=None, videos=None):
+        if input_ids.shape[1] == 1:
+            return input_ids, None
+        ctx = self._ctx()
+        _, stack = self._engine()
+        stack.ensure()
+        B, L = input_ids.shape
+        table = self.model.embed_tokens.weight.detach()
+        H = table.shape[1]
+        embeds = ctx.embed_gather(input_ids, table).view(B, L, H)
+        ids = self.mm_token_ids
+        # one host round trip for the control decisions of the whole batch (the reference syncs per sample)
+        flags = torch.stack([(input_ids == ids["IMG_START"]).sum(1), (input_ids == ids["IMG_END"]).sum(1),
+                             (input_ids == ids["VID_START"]).sum(1), (input_ids == ids["VID_END"]).sum(1),
+                             (input_ids == ids["IMG_START"]).int().argmax(1),
+                             (input_ids == ids["VID_START"]).int().argmax(1)], 1).cpu()
+        for b in range(B):
+            n_is, n_ie, n_vs, n_ve = (int(v) for v in flags[b, :4])
+            assert n_is == n_ie and n_vs == n_ve, \
+                "Number of image start and end tokens should be the same. {0} vs {1}, {2} vs {3}".format(
+                    n_is, n_ie, n_vs, n_ve)
+        img_rows = [b for b in range(B) if int(flags[b, 0]) > 0]
+        vid_rows = [b for b in range(B) if int(flags[b, 0]) == 0 and int(flags[b, 2]) > 0]
+        if img_rows:
+            feats = self.encode_image(images)  # [n_img, P, Hv]
+            n_patch = feats.shape[1]
+            proj = self._project(ctx, feats.reshape(-1, feats.shape[-1])).view(feats.shape[0], n_patch, H)
+            start = torch.full((B,), -1, dtype=torch.int32)
+            feat_rows = torch.zeros((B, n_patch, H), dtype=proj.dtype, device=proj.device) if len(img_rows) != B else None
+            for i, b in enumerate(img_rows):
+                start[b] = int(flags[b, 4])
+                if int(start[b]) + 1 + n_patch > L:
+                    raise ValueError("image patch tokens do not fit in the sequence")
+                if feat_rows is not None:
+                    feat_rows[b] = proj[i]
+            ctx.splice_rows(embeds, proj if feat_rows is None else feat_rows, start.to(embeds.device))
+        if vid_rows:
+            vfeats = self.encode_video(videos)
+            n_fp = vfeats.shape[1]
+            vproj = self._project(ctx, vfeats.reshape(-1, vfeats.shape[-1])).view(vfeats.shape[0], n_fp, H)
+            start = torch.full((B,), -1, dtype=torch.int32)
+            rows = torch.zeros((B, n_fp, H), dtype=vproj.dtype, device=vproj.device)
+            for i, b in enumerate(vid_rows):
+                start[b] = int(flags[b, 5])
+                rows[b] = vproj[i]
+            ctx.splice_rows(embeds, rows, start.to(embeds.device))
+        return None, embeds
+
+    @staticmethod
+    def _check_mask(attention_mask, B, L):
+        """Right padding is harmless under a causal mask (valid positions never see pad tokens);
+        anything else (left padding / holes) is not on the reference's inference path."""
+        if attention_mask is None:
+            return
+        m = attention_mask.bool()
+        if m.shape[-1] != L:
+            return  # generation-time mask covering past + current tokens
+        if bool(m.all()):
+            return
+        valid = m.int().sum(1)
+        expect = torch.arange(L, device=m.device)[None, :] < valid[:, None]
+        if not bool((m == expect).all()):
+            raise NotImplementedError("only right-padded attention masks are supported on the B200 path")
+
+    def forward(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.LongTensor] = None, past_key_values=None,
+                inputs_embeds: Optional[torch.FloatTensor] = None, labels: Optional[torch.LongTensor] = None,
+                use_cache: Optional[bool] = None, output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None, images: Optional[torch.FloatTensor] = None,
+                videos: Optional[torch.FloatTensor] = None, return_dict: Optional[bool] = None,
+                logits_to_keep: int = 0, logits_fp32: bool = False, **kwargs):
+        output_attentions = output_attentions if output_attentions is not None else self.config.output_attentions
+        output_hidden_states = (output_hidden_states if output_hidden_states is not None
+                                else self.config.output_hidden_states)
+        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
+        if output_attentions:
+            raise NotImplementedError("attention probabilities are never materialised by the flash kernels")
+        # position_ids are implied by the KV-cache length (equal-length / right-padded batches)
+        only_last_hidden = bool(kwargs.pop("_return_last_hidden", False))
+        caller_embeds = inputs_embeds is not None
+        ctx = self._ctx()
+        _, stack = self._engine()
+        with torch.no_grad():
+            if inputs_embeds is None:
+                input_ids, inputs_embeds = self.embed_images_videos(input_ids, images, videos)
+                if inputs_embeds is None:  # decode step: [B,1] token ids
+                    table = self.model.embed_tokens.weight.detach()
+                    inputs_embeds = ctx.embed_gather(input_ids, table).view(input_ids.shape[0], 1, -1)
+            B, L, H = inputs_embeds.shape
+            self._check_mask(attention_mask, B, L)
+            if past_key_values is not None and not isinstance(past_key_values, KVCache):
+                raise TypeError("past_key_values must be the KVCache returned by a previous forward(use_cache=True)")
+            if past_key_values is not None:
+                cache = past_key_values
+            else:
+                max_seq = L if not use_cache else max(L + 64, int(getattr(self.config, "native_max_seq", 0) or 0))
+                cache = stack.new_cache(B, max_seq)
+            hidden = inputs_embeds.reshape(B * L, H)
+            if caller_embeds:
+                hidden = hidden.to(stack.dtype).clone()  # the stack updates its input in place
+            final, allh = stack.run(ctx, hidden, cache, B, L, want_all_hidden=bool(output_hidden_states))
+            w = self.lm_head.weight.detach()
+            if logits_to_keep:
+                last = final.view(B, L, H)[:, -logits_to_keep:].reshape(-1, H)
+                logits = ctx.gemm(last, w, out_f32=logits_fp32).view(B, logits_to_keep, -1)
+            else:
+                logits = ctx.gemm(final, w, out_f32=logits_fp32).view(B, L, -1)
+            hs = None
+            if output_hidden_states:
+                hs = tuple(allh[l].view(B, L, H) for l in range(allh.shape[0])) + (final.view(B, L, H),)
+            elif only_last_hidden:
+                hs = (final.view(B, L, H),)
+
+        loss = None
+        if labels is not None:
+            # reference :327-338; off the accelerated path (inference callers ignore it)
+            shift_logits = logits[..., :-1, :].float().reshape(-1, logits.shape[-1])
+            shift_labels = labels[..., 1:].reshape(-1).to(shift_logits.device)
+            loss = nn.functional.cross_entropy(shift_logits, shift_labels)
+
+        pkv = cache if use_cache else None
+        if not return_dict:
+            out = (logits, pkv, hs)
+            out = tuple(o for o in out if o is not None)
+            return (loss,) + out if loss is not None else out
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=pkv, hidden_states=hs,
+                                      attentions=None)
+
+    # ---- generation --------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids=None, images=None, videos=None, max_new_tokens=32, num_beams=1, top_p=None,
+                 do_sample=False, temperature=1.0, output_hidden_states=False, return_dict_in_generate=False,
+                 no_repeat_ngram_size=None, stopping_criteria=None, eos_token_id=None, pad_token_id=None,
+                 attention_mask=None, use_cache=True, **kwargs):
+        """Greedy / sampling generation with a KV cache (replaces HF GenerationMixin.generate for the
+        path used by UllavaForCausalLM.evaluate, models/ullava.py:349-365, and inference_ullava_core.py:73-80).
+
+        With output_hidden_states=True and return_dict_in_generate=True, `hidden_states[-1][-1]` is the
+        post-final-norm hidden state of every processed position, [B, T-1, H] -- exactly what the
+        reference reads when its checkpoints run with use_cache=False."""
+        if num_beams != 1:
+            raise NotImplementedError("beam search is outside the u-LLaVA path (num_beams=1 everywhere)")
+        if no_repeat_ngram_size:
+            raise NotImplementedError("no_repeat_ngram_size is not supported on the B200 path")
+        ctx = self._ctx()
+        _, stack = self._engine()
+        stack.ensure()
+        B, P = input_ids.shape
+        if eos_token_id is None:
+            eos_token_id = getattr(self.config, "eos_token_id", None)
+        if isinstance(eos_token_id, (list, tuple)):
+            eos_token_id = eos_token_id[0] if eos_token_id else None
+        if pad_token_id is None:
+            pad_token_id = getattr(self.config, "pad_token_id", None)
+            if pad_token_id is None:
+                pad_token_id = eos_token_id if eos_token_id is not None else 0
+        self._check_mask(attention_mask, B, P)
+        H = self.config.hidden_size
+        T = P + max_new_tokens
+        cache = stack.new_cache(B, T)
+        table = self.model.embed_tokens.weight.detach()
+        w = self.lm_head.weight.detach()
+        V = w.shape[0]
+
+        _, embeds = self.embed_images_videos(input_ids, images, videos)
+        hidden = embeds.view(B * P, H)
+        final, _ = stack.run(ctx, hidden, cache, B, P)
+        hid_buf = None
+        if output_hidden_states:
+            hid_buf = torch.empty((B, T - 1, H), dtype=final.dtype, device=final.device)
+            hid_buf[:, :P] = final.view(B, P, H)
+        seqs = torch.full((B, T), pad_token_id, dtype=torch.int64, device=input_ids.device)
+        seqs[:, :P] = input_ids
+        logits = torch.empty((B, V), dtype=torch.float32, device=final.device)
+        last = final.view(B, P, H)[:, -1].contiguous()
+        finished = torch.zeros((B,), dtype=torch.bool, device=final.device)
+        step_hidden = torch.empty((B, H), dtype=final.dtype, device=final.device)
+        n_done = T
+        for t in range(max_new_tokens):
+            ctx.gemm(last, w, out=logits)
+            if do_sample and temperature and temperature > 0:
+                nxt = _sample(logits, temperature, top_p)
+            else:
+                nxt = ctx.argmax(logits)
+            if eos_token_id is not None:
+                nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
+                finished = finished | (nxt == eos_token_id)
+            seqs[:, P + t] = nxt
+            stop = False
+            if stopping_criteria is not None:
+                crit = stopping_criteria if isinstance(stopping_criteria, (list, tuple)) else list(stopping_criteria)
+                stop = any(bool(c(seqs[:, :P + t + 1], logits)) for c in crit)
+            if eos_token_id is not None and (t % 8 == 7 or stop) and bool(finished.all()):
+                stop = True
+            if stop or t == max_new_tokens - 1:
+                n_done = P + t + 1
+                break
+            step_in = ctx.embed_gather(nxt, table, out=step_hidden)
+            final, _ = stack.run(ctx, step_in, cache, B, 1)
+            if hid_buf is not None:
+                hid_buf[:, P + t] = final
+            last = final
+        seqs = seqs[:, :n_done]
+        if not return_dict_in_generate:
+            return seqs
+        hs = None
+        if output_hidden_states:
+            hs = ((hid_buf[:, : n_done - 1],),)
+        return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=cache)
+
+    def prepare_inputs_for_generation(self, input_ids=None, inputs_embeds=None, attention_mask=None, images=None,
+                                      videos=None, labels=None, past_key_values=None, **kwargs):
+        """Kept for API parity (reference :357-395); generate() above does not need it."""
+        if past_key_values:
+            input_ids = input_ids[:, -1:]
+        model_inputs = {"inputs_embeds": inputs_embeds} if (inputs_embeds is not None and past_key_values is None) \
+            else {"input_ids": input_ids}
+        model_inputs.update({"position_ids": kwargs.get("position_ids"), "past_key_values": past_key_values,
+                             "use_cache": kwargs.get("use_cache"), "attention_mask": attention_mask,
+                             "images": images, "videos": videos})
+        return model_inputs
+
+
+def _sample(logits: torch.Tensor, temperature: float, top_p: Optional[float]) -> torch.Tensor:
+    """Temperature / nucleus sampling on the device (HF TemperatureLogitsWarper + TopPLogitsWarper order).
+    Host-side glue on [B, V] fp32 logits; the default parity path is greedy (temperature=0)."""
+    scores = logits / temperature
+    if top_p is not None and top_p < 1.0:
+        sorted_logits, sorted_idx = torch.sort(scores, descending=False)
+        cum = sorted_logits.softmax(-1).cumsum(-1)
+        remove = cum <= (1 - top_p)
+        remove[..., -1:] = False
+        scores = scores.masked_fill(remove.scatter(1, sorted_idx, remove), float("-inf"))
+    return torch.multinomial(scores.softmax(-1), 1).squeeze(1)
+
+
+AutoConfig.register("ullava_core", UllavaCoreConfig)
+AutoModelForCausalLM.register(UllavaCoreConfig, UllavaCoreForCausalLM)
