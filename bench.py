@@ -1,0 +1,508 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the u-LLaVA inference hot path on B200 (contract: see DESIGN.md "Measurement").
+
+One step = UllavaForCausalLM.evaluate() on one batch of synthetic inputs per GPU:
+  336x336 image + 608-token prompt (576 visual + 32 text, one [SEG] in the prompt tail)
+  -> CLIP ViT-L/14-336 -> projector -> LLaMA-7B prefill -> 64 greedy tokens (KV cached) -> SAM ViT-H image
+  embedding -> [SEG] hidden state -> seg projector -> SAM mask decoder -> 336x336 mask logits,
+followed (N > 1) by the single all-gather of token ids + bit-packed masks.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels through the C ABI)
+  python bench.py --impl reference ...                     the CPU arm: oracle port of the reference on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "u-llava_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "images/sec (336px img + 32-tok prompt, 64-tok gen + mask)"
+UNIT = "images/s"
+IMG, SAM_IMG, N_PATCH, P_LEN = 336, 1024, 576, 608
+MM_IDS = dict(IMG_PATCH=32001, VID_PATCH=32002, IMG_START=32003, IMG_END=32004, VID_START=32005, VID_END=32006)
+SEG_ID, LOC_ID, VOCAB = 32007, 32008, 32011
+VISION = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=IMG,
+              patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+LLM = dict(vocab_size=VOCAB, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32,
+           num_key_value_heads=32, rms_norm_eps=1e-6, max_position_embeddings=2048, vision_config=VISION,
+           vision_hidden_layer=-2, projector_type="mlp", mm_token_ids=MM_IDS, bos_token_id=1, eos_token_id=None,
+           pad_token_id=32000)
+
+# algorithmic work per image (BASELINE.md section 4 / SURVEY.md section 8d)
+FLOP_VIT, FLOP_PROJ, FLOP_PREFILL_LAST = 366.0e9, 4.83e9, 7.97e12
+FLOP_SAM_ENC, FLOP_MASK_DEC = 5.67e12, 3.61e9
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=32)
+    ap.add_argument("--new-tokens", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+def make_prompt(global_index: int) -> torch.Tensor:
+    """[BOS] + 13 text + <img_beg> + 576 x <image_patch> + </img_end> + 16 text (one of them [SEG]) = 608 ids."""
+    g = torch.Generator().manual_seed(1234 + global_index)
+    head = torch.randint(3, 32000, (13,), generator=g)
+    tail = torch.randint(3, 32000, (16,), generator=g)
+    tail[11] = SEG_ID
+    ids = torch.cat([torch.tensor([1]), head, torch.tensor([MM_IDS["IMG_START"]]),
+                     torch.full((N_PATCH,), MM_IDS["IMG_PATCH"]), torch.tensor([MM_IDS["IMG_END"]]), tail])
+    assert ids.numel() == P_LEN
+    return ids
+
+
+def make_inputs(lo: int, hi: int, dtype):
+    """Pinned host tensors for global images lo..hi-1 (seeded per global index: world-size invariant)."""
+    n = hi - lo
+    ids = torch.stack([make_prompt(i) for i in range(lo, hi)]).pin_memory()
+    images = torch.empty((n, 3, IMG, IMG), dtype=dtype).pin_memory()
+    images_sam = torch.empty((n, 3, SAM_IMG, SAM_IMG), dtype=dtype).pin_memory()
+    for j, i in enumerate(range(lo, hi)):
+        g = torch.Generator().manual_seed(1234 + i)
+        images[j] = torch.randn((3, IMG, IMG), generator=g).to(dtype)
+        images_sam[j] = torch.randn((3, SAM_IMG, SAM_IMG), generator=g).to(dtype)
+    return ids, images, images_sam
+
+
+def build_model(device, dtype):
+    import models
+    cfg = models.UllavaConfig(llm_config=dict(LLM), seg_token_idx=SEG_ID, loc_token_idx=LOC_ID)
+    torch.manual_seed(0)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        with torch.device(device):
+            model = models.UllavaForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    model = model.eval().to(device=device, dtype=dtype)
+    # SAM's rel-pos tables are zero-initialised by the reference constructor; give them seeded values so the
+    # bias path does real work (a trained checkpoint has them non-zero)
+    g = torch.Generator(device=device).manual_seed(7)
+    for n_, p in model.visual_model.image_encoder.named_parameters():
+        if "rel_pos" in n_ or n_ == "pos_embed":
+            p.data.copy_((0.02 * torch.randn(p.shape, generator=g, device=device)).to(dtype))
+    return model
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference on the host cores (bounded sample, extrapolated per image)
+# ------------------------------------------------------------------------------------------------
+class CpuSample:
+    """Times full-width pieces of the reference algorithm (oracle/ullava_oracle.py, fp32, KV-cached greedy loop,
+    which is favourable to the reference: its shipped checkpoints decode with use_cache=False) and scales them to
+    one image of the bench workload:  2/23 CLIP layers, 1/32 LLaMA layers (prefill L=608 and 4 cached decode steps),
+    lm_head (all 608 prefill positions as the reference computes them, and per decode step), 1 windowed + 1 global
+    SAM ViT-H block of 32 (28 windowed + 4 global), patch embeds / neck / mask decoder / post-process in full."""
+
+    description = ("oracle port, fp32, B=1: 2 of 23 CLIP-L/14-336 layers, 1 of 32 LLaMA-7B layers (prefill L=608 + 4 "
+                   "KV-cached decode steps), lm_head V=32011, 1 windowed + 1 global of 32 SAM ViT-H blocks, full SAM "
+                   "mask decoder + post-process; scaled by layer/token counts to one image with 64 generated tokens")
+
+    def __init__(self):
+        from oracle.synth import synth_normal, synth_tensor
+        self.O = __import__("oracle.ullava_oracle", fromlist=["x"])
+        torch.set_grad_enabled(False)
+        st = lambda k, s: synth_tensor(k, s, 0)  # noqa: E731
+        sd = {}
+        # CLIP, 2 layers
+        vp = "vision_encoder.vision_model."
+        sd[vp + "embeddings.patch_embedding.weight"] = st("pe", (1024, 3, 14, 14))
+        sd[vp + "embeddings.class_embedding"] = st("cls", (1024,))
+        sd[vp + "embeddings.position_embedding.weight"] = st("pos", (577, 1024))
+        for nm in ("pre_layrnorm",):
+            sd[vp + nm + ".weight"] = st(nm + ".weight", (1024,)); sd[vp + nm + ".bias"] = st(nm + ".bias", (1024,))
+        for l in range(2):
+            q = vp + f"encoder.layers.{l}."
+            for nm, (o, i) in dict(q_proj=(1024, 1024), k_proj=(1024, 1024), v_proj=(1024, 1024),
+                                   out_proj=(1024, 1024)).items():
+                sd[q + f"self_attn.{nm}.weight"] = st(q + nm + ".weight", (o, i))
+                sd[q + f"self_attn.{nm}.bias"] = st(q + nm + ".bias", (o,))
+            for nm, (o, i) in dict(fc1=(4096, 1024), fc2=(1024, 4096)).items():
+                sd[q + f"mlp.{nm}.weight"] = st(q + nm + ".weight", (o, i)); sd[q + f"mlp.{nm}.bias"] = st(q + nm + ".bias", (o,))
+            for nm in ("layer_norm1", "layer_norm2"):
+                sd[q + nm + ".weight"] = st(q + nm + ".weight", (1024,)); sd[q + nm + ".bias"] = st(q + nm + ".bias", (1024,))
+        sd["vision_projector.weight"] = st("proj.weight", (4096, 1024)); sd["vision_projector.bias"] = st("proj.bias", (4096,))
+        # LLaMA, 1 layer + lm_head
+        p = "model.layers.0."
+        for nm, shp in {"self_attn.q_proj": (4096, 4096), "self_attn.k_proj": (4096, 4096), "self_attn.v_proj": (4096, 4096),
+                        "self_attn.o_proj": (4096, 4096), "mlp.gate_proj": (11008, 4096), "mlp.up_proj": (11008, 4096),
+                        "mlp.down_proj": (4096, 11008)}.items():
+            sd[p + nm + ".weight"] = st(p + nm, shp)
+        for nm in ("input_layernorm", "post_attention_layernorm"):
+            sd[p + nm + ".weight"] = st(p + nm + ".weight", (4096,))
+        sd["model.norm.weight"] = st("model.norm.weight", (4096,))
+        sd["lm_head.weight"] = st("lm_head.weight", (VOCAB, 4096))
+        # SAM ViT-H: 2 blocks (window, global) + patch embed + neck + prompt encoder / mask decoder
+        from tests.util_models import load_golden
+        _, meta = load_golden("sam_decoder")
+        for k, shp in meta["shapes"].items():
+            sd["visual_model." + k] = st(k, shp)
+        e = "visual_model.image_encoder."
+        sd[e + "patch_embed.proj.weight"] = st("sam.pe.w", (1280, 3, 16, 16)); sd[e + "patch_embed.proj.bias"] = st("sam.pe.bias", (1280,))
+        sd[e + "pos_embed"] = st("sam.pos_embed", (1, 64, 64, 1280))
+        for b, size in ((0, 14), (1, 64)):
+            q = e + f"blocks.{b}."
+            for nm, shp in {"norm1.weight": (1280,), "norm1.bias": (1280,), "norm2.weight": (1280,), "norm2.bias": (1280,),
+                            "attn.qkv.weight": (3840, 1280), "attn.qkv.bias": (3840,), "attn.proj.weight": (1280, 1280),
+                            "attn.proj.bias": (1280,), "attn.rel_pos_h": (2 * size - 1, 80), "attn.rel_pos_w": (2 * size - 1, 80),
+                            "mlp.lin1.weight": (5120, 1280), "mlp.lin1.bias": (5120,), "mlp.lin2.weight": (1280, 5120),
+                            "mlp.lin2.bias": (1280,)}.items():
+                sd[q + nm] = st(q + nm, shp)
+        sd[e + "neck.0.weight"] = st("neck0", (256, 1280, 1, 1)); sd[e + "neck.2.weight"] = st("neck2", (256, 256, 3, 3))
+        for i in (1, 3):
+            sd[e + f"neck.{i}.weight"] = st(f"neck{i}.weight", (256,)); sd[e + f"neck.{i}.bias"] = st(f"neck{i}.bias", (256,))
+        self.sd = sd
+        self.px = synth_normal("bench_px", (1, 3, IMG, IMG))
+        self.px_sam = synth_normal("bench_px_sam", (1, 3, SAM_IMG, SAM_IMG))
+        self.x = synth_normal("bench_x", (1, P_LEN, 4096))
+        self.text = synth_normal("bench_text", (1, 256))
+
+    @staticmethod
+    def _t(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        return time.perf_counter() - t0, r
+
+    def run_once(self, new_tokens: int) -> dict:
+        O, sd = self.O, self.sd
+        import torch.nn.functional as F
+        vc = dict(VISION, num_hidden_layers=2)
+        t_clip0, _ = self._t(lambda: O.clip_vit_hidden(sd, "vision_encoder.", self.px, vc, 0))
+        t_clip2, h = self._t(lambda: O.clip_vit_hidden(sd, "vision_encoder.", self.px, vc, 2))
+        t_proj, _ = self._t(lambda: F.linear(h[:, 1:], sd["vision_projector.weight"], sd["vision_projector.bias"]))
+        lc = dict(hidden_size=4096, num_attention_heads=32, num_key_value_heads=32, num_hidden_layers=1)
+        t_pre, (hl, past, _) = self._t(lambda: O.llama_layers(sd, self.x, lc))
+        t_head_all, _ = self._t(lambda: F.linear(hl, sd["lm_head.weight"]))
+        t_dec = 0.0
+        for _ in range(4):
+            dt, (h1, past, _) = self._t(lambda: O.llama_layers(sd, self.x[:, :1], lc, past=past))
+            t_dec += dt / 4
+        t_head1, _ = self._t(lambda: F.linear(h1, sd["lm_head.weight"]))
+        ew = dict(embed_dim=1280, depth=1, num_heads=16, global_attn_indexes=[], window_size=14, patch_size=16)
+        e0 = dict(ew, depth=0)
+        t_s0, _ = self._t(lambda: O.sam_image_encoder(sd, "visual_model.", self.px_sam, e0))
+        t_sw, emb = self._t(lambda: O.sam_image_encoder(sd, "visual_model.", self.px_sam, ew))
+        sdg = dict(sd)
+        for k in list(sd):
+            if ".blocks.1." in k:
+                sdg[k.replace(".blocks.1.", ".blocks.0.")] = sd[k]
+        eg = dict(ew, global_attn_indexes=[0])
+        t_sg, _ = self._t(lambda: O.sam_image_encoder(sdg, "visual_model.", self.px_sam, eg))
+        t_md, (masks, _) = self._t(lambda: O.sam_mask_decoder(sd, "visual_model.", emb, self.text))
+        t_post, _ = self._t(lambda: O.postprocess_masks(masks[:, 0:1], (SAM_IMG, SAM_IMG), (IMG, IMG)))
+        per_image = (t_clip0 + (t_clip2 - t_clip0) / 2 * 23 + t_proj + 32 * t_pre + t_head_all +
+                     (new_tokens - 1) * (32 * t_dec + t_head1) + t_s0 + 28 * max(t_sw - t_s0, 0) + 4 * max(t_sg - t_s0, 0) +
+                     t_md + t_post)
+        return dict(per_image_s=per_image, parts=dict(clip2=t_clip2, prefill_layer=t_pre, lm_head_prefill=t_head_all,
+                                                      decode_layer=t_dec, lm_head_step=t_head1, sam_window_block=t_sw - t_s0,
+                                                      sam_global_block=t_sg - t_s0, sam_embed_neck=t_s0, mask_decoder=t_md,
+                                                      postprocess=t_post))
+
+
+def config_dict(args, world_size):
+    return {"workload": f"c5 shard: full u-LLaVA-7B pipeline (CLIP ViT-L/14-336 + projector + LLaMA-7B prefill 608 + "
+                        f"{args.new_tokens} greedy tokens + SAM ViT-H + mask decoder), {args.batch_per_gpu} images per GPU",
+            "global_batch": args.batch_per_gpu * world_size, "batch_per_gpu": args.batch_per_gpu, "prompt_len": P_LEN,
+            "new_tokens": args.new_tokens, "image": IMG, "sam_image": SAM_IMG, "parallelism": f"dp{world_size}",
+            "l2": "inputs larger than L2 (13.5 GB of weights stream through every step)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cpu = CpuSample()
+    for _ in range(min(args.warmup, 1)):
+        cpu.run_once(args.new_tokens)
+    t0 = time.perf_counter()
+    rs = [cpu.run_once(args.new_tokens) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    per_image = statistics.median(r["per_image_s"] for r in rs)
+    v = 1.0 / per_image
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, ws),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": CpuSample.description, "host_cpus": os.cpu_count(), "parts_s": rs[-1]["parts"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import native
+    import dist_eval
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16
+    B = args.batch_per_gpu
+    lo, hi = rank * B, (rank + 1) * B
+    ctx = native.Context.get(local)
+    model = build_model(dev, dtype)
+    model.pack_mask_bits = True
+    h_ids, h_img, h_sam = make_inputs(lo, hi, dtype)
+    sizes = [(IMG, IMG)] * B
+    resizes = [(SAM_IMG, SAM_IMG)] * B
+    words = (IMG * IMG + 31) // 32
+    T = P_LEN + args.new_tokens
+    MAX_MASKS = 2
+    graph_launches = [0]
+
+    def core(ids, img, sam):
+        out_ids, masks, boxes = model.evaluate(sam, img, ids, sizes, resizes, max_new_tokens=args.new_tokens,
+                                               temperature=0)
+        payload = dist_eval.pack_results(out_ids, model.last_mask_bits, MAX_MASKS, words)
+        gathered = dist_eval.all_gather_results(payload, [B] * ws)
+        return out_ids, masks, gathered
+
+    d_ids, d_img, d_sam = h_ids.to(dev), h_img.to(dev), h_sam.to(dev)
+
+    def step_resident():
+        return core(d_ids, d_img, d_sam)
+
+    h_out_ids = torch.empty((B, T), dtype=torch.int64).pin_memory()
+    h_masks = torch.empty((B, IMG, IMG), dtype=torch.float32).pin_memory()
+    h_gather = torch.empty((B * ws, 1 + 2 * T + MAX_MASKS * words), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        ids = h_ids.to(dev, non_blocking=True)
+        img = h_img.to(dev, non_blocking=True)
+        sam = h_sam.to(dev, non_blocking=True)
+        out_ids, masks, gathered = core(ids, img, sam)
+        h_out_ids.copy_(out_ids, non_blocking=True)
+        h_masks.copy_(torch.stack([m[0] for m in masks]), non_blocking=True)
+        h_gather.copy_(gathered, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the host owns the result before the next step starts
+        return out_ids, masks, gathered
+
+    def timed(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ctx.launch_count() + model.llm.graph_kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if ws > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ctx.launch_count() + model.llm.graph_kernel_launches() - n0, r
+
+    sampler = ClockSampler(physical_gpu_index(local))
+    if rank == 0:
+        sampler.start()
+    ms_res, launches, res = timed(step_resident, args.warmup, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, res2 = timed(step_e2e, 1, args.steps)
+
+    out_ids, masks, gathered = res
+    assert out_ids.shape == (B, T), out_ids.shape
+    n_masks = sum(int(m.shape[0]) for m in masks)
+    assert n_masks >= B, "every image must produce at least one mask"
+    assert gathered.shape[0] == B * ws
+
+    # ---- stage timeline + per-kernel-class CUDA-event profile of one more step (not part of the timed runs) ----
+    stages, prof = None, None
+    if not args.no_stages:
+        model.timeline = []
+        step_resident()
+        torch.cuda.synchronize()
+        tl = model.timeline
+        model.timeline = None
+        stages = {tl[i][0]: tl[i - 1][1].elapsed_time(tl[i][1]) for i in range(1, len(tl))}
+        model.llm.use_cuda_graph = False
+        ctx.profile_begin()
+        step_resident()
+        torch.cuda.synchronize()
+        prof = ctx.profile_end()
+        model.llm.use_cuda_graph = True
+
+    if ws > 1:
+        dist.barrier()
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks_src = "measured (MEASURED_PEAKS.json)"
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            peaks = json.load(f)
+    else:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+        peaks_src = "fallback (B200_PROFILING.md)"
+
+    images = B * ws * args.steps
+    value = images / (ms_res / 1e3)
+    e2e_v = images / (ms_e2e / 1e3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (seeded random weights, N(0,1) images, random prompt ids)",
+            "config": config_dict(args, ws), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h_ids.numel() * 8 + h_img.numel() * 2 + h_sam.numel() * 2),
+                    "d2h_bytes_per_step": int(h_out_ids.numel() * 8 + h_masks.numel() * 4 + h_gather.numel() * 4)},
+            "masks_per_step": n_masks}
+    if stages:
+        line["stages_ms"] = {k: round(v, 3) for k, v in stages.items()}
+    if prof:
+        gt, gs = prof["gemm_tensor"], prof["gemm_stream"]
+        line["kernel_classes"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                      "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1),
+                                      "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)}
+                                  for k, v in prof.items() if v["launches"]}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
+        a_t = gt["flops"] / max(gt["ms"], 1e-9) / 1e9
+        line["roofline"] = {"kernel": "gemm_tcgen05_kernel (large-M, prefill / ViT / SAM-decoder GEMMs)",
+                            "bound": "tensor", "achieved": a_t, "peak": peaks["bf16_tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": a_t / peaks["bf16_tflops_sustained"],
+                            "traffic": (traffic or {}).get("gemm_tensor"), "launches": gt["launches"],
+                            "avg_launch_ms": gt["ms"] / max(gt["launches"], 1), "peak_source": peaks_src + ", sustained"}
+        a_s = gs["bytes"] / max(gs["ms"], 1e-9) / 1e6
+        line["roofline_decode"] = {"kernel": "gemm_tcgen05_kernel swap-AB + splitk_reduce (decode weight streaming)",
+                                   "bound": "hbm", "achieved": a_s, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": a_s / peaks["hbm_gbs"], "traffic": (traffic or {}).get("gemm_stream"),
+                                   "launches": gs["launches"], "avg_launch_ms": gs["ms"] / max(gs["launches"], 1),
+                                   "peak_source": peaks_src}
+        if stages and "prefill" in stages and "vit_projector_splice" in stages:
+            fl = B * (FLOP_VIT + FLOP_PROJ + FLOP_PREFILL_LAST)
+            sec = (stages["prefill"] + stages["vit_projector_splice"]) / 1e3
+            line["vit_prefill"] = {"tflops": fl / sec / 1e12, "frac_of_burst_peak": fl / sec / 1e12 / peaks["bf16_tflops"],
+                                   "frac_of_sustained_peak": fl / sec / 1e12 / peaks["bf16_tflops_sustained"],
+                                   "batch": B, "ms": sec * 1e3}
+    if not args.no_cpu_baseline and ws == 1:
+        cpu = CpuSample()
+        r = cpu.run_once(args.new_tokens)
+        line["cpu_baseline"] = {"value": 1.0 / r["per_image_s"], "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": CpuSample.description, "host_cpus": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

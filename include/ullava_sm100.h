@@ -72,6 +72,23 @@ ULLAVA_API int ullava_set_workspace(ullava_ctx* ctx, void* ptr, size_t bytes);
 /* Number of kernels this context has enqueued so far (bench.py's gpu_launches). */
 ULLAVA_API int64_t ullava_launch_count(ullava_ctx* ctx);
 
+/* CUDA-event profiler by kernel class (bench.py's live roofline measurement).  Between begin and end every
+ * kernel-launching entry point brackets its launches with events on the caller's stream; end synchronises
+ * and fills out[ULLAVA_PROF_CLASSES][4] = {milliseconds, algorithmic FLOPs, algorithmic bytes, launches}.
+ * Not usable during CUDA-graph capture. */
+enum ullava_prof_class {
+  ULLAVA_PROF_GEMM_TENSOR = 0,  /* large-M tcgen05 GEMM (tensor-pipe bound) */
+  ULLAVA_PROF_GEMM_STREAM = 1,  /* small-M swap-AB weight-streaming GEMM + split-K reduce (HBM bound) */
+  ULLAVA_PROF_ATTN_PREFILL = 2,
+  ULLAVA_PROF_ATTN_DECODE = 3,
+  ULLAVA_PROF_NORM = 4,
+  ULLAVA_PROF_GLUE = 5,         /* im2col, gather/splice/copy, RoPE + KV scatter, argmax */
+  ULLAVA_PROF_SAM = 6           /* SAM decoder-specific kernels (token transposes, hyper-mask, post-process) */
+};
+#define ULLAVA_PROF_CLASSES 8
+ULLAVA_API int ullava_profile_begin(ullava_ctx* ctx);
+ULLAVA_API int ullava_profile_end(ullava_ctx* ctx, double* out);
+
 /* ---- GEMM: D[M,N] = act(A[M,K] * B[N,K]^T + bias[N]) + residual[M,N] ------------------
  * Replaces torch.nn.Linear at every call site of the path (CLIP / LLaMA / projector / lm_head /
  * seg & det projectors).  A, B: 16-bit row-major, lda/ldb in elements (multiples of 8).
@@ -229,6 +246,31 @@ typedef struct ullava_llama_args {
 } ullava_llama_args;
 ULLAVA_API int ullava_llama_forward(ullava_ctx* ctx, const ullava_llama_args* args, void* stream);
 ULLAVA_API size_t ullava_llama_scratch_bytes(int32_t rows, int32_t hidden_size, int32_t ffn);
+
+/* One greedy decode step, CUDA-graph replayable: the position of the token being processed is read from
+ * device memory (*pos_dev = number of tokens already in the KV cache) and incremented by the last kernel.
+ *   hidden <- embed_table[cur_ids]; decoder stack (seq 1, llama.pos0 ignored); final norm; logits = lm_head(final);
+ *   next = argmax(logits) (pad once finished; eos sets finished); cur_ids <- next; seqs[b][pos+1] <- next;
+ *   hid_buf[b][pos] <- final (post-norm hidden state, what UllavaForCausalLM.evaluate gathers for [SEG]).
+ * One iteration of the generate loop of models/ullava.py:350-362 / models/ullava_core.py:357-395. */
+typedef struct ullava_decode_args {
+  ullava_llama_args llama;      /* seq == 1, final_out != NULL */
+  int32_t* pos_dev;             /* device int32 scalar */
+  const void* embed_table; int32_t vocab;   /* [vocab, H] 16-bit */
+  const void* lm_head;          /* [vocab, H] 16-bit */
+  int64_t* cur_ids;             /* device [B]: in = token to process, out = next token */
+  float* logits;                /* device [B, vocab] fp32 */
+  int64_t* seqs; int64_t seqs_ld;           /* device [B, seqs_ld] or NULL */
+  void* hid_buf; int64_t hid_bs;            /* device [B, hid_bs / H, H] 16-bit or NULL (hid_bs in elements) */
+  uint8_t* finished;            /* device [B] or NULL */
+  int32_t eos_id, pad_id;       /* eos_id < 0: never stop */
+} ullava_decode_args;
+ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, void* stream);
+/* The bookkeeping tail of a step on its own (used once after the prefill, with *pos_dev = P - 1):
+ * argmax + eos/pad handling, cur_ids / seqs[b][pos+1] / hid_buf[b][pos] updates, ++*pos_dev. */
+ULLAVA_API int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, int64_t* cur_ids,
+                       int64_t* seqs, int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
+                       uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, void* stream);
 
 #ifdef __cplusplus
 }

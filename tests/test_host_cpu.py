@@ -1,0 +1,142 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/ullava_sm100.h declares, the
+host-side mirror keeps the reference's module API / state_dict keys, and the host logic of the sharded eval
+path (shard ranges, result packing, the single all-gather under gloo with world_size 2)."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import native
+    hdr = open(os.path.join(ROOT, "include", "ullava_sm100.h")).read()
+    declared = set(re.findall(r"ULLAVA_API\s+[\w\s\*]+?\b(ullava_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    assert declared == set(native.exported_symbols()), declared ^ set(native.exported_symbols())
+    lib = native.load_library()  # dlopen; raises if the .so is missing (no fallback)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ullava_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the C structs: spot-check sizes against the natural C layout."""
+    import ctypes as C
+    import native
+    assert C.sizeof(native.GemmArgs) == 8 * 9 + 4 * 9 + 4  # 9 pointers/int64, 9 int32, tail padding
+    assert C.sizeof(native.AttnArgs) == 16 * 8 + 4 * 9 + 4
+    assert C.sizeof(native.DecodeArgs) > C.sizeof(native.LlamaArgs)
+
+
+def test_no_cuda_means_loud_failure():
+    import native
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(native.NativeError):
+        native.Context(0)
+
+
+def test_state_dict_keys_match_reference():
+    """tests/golden/*.json hold the state_dict key/shape lists of the REAL reference modules."""
+    from tests.util_models import build_tiny_core, build_tiny_full, load_golden
+    m, _, _ = build_tiny_core(torch.float32, device="cpu")  # strict=True load inside
+    _, meta = load_golden("tiny_core")
+    assert set(m.state_dict().keys()) == set(meta["shapes"].keys())
+    m, _, _ = build_tiny_full(torch.float32, device="cpu")
+    _, meta = load_golden("tiny_full")
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(meta["shapes"].keys())
+    for k, shp in meta["shapes"].items():
+        assert list(sd[k].shape) == list(shp), k
+    for attr in ("llm", "seg_projector", "det_projector", "det_decoder", "visual_model"):
+        assert hasattr(m, attr)
+    for attr in ("model", "lm_head", "vision_encoder", "vision_projector", "generate", "encode_image"):
+        assert hasattr(m.llm, attr)
+    for attr in ("image_encoder", "prompt_encoder", "mask_decoder", "postprocess_masks", "preprocess"):
+        assert hasattr(m.visual_model, attr)
+
+
+def test_config_roundtrip(tmp_path):
+    import models
+    from tests import configs as C
+    cfg = models.UllavaConfig(llm_config=dict(C.TINY_LLM), seg_token_idx=C.SEG_ID, loc_token_idx=C.LOC_ID)
+    d = cfg.to_dict()
+    assert d["model_type"] == "ullava" and d["llm_config"]["model_type"] == "ullava_core"
+    assert d["llm_config"]["vision_config"]["hidden_size"] == 64
+    cfg.save_pretrained(tmp_path)
+    back = models.UllavaConfig.from_pretrained(tmp_path)
+    assert back.seg_token_idx == C.SEG_ID and back.llm_config.vision_hidden_layer == -2
+    assert back.llm_config.mm_token_ids["IMG_START"] == C.MM_IDS["IMG_START"]
+    from transformers import AutoConfig
+    assert isinstance(AutoConfig.from_pretrained(tmp_path), models.UllavaConfig)
+
+
+def test_interleave_gate_up_layout():
+    from models.engine import interleave_gate_up
+    g = torch.arange(32 * 3, dtype=torch.float32).view(32, 3)
+    u = -g
+    w = interleave_gate_up(g, u)
+    assert w.shape == (64, 3)
+    assert torch.equal(w[:16], g[:16]) and torch.equal(w[16:32], u[:16])
+    assert torch.equal(w[32:48], g[16:]) and torch.equal(w[48:], u[16:])
+
+
+def test_shard_ranges_cover_batch():
+    from dist_eval import shard_range
+    for gb, ws in ((256, 8), (10, 4), (3, 8), (32, 1)):
+        spans = [shard_range(gb, r, ws) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        for a, b in zip(spans, spans[1:]):
+            assert a[1] == b[0]
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_unpack_results_roundtrip():
+    from dist_eval import pack_results, unpack_bits, unpack_results
+    g = torch.Generator().manual_seed(0)
+    B, T, h, w = 3, 9, 5, 13
+    words = (h * w + 31) // 32
+    ids = torch.randint(0, 2 ** 40, (B, T), generator=g)
+    masks = [torch.rand((n, h, w), generator=g) > 0.5 for n in (1, 0, 2)]
+    bits = []
+    for m in masks:
+        flat = torch.zeros((m.shape[0], words * 32), dtype=torch.bool)
+        flat[:, : h * w] = m.reshape(m.shape[0], h * w)
+        wv = (flat.view(m.shape[0], words, 32).long() << torch.arange(32)).sum(-1)
+        bits.append(torch.where(wv >= 2 ** 31, wv - 2 ** 32, wv).to(torch.int32))
+    payload = pack_results(ids, bits, 2, words)
+    ids2, bits2 = unpack_results(payload, T, 2, words)
+    assert torch.equal(ids, ids2)
+    for m, b in zip(masks, bits2):
+        assert torch.equal(unpack_bits(b, h, w), m)
+
+
+def _gather_worker(rank, ws, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "u-llava_b200")]
+    import torch.distributed as dist
+    from dist_eval import all_gather_results, shard_range
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    gb = 5  # ragged: shards of 3 and 2
+    lo, hi = shard_range(gb, rank, ws)
+    payload = torch.arange(lo, hi, dtype=torch.int32)[:, None] * 100 + torch.arange(7, dtype=torch.int32)[None]
+    sizes = [shard_range(gb, r, ws)[1] - shard_range(gb, r, ws)[0] for r in range(ws)]
+    out = all_gather_results(payload, sizes)
+    expect = torch.arange(gb, dtype=torch.int32)[:, None] * 100 + torch.arange(7, dtype=torch.int32)[None]
+    ret[rank] = bool(torch.equal(out, expect))
+    dist.destroy_process_group()
+
+
+def test_all_gather_results_gloo_world2():
+    ws = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gather_worker, args=(ws, port, ret), nprocs=ws, join=True)
+    assert ret[0] and ret[1]

@@ -271,6 +271,7 @@ static int flash_launch(const FlashParams& p, int batch, int heads, cudaStream_t
 }
 
 int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_ATTN_PREFILL, (a.causal ? 2.0 : 4.0) * a.batch * a.heads * (double)a.seq_q * a.seq_k * a.head_dim, 2.0 * a.batch * a.heads * a.head_dim * (2.0 * a.seq_q + 2.0 * a.seq_k));
   ULLAVA_REQUIRE(a.q && a.k && a.v && a.o, "attention: null pointer");
   ULLAVA_REQUIRE(a.batch >= 0 && a.heads > 0 && a.seq_q >= 0 && a.seq_k > 0, "attention: bad shape");
   const int64_t strides[] = {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs};
@@ -317,7 +318,8 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ kc, const T* __restrict__ vc,
                    int64_t cache_bs, int64_t cache_hs, T* __restrict__ o, int64_t o_bs, int ctx_len,
-                   float scale_log2) {
+                   float scale_log2, const int32_t* __restrict__ ctx_dev) {
+  if (ctx_dev) ctx_len = *ctx_dev + 1;  // CUDA-graph decode: keys 0..pos are attended, pos read from device memory
   extern __shared__ float dec_smem[];   // [ctx_len] scores, then [groups][HD] partial outputs
   __shared__ float red[DEC_THREADS / 32];
   __shared__ float bcast[2];
@@ -425,9 +427,10 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
 template <typename T, int HD>
 static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const int32_t* ctx_dev, int max_ctx) {
   constexpr int GROUPS = DEC_THREADS / (HD / 8);
-  size_t smem = sizeof(float) * static_cast<size_t>(ctx_len > GROUPS * HD ? ctx_len : GROUPS * HD);
+  const int smem_ctx = ctx_dev ? max_ctx : ctx_len;  // with a device-side length the buffer covers the whole cache
+  size_t smem = sizeof(float) * static_cast<size_t>(smem_ctx > GROUPS * HD ? smem_ctx : GROUPS * HD);
   auto kern = attn_decode_kernel<T, HD>;
   if (smem > 48 * 1024) {
     ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -435,20 +438,23 @@ static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void
   dim3 grid(heads, batch);
   kern<<<grid, DEC_THREADS, smem, stream>>>(static_cast<const T*>(q), q_bs, static_cast<const T*>(kc),
                                             static_cast<const T*>(vc), cache_bs, cache_hs, static_cast<T*>(o), o_bs,
-                                            ctx_len, scale * 1.4426950408889634f);
+                                            ctx_len, scale * 1.4426950408889634f, ctx_dev);
   return check_cuda(cudaGetLastError(), "attn_decode launch");
 }
 
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
-                         float scale, int dtype, cudaStream_t stream) {
+                         float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev, int max_ctx) {
+  if (ctx_dev) ctx_len = max_ctx;
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_ATTN_DECODE, 4.0 * batch * heads * (double)ctx_len * head_dim, 4.0 * batch * heads * (double)ctx_len * head_dim);
   ULLAVA_REQUIRE(q && kc && vc && o, "attention_decode: null pointer");
   ULLAVA_REQUIRE(ctx_len > 0 && ctx_len <= 16384, "attention_decode: ctx_len %d out of range", ctx_len);
   ULLAVA_REQUIRE(q_bs % 8 == 0 && cache_bs % 8 == 0 && cache_hs % 8 == 0, "attention_decode: bad strides");
   if (batch == 0) return OK;
   int st;
 #define ULLAVA_DEC(TT, HDIM) \
-  st = decode_launch<TT, HDIM>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream)
+  st = decode_launch<TT, HDIM>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream, \
+                               ctx_dev, max_ctx)
   if (dtype == DT_BF16) {
     if (head_dim == 128) ULLAVA_DEC(__nv_bfloat16, 128);
     else if (head_dim == 64) ULLAVA_DEC(__nv_bfloat16, 64);

@@ -117,6 +117,20 @@ int ullava_llama_forward(ullava_ctx* ctx, const ullava_llama_args* args, void* s
   return llama_forward_run(ctx, *args, static_cast<cudaStream_t>(stream));
 }
 
+int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, void* stream) {
+  CTX_CHECK("ullava_llama_decode_step");
+  if (!args) { set_last_error("ullava_llama_decode_step: args is NULL"); return ERR_BAD_ARG; }
+  return llama_decode_step_run(ctx, *args, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, int64_t* cur_ids,
+                       int64_t* seqs, int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
+                       uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, void* stream) {
+  CTX_CHECK("ullava_greedy_step");
+  return greedy_step_run(ctx, logits, ld, rows, cols, cur_ids, seqs, seqs_ld, final_h, hid_buf, hid_bs, hdim, finished,
+                         eos_id, pad_id, pos_dev, static_cast<cudaStream_t>(stream));
+}
+
 size_t ullava_llama_scratch_bytes(int32_t rows, int32_t hidden_size, int32_t ffn) {
   return llama_scratch(rows, hidden_size, ffn);
 }

@@ -14,7 +14,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rope_kvcache_kernel(T* __restrict__ qkv, int64_t ld, T* __restrict__ kc, T* __restrict__ vc, int64_t cache_bs,
                     int64_t cache_hs, int seq, int heads, int hd, int pos0, const float* __restrict__ cos_t,
-                    const float* __restrict__ sin_t) {
+                    const float* __restrict__ sin_t, const int32_t* __restrict__ pos_dev) {
+  if (pos_dev) pos0 = *pos_dev;  // CUDA-graph decode: the position lives in device memory
   const int row = blockIdx.x;
   const int b = row / seq, s = row - b * seq;
   const int pos = pos0 + s;
@@ -63,7 +64,8 @@ rope_kvcache_kernel(T* __restrict__ qkv, int64_t ld, T* __restrict__ kc, T* __re
 
 int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld, void* kc, void* vc, int64_t cache_bs, int64_t cache_hs,
                      int batch, int seq, int heads, int hd, int pos0, const float* cos_t, const float* sin_t,
-                     int dtype, cudaStream_t stream) {
+                     int dtype, cudaStream_t stream, const int32_t* pos_dev) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 2.0 * batch * seq * 3.0 * heads * hd * 2.0);
   ULLAVA_REQUIRE(qkv && kc && vc && cos_t && sin_t, "rope: null pointer");
   ULLAVA_REQUIRE(hd % 16 == 0 && ld % 8 == 0 && cache_bs % 8 == 0 && cache_hs % 8 == 0, "rope: bad alignment");
   const int rows = batch * seq;
@@ -71,11 +73,11 @@ int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld, void* kc, void* vc, in
   if (dtype == DT_BF16)
     rope_kvcache_kernel<__nv_bfloat16><<<rows, 256, 0, stream>>>(
         static_cast<__nv_bfloat16*>(qkv), ld, static_cast<__nv_bfloat16*>(kc), static_cast<__nv_bfloat16*>(vc),
-        cache_bs, cache_hs, seq, heads, hd, pos0, cos_t, sin_t);
+        cache_bs, cache_hs, seq, heads, hd, pos0, cos_t, sin_t, pos_dev);
   else if (dtype == DT_F16)
     rope_kvcache_kernel<__half><<<rows, 256, 0, stream>>>(static_cast<__half*>(qkv), ld, static_cast<__half*>(kc),
                                                           static_cast<__half*>(vc), cache_bs, cache_hs, seq, heads,
-                                                          hd, pos0, cos_t, sin_t);
+                                                          hd, pos0, cos_t, sin_t, pos_dev);
   else { set_last_error("rope: unsupported dtype"); return ERR_UNSUPPORTED; }
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "rope_kvcache launch");
@@ -109,6 +111,7 @@ im2col_kernel(const T* __restrict__ px, T* __restrict__ out, int img, int patch,
 
 int vit_im2col_run(Context* ctx, const void* pixels, void* out, int batch, int img, int patch, int k_pad, int dtype,
                    cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 2.0 * batch * (3.0 * img * img + (double)(img / patch) * (img / patch) * k_pad));
   ULLAVA_REQUIRE(pixels && out, "im2col: null pointer");
   ULLAVA_REQUIRE(img % patch == 0 && k_pad >= 3 * patch * patch, "im2col: bad geometry");
   const int g = img / patch;
@@ -154,6 +157,7 @@ vit_assemble_kernel(const T* __restrict__ pe, const T* __restrict__ cls, const T
 
 int vit_assemble_run(Context* ctx, const void* pe, const void* cls, const void* pos, void* out, int batch, int np,
                      int dim, int dtype, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * batch * (np + 1.0) * dim);
   ULLAVA_REQUIRE(pe && cls && pos && out, "vit_assemble: null pointer");
   ULLAVA_REQUIRE(dim % 8 == 0, "vit_assemble: dim must be a multiple of 8");
   if (batch == 0) return OK;
@@ -191,6 +195,7 @@ copy_rows_kernel(const uint16_t* __restrict__ src, int64_t sbs, int64_t srs, uin
 
 int copy_rows_run(Context* ctx, const void* src, int64_t sbs, int64_t srs, void* dst, int64_t dbs, int64_t drs,
                   int batch, int rows, int cols, int dtype, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * batch * rows * cols);
   ULLAVA_REQUIRE(src && dst, "copy_rows: null pointer");
   ULLAVA_REQUIRE(dtype == DT_BF16 || dtype == DT_F16, "copy_rows: 16-bit dtypes only");
   if (batch == 0 || rows == 0 || cols == 0) return OK;
@@ -219,6 +224,7 @@ embed_gather_kernel(const int64_t* __restrict__ ids, const uint16_t* __restrict_
 
 int embed_gather_run(Context* ctx, const int64_t* ids, const void* table, void* out, int rows, int dim, int vocab,
                      int dtype, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * rows * dim);
   ULLAVA_REQUIRE(ids && table && out, "embed_gather: null pointer");
   ULLAVA_REQUIRE(dim % 8 == 0, "embed_gather: dim must be a multiple of 8");
   ULLAVA_REQUIRE(dtype == DT_BF16 || dtype == DT_F16, "embed_gather: 16-bit dtypes only");
@@ -242,6 +248,7 @@ splice_rows_kernel(uint16_t* __restrict__ embeds, const uint16_t* __restrict__ f
 
 int splice_rows_run(Context* ctx, void* embeds, const void* feats, const int32_t* start, int batch, int seq,
                     int n_patch, int dim, int dtype, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * batch * n_patch * dim);
   ULLAVA_REQUIRE(embeds && feats && start, "splice_rows: null pointer");
   ULLAVA_REQUIRE(dim % 8 == 0, "splice_rows: dim must be a multiple of 8");
   ULLAVA_REQUIRE(dtype == DT_BF16 || dtype == DT_F16, "splice_rows: 16-bit dtypes only");
@@ -290,7 +297,83 @@ argmax_kernel(const float* __restrict__ logits, int64_t ld, int64_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-side bookkeeping of one greedy decode step (CUDA-graph replayable: the position is read from
+// device memory).  pos = index of the token that was just processed.
+//   greedy_step_kernel : next = argmax(logits[b]); finished/eos/pad handling; cur_ids[b] = next;
+//                        seqs[b][pos + 1] = next; hid_buf[b][pos] = final[b]
+//   advance_pos_kernel : ++*pos  (last node of the step)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+greedy_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, int64_t* __restrict__ cur_ids,
+                   int64_t* __restrict__ seqs, int64_t seqs_ld, const uint16_t* __restrict__ final_h,
+                   uint16_t* __restrict__ hid_buf, int64_t hid_bs, int hdim, uint8_t* __restrict__ finished,
+                   int eos_id, int pad_id, const int32_t* __restrict__ pos_dev) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int b = blockIdx.x;
+  const int pos = *pos_dev;
+  if (hid_buf) {
+    const uint4* src = reinterpret_cast<const uint4*>(final_h + static_cast<int64_t>(b) * hdim);
+    uint4* dst = reinterpret_cast<uint4*>(hid_buf + b * hid_bs + static_cast<int64_t>(pos) * hdim);
+    for (int v = threadIdx.x; v < hdim / 8; v += blockDim.x) dst[v] = src[v];
+  }
+  const float* row = logits + b * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = row[c];
+    if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    best = l < nw ? sv[l] : -INFINITY;
+    bi = l < nw ? si[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (l == 0) {
+      int64_t nxt = (bi == 0x7fffffff) ? 0 : bi;
+      if (finished) {
+        if (finished[b]) nxt = pad_id;
+        else if (eos_id >= 0 && nxt == eos_id) finished[b] = 1;
+      }
+      cur_ids[b] = nxt;
+      if (seqs) seqs[b * seqs_ld + pos + 1] = nxt;
+    }
+  }
+}
+
+__global__ void advance_pos_kernel(int32_t* pos) { *pos += 1; }
+
+int greedy_step_run(Context* ctx, const float* logits, int64_t ld, int rows, int cols, int64_t* cur_ids, int64_t* seqs,
+                    int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int hdim, uint8_t* finished,
+                    int eos_id, int pad_id, int32_t* pos_dev, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * rows * cols);
+  ULLAVA_REQUIRE(logits && cur_ids && pos_dev && cols > 0 && hdim % 8 == 0, "greedy_step: bad arguments");
+  if (rows == 0) return OK;
+  greedy_step_kernel<<<rows, 1024, 0, stream>>>(logits, ld, cols, cur_ids, seqs, seqs_ld,
+                                                static_cast<const uint16_t*>(final_h), static_cast<uint16_t*>(hid_buf),
+                                                hid_bs, hdim, finished, eos_id, pad_id, pos_dev);
+  advance_pos_kernel<<<1, 1, 0, stream>>>(pos_dev);
+  ctx->launches += 2;
+  return check_cuda(cudaGetLastError(), "greedy_step launch");
+}
+
 int argmax_run(Context* ctx, const float* logits, int64_t ld, int64_t* out, int rows, int cols, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * rows * cols);
   ULLAVA_REQUIRE(logits && out && cols > 0, "argmax: bad arguments");
   if (rows == 0) return OK;
   argmax_kernel<<<rows, 1024, 0, stream>>>(logits, ld, out, cols);

@@ -507,6 +507,10 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
 
   // Small-M products: swap operands so the weight matrix feeds the 128-row side.
   const bool swap = (a.M <= 32) && (a.N >= 128) && !a.no_swap;
+  const double out_cols = a.epilogue == EPI_SILU_MUL ? a.N / 2.0 : a.N;
+  ProfScope _ps(ctx, stream, swap ? ULLAVA_PROF_GEMM_STREAM : ULLAVA_PROF_GEMM_TENSOR, 2.0 * a.M * a.N * a.K,
+                2.0 * (static_cast<double>(a.M) * a.K + static_cast<double>(a.N) * a.K) +
+                    (a.out_f32 ? 4.0 : 2.0) * a.M * out_cols);
   GemmKernelParams p{};
   p.kb_total = kb_total;
   p.epilogue = a.epilogue;

@@ -121,7 +121,8 @@ size_t llama_scratch(int rows, int hidden, int ffn) {
   return t + 4096;
 }
 
-int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s) {
+int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev) {
+  ULLAVA_REQUIRE(pos_dev == nullptr || a.seq == 1, "llama_forward: a device-side position needs seq == 1");
   ULLAVA_REQUIRE(a.weights && a.hidden && a.k_cache && a.v_cache && a.scratch && a.rope_cos && a.rope_sin,
                  "llama_forward: null pointer");
   ULLAVA_REQUIRE(a.n_weights == 6 * a.layers + 1, "llama_forward: expected %d weights, got %d", 6 * a.layers + 1,
@@ -157,10 +158,10 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s) 
     RUN(rmsnorm_run(ctx, a.hidden, H, L[0], xn, H, rows, H, a.eps, dt, s));
     RUN(gemm(ctx, s, dt, xn, H, L[1], H, qkv, 3 * H, rows, 3 * H, H));
     RUN(rope_kvcache_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, a.batch, a.seq, a.heads, hd, a.pos0, a.rope_cos,
-                         a.rope_sin, dt, s));
+                         a.rope_sin, dt, s, pos_dev));
     if (a.seq == 1) {
       RUN(attention_decode_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, att, H, a.batch, a.heads, hd, a.pos0 + 1,
-                               scale, dt, s));
+                               scale, dt, s, pos_dev, a.max_seq));
     } else {
       AttnArgs at{};
       at.q = qkv; at.q_bs = static_cast<int64_t>(a.seq) * 3 * H; at.q_rs = 3 * H; at.q_hs = hd;
@@ -179,6 +180,27 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s) 
   if (a.final_out) {
     RUN(rmsnorm_run(ctx, a.hidden, H, a.weights[6 * a.layers], a.final_out, H, rows, H, a.eps, dt, s));
   }
+  return OK;
+}
+
+// =================================================================================================
+// One greedy decode step with the position in device memory (CUDA-graph replayable):
+// embed(cur_ids) -> decoder stack (seq 1) -> final norm -> lm_head -> argmax -> bookkeeping.
+// Replaces one iteration of GenerationMixin.generate's loop as driven by UllavaForCausalLM.evaluate
+// (models/ullava.py:350-362 -> models/ullava_core.py:357-395,279-355).
+// =================================================================================================
+int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_t s) {
+  const ullava_llama_args& L = a.llama;
+  ULLAVA_REQUIRE(L.seq == 1 && L.final_out, "decode_step: llama.seq must be 1 and final_out set");
+  ULLAVA_REQUIRE(a.pos_dev && a.embed_table && a.lm_head && a.cur_ids && a.logits, "decode_step: null pointer");
+  RUN(embed_gather_run(ctx, a.cur_ids, a.embed_table, L.hidden, L.batch, L.hidden_size, a.vocab, L.dtype, s));
+  RUN(llama_forward_run(ctx, L, s, a.pos_dev));
+  GemmArgs g{};
+  g.A = L.final_out; g.lda = L.hidden_size; g.B = a.lm_head; g.ldb = L.hidden_size; g.D = a.logits; g.ldd = a.vocab;
+  g.M = L.batch; g.N = a.vocab; g.K = L.hidden_size; g.dtype = L.dtype; g.out_f32 = 1; g.epilogue = EPI_NONE;
+  RUN(gemm_run(ctx, g, s));
+  RUN(greedy_step_run(ctx, a.logits, a.vocab, L.batch, a.vocab, a.cur_ids, a.seqs, a.seqs_ld, L.final_out, a.hid_buf,
+                      a.hid_bs, L.hidden_size, a.finished, a.eos_id, a.pad_id, a.pos_dev, s));
   return OK;
 }
 

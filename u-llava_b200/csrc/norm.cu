@@ -140,11 +140,13 @@ static int norm_launch(Context* ctx, const void* x, int64_t ldx, const void* w, 
 
 int layernorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
                   int rows, int cols, float eps, int act, int dtype, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_NORM, 0.0, 4.0 * rows * cols);
   ULLAVA_REQUIRE(act == EPI_NONE || act == EPI_GELU, "layernorm: act must be NONE or GELU");
   return norm_launch<false>(ctx, x, ldx, w, b, y, ldy, rows, cols, eps, act, dtype, stream);
 }
 int rmsnorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols,
                 float eps, int dtype, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_NORM, 0.0, 4.0 * rows * cols);
   return norm_launch<true>(ctx, x, ldx, w, nullptr, y, ldy, rows, cols, eps, 0, dtype, stream);
 }
 

@@ -68,6 +68,24 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t 
   return OK;
 }
 
+ProfScope::ProfScope(Context* c, cudaStream_t s, int cls, double flops, double bytes)
+    : ctx(c), stream(s), idx(-1), launches0(c ? c->launches : 0) {
+  if (!c || !c->prof_on) return;
+  ullava_prof_rec r{};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  r.cls = cls; r.flops = flops; r.bytes = bytes; r.launches = 0;
+  cudaEventRecord(r.a, s);
+  c->prof.push_back(r);
+  idx = static_cast<int>(c->prof.size()) - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  ullava_prof_rec& r = ctx->prof[idx];
+  r.launches = static_cast<int>(ctx->launches - launches0);
+  cudaEventRecord(r.b, stream);
+}
+
 }  // namespace ullava
 
 using namespace ullava;
@@ -124,6 +142,37 @@ int ullava_set_workspace(ullava_ctx* ctx, void* ptr, size_t bytes) {
 }
 
 int64_t ullava_launch_count(ullava_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ullava_profile_begin(ullava_ctx* ctx) {
+  if (!ctx) { set_last_error("ullava_profile_begin: ctx is NULL"); return ERR_BAD_ARG; }
+  for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  ctx->prof.clear();
+  ctx->prof_on = true;
+  return OK;
+}
+
+int ullava_profile_end(ullava_ctx* ctx, double* out) {
+  if (!ctx || !out) { set_last_error("ullava_profile_end: NULL argument"); return ERR_BAD_ARG; }
+  ctx->prof_on = false;
+  for (int i = 0; i < ULLAVA_PROF_CLASSES * 4; ++i) out[i] = 0.0;
+  int st = OK;
+  for (auto& r : ctx->prof) {
+    if (st == OK) {
+      cudaError_t e = cudaEventSynchronize(r.b);
+      float ms = 0.f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+      if (e != cudaSuccess) st = check_cuda(e, "ullava_profile_end");
+      else if (r.cls >= 0 && r.cls < ULLAVA_PROF_CLASSES) {
+        double* o = out + 4 * r.cls;
+        o[0] += ms; o[1] += r.flops; o[2] += r.bytes; o[3] += r.launches;
+      }
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  return st;
+}
 
 int ullava_gemm(ullava_ctx* ctx, const ullava_gemm_args* args, void* stream) {
   if (!ctx || !args) {

@@ -178,6 +178,7 @@ sam_postprocess_kernel(const T* __restrict__ masks, int64_t mask_stride, float* 
 
 int sam_postprocess_run(Context* ctx, const void* masks, int64_t mask_stride, float* out, uint32_t* bits, int n,
                         int low, int img, int in_h, int in_w, int out_h, int out_w, int dtype, cudaStream_t s) {
+  ProfScope _ps(ctx, s, ULLAVA_PROF_SAM, 0.0, n * (2.0 * low * low + 4.0 * out_h * out_w));
   ULLAVA_REQUIRE(masks && out, "sam_postprocess: null pointer");
   ULLAVA_REQUIRE(low > 0 && img > 0 && in_h > 0 && in_w > 0 && in_h <= img && in_w <= img && out_h > 0 && out_w > 0,
                  "sam_postprocess: bad geometry");
@@ -243,6 +244,7 @@ struct Dec {
     return layernorm_run(ctx, x, cols, W[wi], W[wi + 1], x, cols, rows, cols, eps, act, dt, s);
   }
   int add(const void* a, const void* b, void* out, int64_t n_elems, int64_t period) {
+    ProfScope _ps(ctx, s, ULLAVA_PROF_SAM, 0.0, 4.0 * n_elems);
     const int64_t nvec = n_elems / 8, pv = period / 8;
     const int grid = static_cast<int>(std::min<int64_t>((nvec + 255) / 256, 148 * 8));
     if (dt == DT_BF16)
@@ -310,6 +312,7 @@ int sam_mask_decoder_run(Context* ctx, const ullava_sam_decoder_args& a, cudaStr
 
   // ---- inputs: tokens, image tokens (+ dense no-mask embedding), positional encoding ----
   {
+    ProfScope _ps(ctx, s, ULLAVA_PROF_SAM, 0.0, 4.0 * (n + 1.0) * HW * C);
     dim3 g(HW / 32, C / 32, n), g1(HW / 32, C / 32, 1);
     if (a.dtype == DT_BF16) {
       using T = __nv_bfloat16;
@@ -393,6 +396,7 @@ int sam_mask_decoder_run(Context* ctx, const ullava_sam_decoder_args& a, cudaStr
     RUN(d.gemm(h1, C, w + 4, static_cast<uint16_t*>(hyper) + m * 32, 128, n, 32, C));
   }
   {
+    ProfScope _ps(ctx, s, ULLAVA_PROF_SAM, 2.0 * n * 4.0 * 32 * 65536, 2.0 * n * (HW * 4.0 * 128 + 4.0 * 65536));
     dim3 g((HW * 4 + 255) / 256, n);
     if (a.dtype == DT_BF16)
       hyper_mask_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(up2),

@@ -3,7 +3,15 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/ullava_sm100.h"
+
+struct ullava_prof_rec {
+  cudaEvent_t a, b;
+  int cls;
+  double flops, bytes;
+  int launches;
+};
 
 struct ullava_ctx {
   int device = 0;
@@ -11,6 +19,9 @@ struct ullava_ctx {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int64_t launches = 0;
+  // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
+  bool prof_on = false;
+  std::vector<ullava_prof_rec> prof;
 };
 
 namespace ullava {
@@ -27,6 +38,16 @@ enum Epilogue : int {
   EPI_SILU_MUL = ULLAVA_EPI_SILU_MUL,
 };
 
+// runtime.cu -- kernel classes of the CUDA-event profiler (ULLAVA_PROF_* in the public header)
+struct ProfScope {
+  Context* ctx;
+  cudaStream_t stream;
+  int idx;
+  int64_t launches0;
+  ProfScope(Context* c, cudaStream_t s, int cls, double flops, double bytes);
+  ~ProfScope();
+};
+
 // gemm_sm100.cu
 int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream);
 
@@ -40,12 +61,16 @@ int rmsnorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, void* y
 int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream);
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
-                         float scale, int dtype, cudaStream_t stream);
+                         float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev = nullptr,
+                         int max_ctx = 0);
 
 // elementwise.cu
 int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld_qkv, void* kc, void* vc, int64_t cache_bs, int64_t cache_hs,
                      int batch, int seq, int heads, int head_dim, int pos0, const float* cos_t, const float* sin_t,
-                     int dtype, cudaStream_t stream);
+                     int dtype, cudaStream_t stream, const int32_t* pos_dev = nullptr);
+int greedy_step_run(Context* ctx, const float* logits, int64_t ld, int rows, int cols, int64_t* cur_ids, int64_t* seqs,
+                    int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int hdim, uint8_t* finished,
+                    int eos_id, int pad_id, int32_t* pos_dev, cudaStream_t stream);
 int vit_im2col_run(Context* ctx, const void* pixels, void* out, int batch, int img, int patch, int k_pad, int dtype,
                    cudaStream_t stream);
 int vit_assemble_run(Context* ctx, const void* pe, const void* cls, const void* pos, void* out, int batch, int np,
@@ -68,7 +93,8 @@ int sam_postprocess_run(Context* ctx, const void* masks, int64_t mask_stride, fl
 // models.cu
 int vit_forward_run(Context* ctx, const ullava_vit_args& a, cudaStream_t stream);
 size_t vit_scratch(int batch, int img, int patch, int hidden, int ffn, int k_pad);
-int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t stream);
+int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev = nullptr);
+int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_t s);
 size_t llama_scratch(int rows, int hidden, int ffn);
 
 }  // namespace ullava

@@ -125,6 +125,16 @@ class LlamaStack:
         self._sig = None
         self._scratch = None
         self._rope = None
+        self._session = None
+        self.graph_launches = 0  # kernels launched through CUDA-graph replays (not seen by ullava_launch_count)
+
+    def decode_session(self, ctx, batch: int, max_seq: int, embed_table, lm_head, keep_hidden: bool) -> "DecodeSession":
+        self.ensure()
+        key = (batch, max_seq, keep_hidden, embed_table.data_ptr(), lm_head.data_ptr(), self._sig)
+        if self._session is None or self._session.key != key:
+            self._session = None  # free the old KV cache before allocating the new one
+            self._session = DecodeSession(self, ctx, batch, max_seq, embed_table, lm_head, keep_hidden)
+        return self._session
 
     def _pack(self):
         cfg = self.model.config
@@ -200,3 +210,94 @@ class LlamaStack:
                           batch, seq, pos0, self.cfg, cos, sin, final_out=final, all_hidden=allh)
         cache.length = pos0 + seq
         return final, allh
+
+
+class DecodeSession:
+    """Persistent device state of the greedy decode loop for one (batch, max_seq) shape: KV cache, step
+    buffers, the device-side position and the CUDA graph of one decode step (ullava_llama_decode_step reads
+    the position from device memory, so ONE captured graph is replayed for every step and every later
+    generate() call of the same shape)."""
+
+    def __init__(self, stack: "LlamaStack", ctx, batch: int, max_seq: int, embed_table: torch.Tensor,
+                 lm_head: torch.Tensor, keep_hidden: bool):
+        stack.ensure()
+        self.stack, self.ctx, self.batch, self.max_seq = stack, ctx, batch, max_seq
+        dev, dt = stack.device, stack.dtype
+        H, V = stack.cfg["hidden"], lm_head.shape[0]
+        self.key = (batch, max_seq, keep_hidden, embed_table.data_ptr(), lm_head.data_ptr(), stack._sig)
+        self.cache = stack.new_cache(batch, max_seq)
+        self.hidden = torch.empty((batch, H), dtype=dt, device=dev)
+        self.final = torch.empty((batch, H), dtype=dt, device=dev)
+        self.logits = torch.empty((batch, V), dtype=torch.float32, device=dev)
+        self.cur_ids = torch.zeros((batch,), dtype=torch.int64, device=dev)
+        self.pos = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.finished = torch.zeros((batch,), dtype=torch.uint8, device=dev)
+        self.seqs = torch.zeros((batch, max_seq), dtype=torch.int64, device=dev)
+        self.hid_buf = torch.empty((batch, max_seq - 1, H), dtype=dt, device=dev) if keep_hidden else None
+        self.scratch = torch.empty(ctx.llama_scratch_bytes(batch, H, stack.cfg["ffn"]), dtype=torch.uint8, device=dev)
+        self.embed_table, self.lm_head = embed_table, lm_head
+        self.graph = None
+        self.graph_nodes = 0
+        self.eos_id, self.pad_id = -1, 0
+        self.args = None
+
+    def _build_args(self):
+        cos, sin = self.stack.rope_tables(self.max_seq)
+        a = native.DecodeArgs()
+        self.ctx.fill_llama_args(a.llama, self.stack.table, len(self.stack.tensors), self.hidden, self.cache.k,
+                                 self.cache.v, self.scratch, self.batch, 1, 0, self.stack.cfg, cos, sin,
+                                 final_out=self.final)
+        a.pos_dev = self.pos.data_ptr()
+        a.embed_table, a.vocab, a.lm_head = self.embed_table.data_ptr(), self.lm_head.shape[0], self.lm_head.data_ptr()
+        a.cur_ids, a.logits = self.cur_ids.data_ptr(), self.logits.data_ptr()
+        a.seqs, a.seqs_ld = self.seqs.data_ptr(), self.seqs.stride(0)
+        a.hid_buf = self.hid_buf.data_ptr() if self.hid_buf is not None else None
+        a.hid_bs = self.hid_buf.stride(0) if self.hid_buf is not None else 0
+        a.finished, a.eos_id, a.pad_id = self.finished.data_ptr(), self.eos_id, self.pad_id
+        self.args = a
+
+    def begin(self, input_ids: torch.Tensor, eos_id, pad_id: int):
+        eos = -1 if eos_id is None else int(eos_id)
+        if self.args is None or eos != self.eos_id or int(pad_id) != self.pad_id:
+            self.eos_id, self.pad_id = eos, int(pad_id)
+            self._build_args()
+            self.graph = None  # eos / pad ids are baked into the captured kernel arguments
+        P = input_ids.shape[1]
+        self.cache.length = 0
+        self.finished.zero_()
+        self.seqs.fill_(pad_id)
+        self.seqs[:, :P] = input_ids
+
+    def first_token(self, last_final: torch.Tensor, prompt_len: int):
+        """Greedy token after the prefill: lm_head on the last prompt position + the step bookkeeping at pos = P-1."""
+        self.ctx.gemm(last_final, self.lm_head, out=self.logits)
+        self.pos.fill_(prompt_len - 1)
+        self.ctx.greedy_step(self.logits, self.cur_ids, self.seqs, last_final, self.hid_buf, self.finished, self.eos_id,
+                             self.pad_id, self.pos)
+
+    def steps(self, n: int, use_graph: bool = True) -> int:
+        """Runs n decode steps; returns the number of native kernels launched through graph REPLAYS (eager
+        launches are counted by ullava_launch_count; the phantom increments made while capturing are cancelled)."""
+        if n <= 0:
+            return 0
+        replayed = 0
+        done = 0
+        if use_graph and self.graph is None:
+            self.ctx.llama_decode_step(self.args)  # eager warm-up step (also a real step)
+            done = 1
+            if n > 1:
+                c0 = self.ctx.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.ctx.llama_decode_step(self.args)
+                self.graph_nodes = self.ctx.launch_count() - c0
+                replayed -= self.graph_nodes  # capture bumped the native counter without launching anything
+                self.graph = g
+        for _ in range(n - done):
+            if use_graph and self.graph is not None:
+                self.graph.replay()
+                replayed += self.graph_nodes
+            else:
+                self.ctx.llama_decode_step(self.args)
+        self.cache.length += n
+        return replayed

@@ -64,6 +64,17 @@ class UllavaForCausalLM(PreTrainedModel):
         self.llm = UllavaCoreForCausalLM(llm_config)
         self.seg_projector, self.visual_model = self.init_seg_modules(llm_config.hidden_size)
         self.det_projector, self.det_decoder = self.init_det_modules(llm_config.hidden_size)
+        # optional extras for the sharded eval path (dist_eval.py): when pack_mask_bits is set, evaluate()/forward()
+        # also keep the thresholded masks bit-packed ([n, ceil(H*W/32)] int32 per image) in last_mask_bits
+        self.pack_mask_bits = False
+        self.last_mask_bits = None
+        self.timeline = None  # list of (stage name, torch.cuda.Event) when stage timing is requested
+
+    def _mark(self, name: str):
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timeline.append((name, ev))
 
     def init_det_modules(self, hidden_size):
         out_dim = self.config.out_dim
@@ -166,18 +177,25 @@ class UllavaForCausalLM(PreTrainedModel):
             raise NotImplementedError("training losses are outside the B200 inference hot path "
                                       "(SURVEY.md section 8: forward(inference=True) and evaluate() are in scope)")
         with torch.no_grad():
+            self._mark("start")
             image_embeddings = self.get_visual_embs(images_sam)
+            self._mark("sam_encoder")
             output = self.llm.forward(images=images, attention_mask=attention_mask, input_ids=input_ids, labels=labels,
                                       output_hidden_states=False, use_cache=False, _return_last_hidden=True)
+            self._mark("vit_prefill_lmhead")
             last_hidden = output.hidden_states[-1]
-            pred_masks, pred_boxes, _ = self._decode_heads(input_ids, last_hidden, image_embeddings, size_list,
-                                                           resize_list)
+            pred_masks, pred_boxes, bits = self._decode_heads(input_ids, last_hidden, image_embeddings, size_list,
+                                                              resize_list, pack_bits=self.pack_mask_bits)
+            self.last_mask_bits = bits if self.pack_mask_bits else None
+            self._mark("mask_heads")
         return {"pred_masks": pred_masks, "pred_boxes": pred_boxes, "gt_masks": mask_list, "gt_boxes": bbox_list,
                 "logits": output.logits}
 
     def evaluate(self, images_sam, images, input_ids, raw_size_list, resize_list, max_new_tokens=32, temperature=0.2,
                  top_p=None, num_beams=1, no_repeat_ngram_size=None, stopping_criteria=None):
         with torch.inference_mode():
+            self._mark("start")
+            self.llm.timeline = self.timeline
             outputs = self.llm.generate(input_ids=input_ids, images=images, max_new_tokens=max_new_tokens,
                                         num_beams=num_beams, top_p=top_p, do_sample=True if temperature > 0 else False,
                                         temperature=temperature, output_hidden_states=True,
@@ -185,9 +203,14 @@ class UllavaForCausalLM(PreTrainedModel):
                                         stopping_criteria=stopping_criteria)
             output_ids = outputs.sequences
             last_hidden = outputs.hidden_states[-1][-1]
+            self.llm.timeline = None
+            self._mark("decode")
             image_embeddings = self.get_visual_embs(images_sam)
-            pred_masks, pred_boxes, _ = self._decode_heads(output_ids, last_hidden, image_embeddings, raw_size_list,
-                                                           resize_list)
+            self._mark("sam_encoder")
+            pred_masks, pred_boxes, bits = self._decode_heads(output_ids, last_hidden, image_embeddings, raw_size_list,
+                                                              resize_list, pack_bits=self.pack_mask_bits)
+            self.last_mask_bits = bits if self.pack_mask_bits else None
+            self._mark("mask_heads")
         return output_ids, pred_masks, pred_boxes
 
 

@@ -93,6 +93,18 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         self.post_init()
         self._tower = None
         self._stack = None
+        self.timeline = None  # optional list of (stage, torch.cuda.Event), see UllavaForCausalLM._mark
+        self.use_cuda_graph = True  # greedy decode loop replays one captured step graph (engine.DecodeSession)
+
+    def graph_kernel_launches(self) -> int:
+        """Native kernels launched through CUDA-graph replays (they bypass ullava_launch_count)."""
+        return self._stack.graph_launches if self._stack is not None else 0
+
+    def _mark(self, name: str):
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timeline.append((name, ev))
 
     @staticmethod
     def build_vision_projector(in_dim, hidden_dim, name='mlp'):
@@ -311,14 +323,20 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         self._check_mask(attention_mask, B, P)
         H = self.config.hidden_size
         T = P + max_new_tokens
+        greedy = not (do_sample and temperature and temperature > 0)
+        if greedy and stopping_criteria is None and max_new_tokens >= 1:
+            return self._generate_greedy_device(ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id,
+                                                pad_token_id, output_hidden_states, return_dict_in_generate)
         cache = stack.new_cache(B, T)
         table = self.model.embed_tokens.weight.detach()
         w = self.lm_head.weight.detach()
         V = w.shape[0]
 
         _, embeds = self.embed_images_videos(input_ids, images, videos)
+        self._mark("vit_projector_splice")
         hidden = embeds.view(B * P, H)
         final, _ = stack.run(ctx, hidden, cache, B, P)
+        self._mark("prefill")
         hid_buf = None
         if output_hidden_states:
             hid_buf = torch.empty((B, T - 1, H), dtype=final.dtype, device=final.device)
@@ -361,6 +379,58 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         if output_hidden_states:
             hs = ((hid_buf[:, : n_done - 1],),)
         return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=cache)
+
+    def _generate_greedy_device(self, ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id, pad_token_id,
+                                output_hidden_states, return_dict_in_generate):
+        """Greedy loop with all per-step state on the device: prefill, then max_new_tokens-1 replays of ONE
+        captured decode-step graph (the position is read from device memory).  The host only synchronises to
+        test for EOS (every 8 steps, and only when an eos id is set)."""
+        B, P = input_ids.shape
+        H = self.config.hidden_size
+        T = P + max_new_tokens
+        table = self.model.embed_tokens.weight.detach()
+        w = self.lm_head.weight.detach()
+        sess = stack.decode_session(ctx, B, T, table, w, bool(output_hidden_states))
+        sess.begin(input_ids, eos_token_id, pad_token_id)
+        _, embeds = self.embed_images_videos(input_ids, images, videos)
+        self._mark("vit_projector_splice")
+        final, _ = stack.run(ctx, embeds.view(B * P, H), sess.cache, B, P)
+        if sess.hid_buf is not None:
+            ctx.copy_rows(final, sess.hid_buf, B, P, H, P * H, H, sess.hid_buf.stride(0), H)
+        self._mark("prefill")
+        last = final.view(B, P, H)[:, -1].contiguous()
+        sess.first_token(last, P)
+        remaining = max_new_tokens - 1
+        n_tokens = 1
+        if eos_token_id is None:
+            stack.graph_launches += self._count_graph(ctx, sess, remaining)
+            n_tokens += remaining
+        else:
+            while remaining > 0:
+                if bool(sess.finished.all()):
+                    break
+                n = min(8, remaining)
+                stack.graph_launches += self._count_graph(ctx, sess, n)
+                remaining -= n
+                n_tokens += n
+        seqs = sess.seqs[:, :P + n_tokens]
+        if eos_token_id is not None:
+            # HF stops as soon as every sequence has emitted eos: trim the pad-only columns of the last chunk
+            gen = seqs[:, P:]
+            is_eos = gen == eos_token_id
+            if bool(is_eos.any(1).all()):
+                first = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full_like(gen[:, 0], gen.shape[1]))
+                seqs = seqs[:, :P + int(first.max()) + 1]
+        seqs = seqs.clone()
+        if not return_dict_in_generate:
+            return seqs
+        hs = None
+        if output_hidden_states:
+            hs = ((sess.hid_buf[:, : seqs.shape[1] - 1].clone(),),)
+        return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=sess.cache)
+
+    def _count_graph(self, ctx, sess, n):
+        return sess.steps(n, use_graph=self.use_cuda_graph)
 
     def prepare_inputs_for_generation(self, input_ids=None, inputs_embeds=None, attention_mask=None, images=None,
                                       videos=None, labels=None, past_key_values=None, **kwargs):

@@ -66,6 +66,12 @@ class LlamaArgs(C.Structure):
                 ("eps", _f32), ("rope_cos", _vp), ("rope_sin", _vp), ("dtype", _i32)]
 
 
+class DecodeArgs(C.Structure):
+    _fields_ = [("llama", LlamaArgs), ("pos_dev", _vp), ("embed_table", _vp), ("vocab", _i32), ("lm_head", _vp),
+                ("cur_ids", _vp), ("logits", _vp), ("seqs", _vp), ("seqs_ld", _i64), ("hid_buf", _vp),
+                ("hid_bs", _i64), ("finished", _vp), ("eos_id", _i32), ("pad_id", _i32)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/ullava_sm100.h
 _SIGNATURES = {
     "ullava_abi_version": (_i32, []),
@@ -74,6 +80,8 @@ _SIGNATURES = {
     "ullava_destroy": (_i32, [_vp]),
     "ullava_set_workspace": (_i32, [_vp, _vp, _sz]),
     "ullava_launch_count": (_i64, [_vp]),
+    "ullava_profile_begin": (_i32, [_vp]),
+    "ullava_profile_end": (_i32, [_vp, C.POINTER(C.c_double)]),
     "ullava_gemm": (_i32, [_vp, C.POINTER(GemmArgs), _vp]),
     "ullava_layernorm": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _i32, _i32, _vp]),
     "ullava_rmsnorm": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _f32, _i32, _vp]),
@@ -96,6 +104,9 @@ _SIGNATURES = {
     "ullava_vit_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "ullava_llama_forward": (_i32, [_vp, C.POINTER(LlamaArgs), _vp]),
     "ullava_llama_scratch_bytes": (_sz, [_i32, _i32, _i32]),
+    "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
+    "ullava_greedy_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
+                                  _vp, _vp]),
 }
 
 _lib = None
@@ -192,6 +203,18 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.ullava_launch_count(self.handle))
+
+    # ---- per-kernel-class CUDA-event profile (bench.py roofline) ---------------------------
+    PROF_CLASSES = ("gemm_tensor", "gemm_stream", "attn_prefill", "attn_decode", "norm", "glue", "sam", "other")
+
+    def profile_begin(self):
+        self._chk(self.lib.ullava_profile_begin(self.handle))
+
+    def profile_end(self) -> dict:
+        buf = (C.c_double * (len(self.PROF_CLASSES) * 4))()
+        self._chk(self.lib.ullava_profile_end(self.handle, buf))
+        return {name: dict(ms=buf[4 * i], flops=buf[4 * i + 1], bytes=buf[4 * i + 2], launches=int(buf[4 * i + 3]))
+                for i, name in enumerate(self.PROF_CLASSES)}
 
     # ---- primitives ------------------------------------------------------------------
     def gemm(self, a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, epilogue=EPI_NONE, out=None,
@@ -377,6 +400,34 @@ class Context:
         a.dtype = dtype_code(pixels.dtype)
         self._chk(self.lib.ullava_vit_forward(self.handle, C.byref(a), _stream()))
         return out
+
+    def llama_decode_step(self, args: "DecodeArgs"):
+        """One greedy decode step with the position in device memory (CUDA-graph replayable)."""
+        self._chk(self.lib.ullava_llama_decode_step(self.handle, C.byref(args), _stream()))
+
+    def greedy_step(self, logits, cur_ids, seqs, final_h, hid_buf, finished, eos_id, pad_id, pos_dev):
+        """next = argmax(logits) with eos/pad handling; cur_ids <- next; seqs[:, pos+1] <- next;
+        hid_buf[:, pos] <- final_h; ++pos (pos read from / written to device memory)."""
+        rows, cols = logits.shape
+        self._chk(self.lib.ullava_greedy_step(
+            self.handle, logits.data_ptr(), logits.stride(0), rows, cols, cur_ids.data_ptr(), _ptr(seqs),
+            seqs.stride(0) if seqs is not None else 0, _ptr(final_h), _ptr(hid_buf),
+            hid_buf.stride(0) if hid_buf is not None else 0, final_h.shape[-1] if final_h is not None else 8,
+            _ptr(finished), int(eos_id), int(pad_id), pos_dev.data_ptr(), _stream()))
+
+    def fill_llama_args(self, a: "LlamaArgs", weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq,
+                        pos0, cfg: dict, rope_cos, rope_sin, final_out=None, all_hidden=None):
+        a.weights, a.n_weights = weight_table, n_weights
+        a.hidden, a.final_out, a.all_hidden = hidden.data_ptr(), _ptr(final_out), _ptr(all_hidden)
+        a.k_cache, a.v_cache = k_cache.data_ptr(), v_cache.data_ptr()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        a.batch, a.seq, a.pos0, a.max_seq = batch, seq, pos0, k_cache.shape[3]
+        a.layers, a.hidden_size, a.heads, a.head_dim, a.ffn = (cfg["layers"], cfg["hidden"], cfg["heads"],
+                                                               cfg["head_dim"], cfg["ffn"])
+        a.eps = cfg["eps"]
+        a.rope_cos, a.rope_sin = rope_cos.data_ptr(), rope_sin.data_ptr()
+        a.dtype = dtype_code(hidden.dtype)
+        return a
 
     def llama_forward(self, weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq, pos0, cfg: dict,
                       rope_cos, rope_sin, final_out=None, all_hidden=None):
