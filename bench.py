@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--new-tokens", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="one resident step only, no e2e / stages / cpu baseline (for runs under ncu)")
     return ap.parse_args()
 
 
@@ -397,6 +399,12 @@ def run_b200(args):
         if ws > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), ctx.launch_count() + model.llm.graph_kernel_launches() - n0, r
+
+    if args.profile_mode:
+        step_resident()
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_mode": True, "launches": ctx.launch_count() + model.llm.graph_kernel_launches()}))
+        return
 
     sampler = ClockSampler(physical_gpu_index(local))
     if rank == 0:

@@ -225,6 +225,28 @@ typedef struct ullava_vit_args {
 ULLAVA_API int ullava_vit_forward(ullava_ctx* ctx, const ullava_vit_args* args, void* stream);
 ULLAVA_API size_t ullava_vit_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32_t hidden, int32_t ffn, int32_t k_pad);
 
+/* SAM ViT image encoder (ImageEncoderViT.forward, segment_anything/modeling/image_encoder.py:110-426; called per
+ * image by UllavaForCausalLM.get_visual_embs, models/ullava.py:139-150) on a batch: pixels -> [B, out_chans, g, g].
+ * Window blocks attend inside zero-padded window x window tiles (pads are real tokens holding the qkv bias, as in
+ * the reference); blocks whose bit is set in global_mask attend over the whole g x g grid.  Both use the decomposed
+ * relative-position bias.  win_rows / unwin_rows are the window_partition / window_unpartition row maps
+ * (u-llava_b200/models/segment_anything/modeling/image_encoder.py builds them).  Weight order: csrc/sam_encoder.cu. */
+typedef struct ullava_sam_encoder_args {
+  const void* const* weights; int32_t n_weights;   /* 3 + 14*depth + 6 */
+  const void* pixels;       /* [B,3,img,img] 16-bit */
+  void* out;                /* [B,out_chans,g,g] 16-bit, NCHW */
+  void* scratch; size_t scratch_bytes;
+  const int32_t* win_rows;   /* device [B*g*g]: token row -> row in the padded window layout */
+  const int32_t* unwin_rows; /* device [B*nw*nw*window*window]: window-layout row -> token row, -1 for pads */
+  int32_t batch, img, patch, embed_dim, depth, heads, window, out_chans;
+  uint64_t global_mask;     /* bit l set: block l uses global attention */
+  float eps;                /* LayerNorm eps of the blocks (1e-6) */
+  int32_t dtype;
+} ullava_sam_encoder_args;
+ULLAVA_API int ullava_sam_encoder_forward(ullava_ctx* ctx, const ullava_sam_encoder_args* args, void* stream);
+ULLAVA_API size_t ullava_sam_encoder_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32_t embed_dim, int32_t window,
+                                        int32_t out_chans);
+
 /* LLaMA decoder stack (LlamaModel.forward, hf:models/llama/modeling_llama.py:355-424) on a batch of
  * equal-length sequences: hidden [B*S, H] (in place) at absolute positions pos0..pos0+S-1, appending
  * K/V to the caches.  S == 1 is the decode step (swap-AB GEMMs + single-query attention).

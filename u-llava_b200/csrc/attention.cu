@@ -66,12 +66,20 @@ struct FlashParams {
   float scale_log2;  // scale * log2(e)
 };
 
-// shared tile [rows][HD] 16-bit with a 16-byte-chunk XOR swizzle (conflict-free ldmatrix)
+// shared tile [rows][HD] 16-bit with a 16-byte-chunk XOR swizzle (conflict-free ldmatrix).
+// HD = 80 (SAM ViT-H heads: 10 chunks per row, not a power of two) uses rows padded to 176 bytes instead:
+// 8 consecutive rows then start at banks {0,12,24,4,16,28,8,20}, again conflict-free for ldmatrix.
+template <int HD>
+__host__ __device__ constexpr int fa_row_bytes() { return HD == 80 ? 176 : HD * 2; }
 template <int HD>
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
-  constexpr int CPR = HD / 8;                    // 16-byte chunks per row
-  constexpr int MASK = CPR >= 8 ? 7 : CPR - 1;   // XOR only within the row's own chunks
-  return static_cast<uint32_t>(row * (HD * 2) + (((chunk & ~MASK) | ((chunk ^ row) & MASK)) << 4));
+  if constexpr (HD == 80) {
+    return static_cast<uint32_t>(row * 176 + (chunk << 4));
+  } else {
+    constexpr int CPR = HD / 8;                    // 16-byte chunks per row
+    constexpr int MASK = CPR >= 8 ? 7 : CPR - 1;   // XOR only within the row's own chunks
+    return static_cast<uint32_t>(row * (HD * 2) + (((chunk & ~MASK) | ((chunk ^ row) & MASK)) << 4));
+  }
 }
 
 template <typename T, int HD>
@@ -90,7 +98,7 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(FA_THREADS)
 flash_fwd_kernel(const FlashParams p) {
   extern __shared__ __align__(128) uint8_t fa_smem[];
-  constexpr int TILE_BYTES = FA_BN * HD * 2;
+  constexpr int TILE_BYTES = FA_BN * fa_row_bytes<HD>();
   const uint32_t sQ = smem_u32(fa_smem);
   const uint32_t sK = sQ + TILE_BYTES;            // 2 buffers
   const uint32_t sV = sK + 2 * TILE_BYTES;        // 2 buffers
@@ -304,6 +312,284 @@ int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream) {
     set_last_error("attention: unsupported dtype %d", a.dtype);
     return ERR_UNSUPPORTED;
   }
+  if (st == OK) ctx->launches++;
+  return st;
+}
+
+// ---- flash forward with SAM's decomposed relative-position bias ----------------------------------
+// Attention of the SAM ViT image encoder (segment_anything/modeling/image_encoder.py:196-260, bias :355-392):
+//   softmax( scale * q k^T + q . Rh[qh - kh + S - 1] + q . Rw[qw - kw + S - 1] ) v
+// over an S x S token grid (S = 14 inside a window, 64 for the global blocks), non causal.
+// The two bias products are themselves Q x table^T contractions, so the prologue runs the tables through
+// the same mma.sync path as the keys and parks the [64 x (2S-1)] results of this CTA's query rows in
+// shared memory; the main loop gathers bias(q, k) = Ph[q][qh-kh+S-1] + Pw[q][qw-kw+S-1] from there.
+// o_row_map (optional) scatters output rows: window-layout query row -> un-partitioned token row (-1 = pad).
+struct RelPosParams {
+  const void* rel_h;        // [2S-1, HD] 16-bit
+  const void* rel_w;        // [2S-1, HD] 16-bit
+  int S;
+  const int32_t* o_row_map; // [batch * seq_q] or nullptr
+};
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(FA_THREADS)
+flash_relpos_kernel(const FlashParams p, const RelPosParams rp) {
+  extern __shared__ __align__(128) uint8_t fa_smem[];
+  constexpr int TILE_BYTES = FA_BN * fa_row_bytes<HD>();
+  const uint32_t sQ = smem_u32(fa_smem);
+  const uint32_t sK = sQ + TILE_BYTES;            // 2 buffers
+  const uint32_t sV = sK + 2 * TILE_BYTES;        // 2 buffers
+  float* sP = reinterpret_cast<float*>(fa_smem + 5 * TILE_BYTES);
+  const int S = rp.S, n_rel = 2 * S - 1;
+  const int pstride = 2 * n_rel + 1;              // odd: rows land on different banks
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * FA_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const T* qg = static_cast<const T*>(p.q) + b * p.q_bs + h * p.q_hs;
+  const T* kg = static_cast<const T*>(p.k) + b * p.k_bs + h * p.k_hs;
+  const T* vg = static_cast<const T*>(p.v) + b * p.v_bs + h * p.v_hs;
+  const int n_tiles = (p.seq_k + FA_BN - 1) / FA_BN;
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr int KS = HD / 16;
+
+  // ---- Q tile -> registers ----
+  load_tile<T, HD>(sQ, qg, p.q_rs, m0, p.seq_q, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int chunk = ks * 2 + (lane >> 4);
+    ldsm_x4(sQ + sw_off<HD>(row, chunk), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  }
+
+  // ---- bias prologue: P = Q x table^T for both tables ----
+  for (int tb = 0; tb < 2; ++tb) {
+    const T* table = static_cast<const T*>(tb == 0 ? rp.rel_h : rp.rel_w);
+    for (int c0 = 0; c0 < n_rel; c0 += FA_BN) {
+      __syncthreads();  // previous contents of sK[0] consumed
+      load_tile<T, HD>(sK, table, HD, c0, n_rel, tid);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      float s[FA_BN / 8][4];
+#pragma unroll
+      for (int i = 0; i < FA_BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int nb = 0; nb < FA_BN / 16; ++nb) {
+          uint32_t r0, r1, r2, r3;
+          const int row = nb * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int chunk = ks * 2 + ((lane >> 3) & 1);
+          ldsm_x4(sK + sw_off<HD>(row, chunk), r0, r1, r2, r3);
+          mma16816<T>(s[nb * 2], qf[ks], r0, r1);
+          mma16816<T>(s[nb * 2 + 1], qf[ks], r2, r3);
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < FA_BN / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = c0 + nb * 8 + tq * 2 + (e & 1);
+          const int ql = warp * 16 + g + (e >> 1) * 8;
+          if (col < n_rel) sP[ql * pstride + tb * n_rel + col] = s[nb][e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- main loop ----
+  load_tile<T, HD>(sK, kg, p.k_rs, 0, p.seq_k, tid);
+  load_tile<T, HD>(sV, vg, p.v_rs, 0, p.seq_k, tid);
+  cp_async_commit();
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const int qrow0 = m0 + warp * 16 + g;  // this thread's rows: qrow0 and qrow0 + 8
+  // per-row bases into sP: index = base_h - kh  and  base_w - kw
+  int base_h[2], base_w[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qr = min(qrow0 + r * 8, p.seq_q - 1);
+    const int ql = warp * 16 + g + r * 8;
+    base_h[r] = ql * pstride + qr / S + S - 1;
+    base_w[r] = ql * pstride + n_rel + qr % S + S - 1;
+  }
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < n_tiles) {
+      load_tile<T, HD>(sK + (buf ^ 1) * TILE_BYTES, kg, p.k_rs, (t + 1) * FA_BN, p.seq_k, tid);
+      load_tile<T, HD>(sV + (buf ^ 1) * TILE_BYTES, vg, p.v_rs, (t + 1) * FA_BN, p.seq_k, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    float s[FA_BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < FA_BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    const uint32_t kb = sK + buf * TILE_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int nb = 0; nb < FA_BN / 16; ++nb) {
+        uint32_t r0, r1, r2, r3;
+        const int row = nb * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int chunk = ks * 2 + ((lane >> 3) & 1);
+        ldsm_x4(kb + sw_off<HD>(row, chunk), r0, r1, r2, r3);
+        mma16816<T>(s[nb * 2], qf[ks], r0, r1);
+        mma16816<T>(s[nb * 2 + 1], qf[ks], r2, r3);
+      }
+    }
+
+    const int key0 = t * FA_BN;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nb = 0; nb < FA_BN / 8; ++nb) {
+#pragma unroll
+      for (int e01 = 0; e01 < 2; ++e01) {
+        const int key = key0 + nb * 8 + tq * 2 + e01;
+        int kh, kw;
+        if (S == 64) { kh = key >> 6; kw = key & 63; } else { kh = key / S; kw = key - kh * S; }
+        const bool ok = key < p.seq_k;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int e = r * 2 + e01;
+          float val = -INFINITY;
+          if (ok) val = s[nb][e] * p.scale_log2 + (sP[base_h[r] - kh] + sP[base_w[r] - kw]) * kLog2e;
+          s[nb][e] = val;
+          mx[r] = fmaxf(mx[r], val);
+        }
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_run[r], mx[r]);
+      const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+      corr[r] = exp2f(m_run[r] - msafe);
+      m_run[r] = mnew[r];
+      mnew[r] = msafe;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[FA_BN / 16][4];
+#pragma unroll
+    for (int nb = 0; nb < FA_BN / 8; ++nb) {
+      const float p0 = exp2f(s[nb][0] - mnew[0]);
+      const float p1 = exp2f(s[nb][1] - mnew[0]);
+      const float p2 = exp2f(s[nb][2] - mnew[1]);
+      const float p3 = exp2f(s[nb][3] - mnew[1]);
+      const uint32_t lo = pack2<T>(p0, p1), hi = pack2<T>(p2, p3);
+      const float2 flo = unpack2<T>(lo), fhi = unpack2<T>(hi);
+      rs[0] += flo.x + flo.y;
+      rs[1] += fhi.x + fhi.y;
+      pf[nb >> 1][(nb & 1) * 2 + 0] = lo;
+      pf[nb >> 1][(nb & 1) * 2 + 1] = hi;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o_acc[i][0] *= corr[0];
+      o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1];
+      o_acc[i][3] *= corr[1];
+    }
+    const uint32_t vb = sV + buf * TILE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < FA_BN / 16; ++kk) {
+#pragma unroll
+      for (int db = 0; db < HD / 16; ++db) {
+        uint32_t r0, r1, r2, r3;
+        const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int chunk = db * 2 + (lane >> 4);
+        ldsm_x4_t(vb + sw_off<HD>(row, chunk), r0, r1, r2, r3);
+        mma16816<T>(o_acc[db * 2], pf[kk], r0, r1);
+        mma16816<T>(o_acc[db * 2 + 1], pf[kk], r2, r3);
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv[2] = {l_run[0] > 0.f ? 1.f / l_run[0] : 0.f, l_run[1] > 0.f ? 1.f / l_run[1] : 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qr = qrow0 + r * 8;
+    if (qr >= p.seq_q) continue;
+    T* orow;
+    if (rp.o_row_map) {
+      const int dst = rp.o_row_map[static_cast<int64_t>(b) * p.seq_q + qr];
+      if (dst < 0) continue;  // padded window token: dropped by window_unpartition
+      orow = static_cast<T*>(p.o) + static_cast<int64_t>(dst) * p.o_rs + h * p.o_hs;
+    } else {
+      orow = static_cast<T*>(p.o) + b * p.o_bs + static_cast<int64_t>(qr) * p.o_rs + h * p.o_hs;
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i)
+      *reinterpret_cast<uint32_t*>(orow + i * 8 + tq * 2) = pack2<T>(o_acc[i][r * 2] * inv[r], o_acc[i][r * 2 + 1] * inv[r]);
+  }
+}
+
+template <typename T, int HD>
+static int relpos_launch(const FlashParams& p, const RelPosParams& rp, int batch, int heads, cudaStream_t stream) {
+  const int smem = 5 * FA_BN * fa_row_bytes<HD>() + FA_BM * (2 * (2 * rp.S - 1) + 1) * 4;
+  auto kern = flash_relpos_kernel<T, HD>;
+  static int configured = 0;
+  if (smem > configured) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid((p.seq_q + FA_BM - 1) / FA_BM, heads, batch);
+  kern<<<grid, FA_THREADS, smem, stream>>>(p, rp);
+  return check_cuda(cudaGetLastError(), "flash_relpos launch");
+}
+
+int attention_relpos_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel_w, int S,
+                         const int32_t* o_row_map, cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_ATTN_PREFILL, 4.0 * a.batch * a.heads * (double)a.seq_q * a.seq_k * a.head_dim,
+                2.0 * a.batch * a.heads * a.head_dim * (2.0 * a.seq_q + 2.0 * a.seq_k));
+  ULLAVA_REQUIRE(a.q && a.k && a.v && a.o && rel_h && rel_w, "attention_relpos: null pointer");
+  ULLAVA_REQUIRE(S > 0 && S <= 64 && a.seq_q == S * S && a.seq_k == S * S, "attention_relpos: seq must be S*S, S <= 64");
+  const int64_t strides[] = {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs};
+  for (int64_t st : strides) ULLAVA_REQUIRE(st % 8 == 0, "attention_relpos: strides must be multiples of 8 elements");
+  if (a.batch == 0) return OK;
+  FlashParams p;
+  p.q = a.q; p.q_bs = a.q_bs; p.q_rs = a.q_rs; p.q_hs = a.q_hs;
+  p.k = a.k; p.k_bs = a.k_bs; p.k_rs = a.k_rs; p.k_hs = a.k_hs;
+  p.v = a.v; p.v_bs = a.v_bs; p.v_rs = a.v_rs; p.v_hs = a.v_hs;
+  p.o = a.o; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
+  p.seq_q = a.seq_q; p.seq_k = a.seq_k; p.causal = 0; p.q_pos0 = 0;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  RelPosParams rp{rel_h, rel_w, S, o_row_map};
+  int st;
+#define ULLAVA_RP(TT) \
+  if (a.head_dim == 80) st = relpos_launch<TT, 80>(p, rp, a.batch, a.heads, stream); \
+  else if (a.head_dim == 64) st = relpos_launch<TT, 64>(p, rp, a.batch, a.heads, stream); \
+  else if (a.head_dim == 32) st = relpos_launch<TT, 32>(p, rp, a.batch, a.heads, stream); \
+  else { set_last_error("attention_relpos: head_dim %d not compiled (32/64/80)", a.head_dim); return ERR_UNSUPPORTED; }
+  if (a.dtype == DT_BF16) { ULLAVA_RP(__nv_bfloat16) }
+  else if (a.dtype == DT_F16) { ULLAVA_RP(__half) }
+  else { set_last_error("attention_relpos: unsupported dtype"); return ERR_UNSUPPORTED; }
+#undef ULLAVA_RP
   if (st == OK) ctx->launches++;
   return st;
 }

@@ -111,6 +111,17 @@ size_t ullava_vit_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32
   return vit_scratch(batch, img, patch, hidden, ffn, k_pad);
 }
 
+int ullava_sam_encoder_forward(ullava_ctx* ctx, const ullava_sam_encoder_args* args, void* stream) {
+  CTX_CHECK("ullava_sam_encoder_forward");
+  if (!args) { set_last_error("ullava_sam_encoder_forward: args is NULL"); return ERR_BAD_ARG; }
+  return sam_encoder_run(ctx, *args, static_cast<cudaStream_t>(stream));
+}
+
+size_t ullava_sam_encoder_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32_t embed_dim, int32_t window,
+                                        int32_t out_chans) {
+  return sam_encoder_scratch(batch, img, patch, embed_dim, window, out_chans);
+}
+
 int ullava_llama_forward(ullava_ctx* ctx, const ullava_llama_args* args, void* stream) {
   CTX_CHECK("ullava_llama_forward");
   if (!args) { set_last_error("ullava_llama_forward: args is NULL"); return ERR_BAD_ARG; }

@@ -26,11 +26,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 template <typename T, bool kRms>
 __global__ void __launch_bounds__(512)
 norm_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ w, const T* __restrict__ b,
-            T* __restrict__ y, int64_t ldy, int cols, float eps, int act) {
+            T* __restrict__ y, int64_t ldy, int cols, float eps, int act, const int32_t* __restrict__ dst_rows) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const T* xr = x + static_cast<int64_t>(row) * ldx;
-  T* yr = y + static_cast<int64_t>(row) * ldy;
+  // dst_rows (optional) scatters the output rows, e.g. SAM's window_partition fused into norm1
+  T* yr = y + static_cast<int64_t>(dst_rows ? dst_rows[row] : row) * ldy;
   const int nvec = cols >> 3;
   uint4 regs[kMaxVec];
   float sum = 0.f, sq = 0.f;
@@ -109,7 +110,8 @@ norm_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ w, const
 
 template <bool kRms>
 static int norm_launch(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
-                       int rows, int cols, float eps, int act, int dtype, cudaStream_t stream) {
+                       int rows, int cols, float eps, int act, int dtype, cudaStream_t stream,
+                       const int32_t* dst_rows = nullptr) {
   ULLAVA_REQUIRE(x && w && y && (kRms || b), "norm: null pointer");
   ULLAVA_REQUIRE(rows >= 0 && cols > 0 && (cols % 8) == 0, "norm: cols (%d) must be a positive multiple of 8", cols);
   ULLAVA_REQUIRE((ldx % 8) == 0 && (ldy % 8) == 0, "norm: ldx/ldy must be multiples of 8");
@@ -124,12 +126,12 @@ static int norm_launch(Context* ctx, const void* x, int64_t ldx, const void* w, 
   if (dtype == DT_BF16) {
     norm_kernel<__nv_bfloat16, kRms><<<rows, threads, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w),
-        static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), ldy, cols, eps, act);
+        static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), ldy, cols, eps, act, dst_rows);
   } else if (dtype == DT_F16) {
     norm_kernel<__half, kRms><<<rows, threads, 0, stream>>>(static_cast<const __half*>(x), ldx,
                                                             static_cast<const __half*>(w),
                                                             static_cast<const __half*>(b), static_cast<__half*>(y),
-                                                            ldy, cols, eps, act);
+                                                            ldy, cols, eps, act, dst_rows);
   } else {
     set_last_error("norm: unsupported dtype %d", dtype);
     return ERR_UNSUPPORTED;
@@ -139,10 +141,10 @@ static int norm_launch(Context* ctx, const void* x, int64_t ldx, const void* w, 
 }
 
 int layernorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
-                  int rows, int cols, float eps, int act, int dtype, cudaStream_t stream) {
+                  int rows, int cols, float eps, int act, int dtype, cudaStream_t stream, const int32_t* dst_rows) {
   ProfScope _ps(ctx, stream, ULLAVA_PROF_NORM, 0.0, 4.0 * rows * cols);
   ULLAVA_REQUIRE(act == EPI_NONE || act == EPI_GELU, "layernorm: act must be NONE or GELU");
-  return norm_launch<false>(ctx, x, ldx, w, b, y, ldy, rows, cols, eps, act, dtype, stream);
+  return norm_launch<false>(ctx, x, ldx, w, b, y, ldy, rows, cols, eps, act, dtype, stream, dst_rows);
 }
 int rmsnorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols,
                 float eps, int dtype, cudaStream_t stream) {

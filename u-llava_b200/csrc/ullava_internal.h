@@ -53,12 +53,15 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream);
 
 // norm.cu
 int layernorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
-                  int rows, int cols, float eps, int act, int dtype, cudaStream_t stream);
+                  int rows, int cols, float eps, int act, int dtype, cudaStream_t stream,
+                  const int32_t* dst_rows = nullptr);
 int rmsnorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int cols,
                 float eps, int dtype, cudaStream_t stream);
 
 // attention.cu
 int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream);
+int attention_relpos_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel_w, int S,
+                         const int32_t* o_row_map, cudaStream_t stream);
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
                          float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev = nullptr,
@@ -89,6 +92,10 @@ size_t sam_mask_decoder_scratch(int n);
 int sam_postprocess_run(Context* ctx, const void* masks, int64_t mask_stride, float* out, uint32_t* bits, int n,
                         int low_res, int img_size,
                         int in_h, int in_w, int out_h, int out_w, int dtype, cudaStream_t stream);
+
+// sam_encoder.cu
+int sam_encoder_run(Context* ctx, const ullava_sam_encoder_args& a, cudaStream_t s);
+size_t sam_encoder_scratch(int batch, int img, int patch, int embed_dim, int window, int out_chans);
 
 // models.cu
 int vit_forward_run(Context* ctx, const ullava_vit_args& a, cudaStream_t stream);

@@ -1,17 +1,19 @@
 """SAM ViT image encoder (reference: segment_anything/modeling/image_encoder.py:16-426).
 
-Scope note: the encoder is ON the u-LLaVA path but is not one of
-the kernels the north star names; in this round it runs as batched PyTorch-on-GPU library ops (cuBLAS
-GEMMs + SDPA with the decomposed relative-position bias passed as an additive mask) and is the first
-"next" row to be replaced by sm_100a kernels.  Same parameters / state_dict keys as the reference, so
-SAM checkpoints load unchanged.  Differences from the reference implementation that do not change the
-math: images are processed as one batch (the reference loops image by image with empty_cache() calls),
-windows are attended through scaled_dot_product_attention instead of a materialised softmax."""
+SURVEY.md section 8 row a12 / f1: the encoder is on the u-LLaVA path (models/ullava.py:139-150).
+ImageEncoderViT.forward runs ullava_sam_encoder_forward (csrc/sam_encoder.cu): tcgen05 GEMMs for the patch
+embedding, qkv / proj / MLP and the neck convolutions, flash attention with the decomposed relative-position
+bias for the windowed and global blocks.  The nn.Modules below keep the reference's parameters and
+state_dict keys, so SAM checkpoints load unchanged; their own forward() methods (plain torch ops) are NOT
+on the product path -- forward_torch() exists for tests that cross-check the kernels on a GPU.
+Images are processed as one batch (the reference loops image by image with empty_cache() calls)."""
 from typing import Optional, Tuple, Type
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+import native
 
 from .common import LayerNorm2d, MLPBlock
 
@@ -126,22 +128,102 @@ class ImageEncoderViT(nn.Module):
         self.neck = nn.Sequential(nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False), LayerNorm2d(out_chans),
                                   nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False),
                                   LayerNorm2d(out_chans))
-        self.max_images_per_pass = 8  # bounds the [B, heads, 4096, 4096] bias of the global blocks
+        self.patch_size, self.embed_dim, self.depth, self.num_heads = patch_size, embed_dim, depth, num_heads
+        self.out_chans, self.window_size, self.norm_eps = out_chans, window_size, norm_eps
+        self.global_attn_indexes = tuple(global_attn_indexes)
+        self.use_rel_pos = use_rel_pos
+        self.max_images_per_pass = 32  # bounds the activation scratch (about 0.2 GB per image for ViT-H)
+        self._packed = None
+        self._maps = {}
+        self._scratch = None
 
-    def _forward_chunk(self, x):
+    # ---- native path ---------------------------------------------------------------------------------
+    @staticmethod
+    def _rel_resized(rel_pos: torch.Tensor, size: int) -> torch.Tensor:
+        """Relative-position table with 2*size-1 rows (linear resize like the reference's get_rel_pos :321-352)."""
+        n = 2 * size - 1
+        if rel_pos.shape[0] == n:
+            return rel_pos
+        return F.interpolate(rel_pos.reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1).float(), size=n,
+                             mode="linear").reshape(-1, n).permute(1, 0).to(rel_pos.dtype)
+
+    def _pack(self):
+        if not self.use_rel_pos:
+            raise NotImplementedError("the native SAM encoder is built for use_rel_pos=True (all build_sam_* variants)")
+        dev, dt = self.patch_embed.proj.weight.device, self.patch_embed.proj.weight.dtype
+        g = self.img_size // self.patch_size
+        D, hd = self.embed_dim, self.embed_dim // self.num_heads
+        z = lambda n: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
+        pe = self.patch_embed.proj
+        t = [pe.weight.reshape(D, -1), pe.bias if pe.bias is not None else z(D),
+             self.pos_embed.reshape(g * g, D) if self.pos_embed is not None else torch.zeros((g * g, D), dtype=dt, device=dev)]
+        gmask = 0
+        for i, blk in enumerate(self.blocks):
+            is_global = blk.window_size == 0
+            if is_global:
+                gmask |= 1 << i
+            S = g if is_global else blk.window_size
+            a = blk.attn
+            t += [blk.norm1.weight, blk.norm1.bias, a.qkv.weight, a.qkv.bias if a.qkv.bias is not None else z(3 * D),
+                  self._rel_resized(a.rel_pos_h, S), self._rel_resized(a.rel_pos_w, S), a.proj.weight, a.proj.bias,
+                  blk.norm2.weight, blk.norm2.bias, blk.mlp.lin1.weight, blk.mlp.lin1.bias, blk.mlp.lin2.weight,
+                  blk.mlp.lin2.bias]
+            if not isinstance(blk.mlp.act, nn.GELU):
+                raise NotImplementedError("SAM encoder MLP activation must be GELU")
+        c1, l1, c2, l2 = self.neck[0], self.neck[1], self.neck[2], self.neck[3]
+        C = self.out_chans
+        t += [c1.weight.reshape(C, D), l1.weight, l1.bias, c2.weight.permute(0, 2, 3, 1).reshape(C, 9 * C), l2.weight,
+              l2.bias]
+        t = [x.detach().to(dt).contiguous() for x in t]
+        cfg = dict(img=self.img_size, patch=self.patch_size, embed_dim=D, depth=self.depth, heads=self.num_heads,
+                   window=self.window_size, out_chans=C, global_mask=gmask, eps=float(self.norm_eps))
+        return t, native.Context.pointer_table(t), cfg
+
+    def _row_maps(self, B: int, device):
+        """window_partition / window_unpartition (reference :263-318) as row maps over [B*g*g] tokens."""
+        key = (B, str(device))
+        if key not in self._maps:
+            g, ws = self.img_size // self.patch_size, self.window_size
+            if ws <= 0:
+                self._maps[key] = (None, None)
+            else:
+                nw = (g + ws - 1) // ws
+                b = torch.arange(B, device=device)[:, None, None]
+                y = torch.arange(g, device=device)[None, :, None]
+                x = torch.arange(g, device=device)[None, None, :]
+                win = ((b * nw + y // ws) * nw + x // ws) * (ws * ws) + (y % ws) * ws + (x % ws)
+                win = win.reshape(-1).to(torch.int32).contiguous()
+                unwin = torch.full((B * nw * nw * ws * ws,), -1, dtype=torch.int32, device=device)
+                unwin[win.long()] = torch.arange(B * g * g, dtype=torch.int32, device=device)
+                self._maps[key] = (win, unwin)
+        return self._maps[key]
+
+    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+        if x.device.type != "cuda":
+            raise RuntimeError("ImageEncoderViT (B200 build) runs on a CUDA sm_100 device only; there is no CPU fallback")
+        params = list(self.parameters())
+        sig = tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
+        if self._packed is None or self._packed[0] != sig:
+            self._packed = (sig,) + self._pack()
+        _, tensors, table, cfg = self._packed
+        ctx = native.Context.get(x.device)
+        win, unwin = self._row_maps(x.shape[0], x.device)
+        out, self._scratch = ctx.sam_encoder_forward(table, len(tensors), x.to(tensors[0].dtype).contiguous(), cfg, win,
+                                                     unwin, self._scratch)
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n = self.max_images_per_pass
+        with torch.no_grad():
+            if x.shape[0] <= n:
+                return self._forward_native(x)
+            return torch.cat([self._forward_native(x[i:i + n]) for i in range(0, x.shape[0], n)], 0)
+
+    # ---- plain torch ops, for GPU cross-checks in tests only ---------------------------------------------
+    def forward_torch(self, x: torch.Tensor) -> torch.Tensor:
         x = self.patch_embed(x)
         if self.pos_embed is not None:
             x = x + self.pos_embed
         for blk in self.blocks:
             x = blk(x)
-        x = x.permute(0, 3, 1, 2)
-        if x.dtype == torch.float16:  # the reference runs the neck in fp32 for fp16 models (overflow guard)
-            with torch.autocast(device_type="cuda", dtype=torch.float32):
-                return self.neck(x).to(torch.float16)
-        return self.neck(x)
-
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        n = self.max_images_per_pass
-        if x.shape[0] <= n:
-            return self._forward_chunk(x)
-        return torch.cat([self._forward_chunk(x[i:i + n]) for i in range(0, x.shape[0], n)], 0)
+        return self.neck(x.permute(0, 3, 1, 2))

@@ -3,8 +3,8 @@
 u-LLaVA only ever calls forward(points=None, boxes=None, masks=None, text_embeds=...) and
 get_dense_pe() (models/ullava.py:232-243,405-417).  Both are input-independent glue: the sparse
 embedding IS the text embedding, the dense embedding is a broadcast view of no_mask_embed, and the
-dense positional encoding is a constant of the module that is computed once (with the reference's
-own arithmetic, in the buffer dtype) and cached."""
+dense positional encoding is a constant of the module that is computed once (in fp32, rounded to the
+buffer dtype) and cached."""
 import math
 from typing import Optional, Tuple
 
@@ -22,15 +22,19 @@ class PositionEmbeddingRandom(nn.Module):
         self.register_buffer("positional_encoding_gaussian_matrix", scale * torch.randn((2, num_pos_feats)))
 
     def _pe_encoding(self, coords: torch.Tensor) -> torch.Tensor:
+        """sin/cos(2*pi*(2c-1)@G) evaluated in fp32 from the stored (possibly 16-bit) matrix and rounded once at
+        the end.  The reference evaluates it in the buffer dtype (prompt_encoder.py:203-229), which under bf16
+        carries ~0.1 absolute noise in the angle; the fp32 evaluation stays inside that noise band and matches
+        the fp32 reference to the last bit of the 16-bit output."""
         g = self.positional_encoding_gaussian_matrix
-        coords = (2 * coords - 1).to(g.dtype)
-        coords = 2 * math.pi * (coords @ g)
-        return torch.cat([coords.sin(), coords.cos()], dim=-1)
+        coords = 2 * coords.float() - 1
+        coords = 2 * math.pi * (coords @ g.float())
+        return torch.cat([coords.sin(), coords.cos()], dim=-1).to(g.dtype)
 
     def forward(self, size: Tuple[int, int]) -> torch.Tensor:
         h, w = size
         g = self.positional_encoding_gaussian_matrix
-        ones = torch.ones((h, w), device=g.device, dtype=g.dtype)
+        ones = torch.ones((h, w), device=g.device, dtype=torch.float32)
         y = (ones.cumsum(dim=0) - 0.5) / h
         x = (ones.cumsum(dim=1) - 0.5) / w
         return self._pe_encoding(torch.stack([x, y], dim=-1)).permute(2, 0, 1)

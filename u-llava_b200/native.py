@@ -58,6 +58,14 @@ class VitArgs(C.Structure):
                 ("dtype", _i32)]
 
 
+class SamEncoderArgs(C.Structure):
+    _fields_ = [("weights", C.POINTER(_vp)), ("n_weights", _i32), ("pixels", _vp), ("out", _vp),
+                ("scratch", _vp), ("scratch_bytes", _sz), ("win_rows", _vp), ("unwin_rows", _vp),
+                ("batch", _i32), ("img", _i32), ("patch", _i32), ("embed_dim", _i32), ("depth", _i32),
+                ("heads", _i32), ("window", _i32), ("out_chans", _i32), ("global_mask", C.c_uint64),
+                ("eps", _f32), ("dtype", _i32)]
+
+
 class LlamaArgs(C.Structure):
     _fields_ = [("weights", C.POINTER(_vp)), ("n_weights", _i32), ("hidden", _vp), ("final_out", _vp),
                 ("all_hidden", _vp), ("k_cache", _vp), ("v_cache", _vp), ("scratch", _vp), ("scratch_bytes", _sz),
@@ -102,6 +110,8 @@ _SIGNATURES = {
                                       _vp]),
     "ullava_vit_forward": (_i32, [_vp, C.POINTER(VitArgs), _vp]),
     "ullava_vit_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "ullava_sam_encoder_forward": (_i32, [_vp, C.POINTER(SamEncoderArgs), _vp]),
+    "ullava_sam_encoder_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "ullava_llama_forward": (_i32, [_vp, C.POINTER(LlamaArgs), _vp]),
     "ullava_llama_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
@@ -400,6 +410,25 @@ class Context:
         a.dtype = dtype_code(pixels.dtype)
         self._chk(self.lib.ullava_vit_forward(self.handle, C.byref(a), _stream()))
         return out
+
+    def sam_encoder_forward(self, weight_table, n_weights, pixels, cfg: dict, win_rows, unwin_rows, scratch=None):
+        """SAM ViT image encoder: pixels [B,3,img,img] -> [B,out_chans,g,g] (NCHW)."""
+        B = pixels.shape[0]
+        g = cfg["img"] // cfg["patch"]
+        out = torch.empty((B, cfg["out_chans"], g, g), dtype=pixels.dtype, device=pixels.device)
+        sb = int(self.lib.ullava_sam_encoder_scratch_bytes(B, cfg["img"], cfg["patch"], cfg["embed_dim"],
+                                                           cfg["window"], cfg["out_chans"]))
+        if scratch is None or scratch.numel() < sb:
+            scratch = torch.empty(sb, dtype=torch.uint8, device=pixels.device)
+        a = SamEncoderArgs()
+        a.weights, a.n_weights, a.pixels, a.out = weight_table, n_weights, pixels.data_ptr(), out.data_ptr()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        a.win_rows, a.unwin_rows = _ptr(win_rows), _ptr(unwin_rows)
+        a.batch, a.img, a.patch, a.embed_dim = B, cfg["img"], cfg["patch"], cfg["embed_dim"]
+        a.depth, a.heads, a.window, a.out_chans = cfg["depth"], cfg["heads"], cfg["window"], cfg["out_chans"]
+        a.global_mask, a.eps, a.dtype = cfg["global_mask"], cfg["eps"], dtype_code(pixels.dtype)
+        self._chk(self.lib.ullava_sam_encoder_forward(self.handle, C.byref(a), _stream()))
+        return out, scratch
 
     def llama_decode_step(self, args: "DecodeArgs"):
         """One greedy decode step with the position in device memory (CUDA-graph replayable)."""
