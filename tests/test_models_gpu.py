@@ -171,7 +171,15 @@ def test_sam_decoder_full_geometry(ctx, dtype):
     text = synth_normal("sam_text", (3, 1, 256), seed=1).cuda().to(dtype)
     sparse, dense = sam.prompt_encoder(points=None, boxes=None, masks=None, text_embeds=text)
     pe = sam.prompt_encoder.get_dense_pe()
-    assert max_err(subsample(pe.float().cpu(), 8192)[0], g["dense_pe_sub"]) < 2e-2
+    # The Gaussian projection matrix is a *parameter*: storing it in 16 bits perturbs the angle 2*pi*(c@G) by up to
+    # |angle| * 2^-9 (~0.15 rad in bf16) before any arithmetic happens, in the reference exactly as here.  The
+    # arithmetic is therefore checked against the oracle on the same 16-bit-rounded matrix; fp16 (11 bits) must also
+    # meet the fp32 golden directly.
+    gkey = "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"
+    pe_ref = O.sam_dense_pe({gkey: sd[gkey].to(dtype).float()}, "")
+    assert max_err(pe, pe_ref) < 2e-2
+    if dtype == torch.float16:
+        assert max_err(subsample(pe.float().cpu(), 8192)[0], g["dense_pe_sub"]) < 2e-2
     masks, iou_pred = sam.mask_decoder.predict_masks(emb, pe, sparse.to(dtype), dense)
     assert masks.shape == (3, 4, 256, 256)
     ref_sub = torch.as_tensor(g["masks_sub"])
