@@ -140,6 +140,20 @@ typedef struct ullava_attn_args {
 } ullava_attn_args;
 ULLAVA_API int ullava_attention(ullava_ctx* ctx, const ullava_attn_args* args, void* stream);
 
+/* Attention of the SAM ViT image encoder with decomposed relative-position bias
+ * (segment_anything/modeling/image_encoder.py:196-260, add_decomposed_rel_pos :355-392):
+ *   softmax(scale * q k^T + q . rel_h[qh - kh + S - 1] + q . rel_w[qw - kw + S - 1]) v
+ * over a grid_side x grid_side token grid (seq_q == seq_k == grid_side^2), rel_h / rel_w: [2*grid_side-1, head_dim].
+ * o_row_map (optional, int32 [batch*seq_q]): output row of each query row in units of o_rs (window_unpartition;
+ * -1 drops the row), in which case o_bs is ignored. */
+ULLAVA_API int ullava_attention_relpos(ullava_ctx* ctx, const ullava_attn_args* args, const void* rel_h, const void* rel_w,
+                                       int32_t grid_side, const int32_t* o_row_map, void* stream);
+
+/* Kernel selection for ullava_attention / ullava_attention_relpos and the model-level entry points:
+ * 0 (default) = tcgen05/TMEM flash attention for head_dim 64 / 80 / 128, 1 = warp-level mma.sync kernels only
+ * (kept for A/B measurements; both are sm_100a code, neither is a fallback to another device or library). */
+ULLAVA_API int ullava_set_attention_impl(ullava_ctx* ctx, int32_t impl);
+
 /* Single-query (decode) attention against a KV cache [batch, heads, max_seq, head_dim]:
  * LlamaAttention with past_key_values, one new token per sample.  ctx_len keys are attended. */
 ULLAVA_API int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q_bs, const void* k_cache, const void* v_cache,

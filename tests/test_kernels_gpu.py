@@ -210,6 +210,97 @@ def test_flash_attention(ctx, dtype, B, H, Sq, Sk, D, causal, pos0):
     _check(out, ref, dtype, f"attention {B,H,Sq,Sk,D,causal}")
 
 
+@pytest.fixture
+def legacy_attention(ctx):
+    ctx.set_attention_impl(1)
+    yield ctx
+    ctx.set_attention_impl(0)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,pos0", [
+    (2, 16, 577, 577, 64, False, 0), (2, 4, 608, 608, 128, True, 0), (1, 2, 100, 164, 128, True, 64),
+])
+def test_flash_attention_warp_level_kernel(legacy_attention, dtype, B, H, Sq, Sk, D, causal, pos0):
+    """The mma.sync kernels stay selectable (ullava_set_attention_impl) for A/B measurements; keep them correct."""
+    qkv = _rand((B, max(Sq, Sk), 3, H, D), dtype, seed=41)
+    q, k, v = qkv[:, :Sq, 0], qkv[:, :Sk, 1], qkv[:, :Sk, 2]
+    out = legacy_attention.attention(q, k, v, causal=causal, q_pos0=pos0)
+    _check(out, _attn_ref(q, k, v, causal, pos0, D ** -0.5), dtype, f"legacy attention {B,H,Sq,Sk,D,causal}")
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal,pos0", [
+    (1, 1, 128, 128, 64, False, 0),      # exactly one tile, one 128-byte slab
+    (1, 1, 128, 128, 128, False, 0),     # two slabs
+    (1, 1, 128, 128, 80, False, 0),      # 64-column slab + 16-column SWIZZLE_32B tail
+    (1, 2, 128, 384, 64, False, 0),      # three key tiles: ring + online softmax
+    (2, 3, 300, 1000, 80, False, 0),     # ragged rows / keys
+    (1, 2, 640, 640, 128, True, 0),      # causal, diagonal tiles
+    (2, 2, 33, 2049, 128, True, 2016),   # chunked prefill deep into a cache
+    (1, 1, 256, 4096, 64, False, 0),     # long key sequence: lazy rescale over 32 tiles
+])
+def test_flash_attention_tcgen05_tiles(ctx, dtype, B, H, Sq, Sk, D, causal, pos0):
+    qkv = _rand((B, max(Sq, Sk), 3, H, D), dtype, seed=42)
+    q, k, v = qkv[:, :Sq, 0], qkv[:, :Sk, 1], qkv[:, :Sk, 2]
+    out = ctx.attention(q, k, v, causal=causal, q_pos0=pos0)
+    _check(out, _attn_ref(q, k, v, causal, pos0, D ** -0.5), dtype, f"tcgen05 attention {B,H,Sq,Sk,D,causal}")
+
+
+def test_flash_attention_rescale_growing_maximum(ctx):
+    """Scores that keep growing along the key axis force the O / row-sum rescale on every tile."""
+    B, H, S, D = 1, 2, 1024, 64
+    q = _rand((B, S, H, D), torch.bfloat16, seed=43)
+    k = _rand((B, S, H, D), torch.bfloat16, seed=44)
+    v = _rand((B, S, H, D), torch.bfloat16, seed=45)
+    ramp = torch.linspace(0.2, 6.0, S, device="cuda")[None, :, None, None]
+    k = (k.float() * 0.1 + q.float().mean(1, keepdim=True) * ramp).to(torch.bfloat16)
+    out = ctx.attention(q, k, v)
+    _check(out, _attn_ref(q, k, v, False, 0, D ** -0.5), torch.bfloat16, "growing-max attention")
+
+
+def _relpos_ref(q, k, v, rel_h, rel_w, S, scale):
+    """segment_anything/modeling/image_encoder.py:196-260 + add_decomposed_rel_pos (:355-392), fp32."""
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))           # [B, H, N, D]
+    attn = qf @ kf.transpose(-1, -2) * scale
+    idx = torch.arange(S, device=q.device)
+    rel = idx[:, None] - idx[None, :] + (S - 1)
+    Rh, Rw = rel_h.float()[rel], rel_w.float()[rel]                            # [S, S, D]
+    B, H, N, D = qf.shape
+    r_q = qf.reshape(B, H, S, S, D)
+    bh = torch.einsum("bnhwc,hkc->bnhwk", r_q, Rh)
+    bw = torch.einsum("bnhwc,wkc->bnhwk", r_q, Rw)
+    attn = (attn.view(B, H, S, S, S, S) + bh[..., :, None] + bw[..., None, :]).view(B, H, N, N)
+    return (torch.softmax(attn, -1) @ vf).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,S,D", [(3, 2, 14, 80), (1, 2, 64, 80), (2, 2, 9, 64), (50, 16, 14, 80)])
+def test_attention_relpos(ctx, dtype, impl, B, H, S, D):
+    N = S * S
+    qkv = _rand((B, N, 3, H, D), dtype, seed=46)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    rel_h = _rand((2 * S - 1, D), dtype, scale=0.5, seed=47)
+    rel_w = _rand((2 * S - 1, D), dtype, scale=0.5, seed=48)
+    ctx.set_attention_impl(impl)
+    try:
+        out = ctx.attention_relpos(q, k, v, rel_h, rel_w, S)
+        # scattered output rows (window_unpartition): reverse the row order, drop every 7th row
+        rows = torch.arange(B * N, device="cuda", dtype=torch.int32).flip(0).contiguous()
+        rows[::7] = -1
+        scat = torch.zeros((B * N, H, D), dtype=dtype, device="cuda")
+        ctx.attention_relpos(q, k, v, rel_h, rel_w, S, out=scat.view(B, N, H, D), o_row_map=rows)
+    finally:
+        ctx.set_attention_impl(0)
+    ref = _relpos_ref(q, k, v, rel_h, rel_w, S, D ** -0.5)
+    _check(out, ref, dtype, f"relpos attention impl={impl} {B,H,S,D}")
+    keep = rows >= 0
+    exp = torch.zeros_like(scat)
+    exp[rows[keep].long()] = out.reshape(B * N, H, D)[keep]
+    assert torch.equal(scat, exp)
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("B,H,D,ctx_len,max_seq", [(2, 32, 128, 609, 672), (32, 32, 128, 672, 672), (3, 4, 64, 5, 16),
                                                    (1, 2, 16, 33, 40), (2, 2, 32, 1, 8)])

@@ -31,6 +31,20 @@ int ullava_attention(ullava_ctx* ctx, const ullava_attn_args* args, void* stream
   return attention_run(ctx, *args, static_cast<cudaStream_t>(stream));
 }
 
+int ullava_attention_relpos(ullava_ctx* ctx, const ullava_attn_args* args, const void* rel_h, const void* rel_w,
+                             int32_t grid_side, const int32_t* o_row_map, void* stream) {
+  CTX_CHECK("ullava_attention_relpos");
+  if (!args) { set_last_error("ullava_attention_relpos: args is NULL"); return ERR_BAD_ARG; }
+  return attention_relpos_run(ctx, *args, rel_h, rel_w, grid_side, o_row_map, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_set_attention_impl(ullava_ctx* ctx, int32_t impl) {
+  CTX_CHECK("ullava_set_attention_impl");
+  if (impl != 0 && impl != 1) { set_last_error("ullava_set_attention_impl: impl must be 0 or 1"); return ERR_BAD_ARG; }
+  ctx->attn_impl = impl;
+  return OK;
+}
+
 int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q_bs, const void* k_cache, const void* v_cache,
                             int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
                             int32_t head_dim, int32_t ctx_len, float scale, int32_t dtype, void* stream) {

@@ -1,0 +1,526 @@
+// tcgen05 / TMEM flash attention for the u-LLaVA hot path (sm_100a).
+//
+//   softmax(scale * Q K^T [+ rel-pos bias] [causal mask]) V      fp32 scores, fp32 online softmax
+//
+// Call sites it serves (reference file:line):
+//   * CLIP ViT-L/14 self-attention, hd 64, S = 577        hf:models/clip/modeling_clip.py:282-336
+//   * LLaMA prefill causal attention, hd 128, S = 608     hf:models/llama/modeling_llama.py:199-291
+//   * SAM ViT-H windowed (14x14) and global (64x64) attention with decomposed relative-position bias,
+//     hd 80                                               segment_anything/modeling/image_encoder.py:196-260,355-392
+//
+// One CTA = one 128-row query tile of one (batch, head).  192 threads:
+//   warp 0      TMA producer: Q once, then K/V tiles of 128 keys through a STAGES-deep ring
+//               (cp.async.bulk.tensor.4d over the strided [d, token, head, batch] view, SWIZZLE_128B slabs of
+//               64 columns plus, for hd 80, one SWIZZLE_32B slab of 16 columns);
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
+//                 S_j   = Q K_j^T        (SS form: A = Q smem K-major, B = K smem K-major, N = 128)
+//                 O    += P_j V_j        (TS form: A = P_j in TMEM, B = V smem MN-major, N = hd)
+//               S is double buffered in TMEM (2 x 128 columns) so QK^T of tile j+1 runs under the softmax of tile j;
+//               P_j overwrites the first 64 columns of its own S buffer as packed 16-bit pairs;
+//   warps 2-5   softmax: one thread per query row (no shuffles).  Pass 1 takes the row maximum straight from
+//               TMEM, pass 2 re-reads, exponentiates (one MUFU.EX2 per score), accumulates the row sum and
+//               stores P.  O lives in TMEM for the whole CTA; it is only rescaled when the running maximum grew by
+//               more than 2^8 ("lazy rescale" - the stale maximum is used consistently for P and the row sum, so the
+//               result is exact), which after the first tiles practically never happens.
+// Rel-pos bias: the prologue runs Q Rh^T and Q Rw^T through the same MMA path into the two S buffers; each softmax
+// thread turns its two rows into per-row tables A_h[kh], A_w[kw] (x log2 e, fp32, shared memory), so that in the
+// main loop bias(q, k) = A_h[kh(k)] + A_w[kw(k)].  For the 64x64 global grid a key tile is exactly two grid rows:
+// A_w sits in 64 registers and A_h costs two shared loads per tile.
+#include "common.cuh"
+#include "ullava_internal.h"
+
+namespace ullava {
+
+static constexpr int FM_BM = 128;       // query rows per CTA (= TMEM lanes)
+static constexpr int FM_BN = 128;       // keys per tile
+static constexpr int FM_THREADS = 192;
+static constexpr int FM_TMEM_COLS = 512;
+static constexpr int FM_COL_S = 0;      // S buffers: columns [0,128) and [128,256)
+static constexpr int FM_COL_O = 256;    // O accumulator: columns [256, 256 + hd)
+static constexpr float FM_RESCALE_THRESHOLD = 8.f;  // log2 units
+
+struct FmhaMaps {
+  CUtensorMap q, qt, k, kt, v, vt, rh, rht, rw, rwt;  // *t = tail slab (hd % 64 columns, SWIZZLE_32B)
+};
+
+struct FmhaParams {
+  void* o;
+  int64_t o_bs, o_rs, o_hs;
+  const int32_t* o_row_map;
+  int seq_q, seq_k, causal, q_pos0;
+  float scale_log2;
+  int S;  // rel-pos grid side (RP != 0)
+};
+
+template <int HD>
+struct FmhaCfg {
+  static constexpr int NS = HD / 64;                      // 64-column SWIZZLE_128B slabs
+  static constexpr int TAIL = HD % 64;                    // 0 or 16 columns in a SWIZZLE_32B slab
+  static constexpr int SLAB = 128 * 128;                  // bytes: 128 rows x 128 B
+  static constexpr int TAIL_BYTES = 128 * TAIL * 2;
+  static constexpr int TILE = NS * SLAB + TAIL_BYTES;     // one Q / K / V tile
+  static constexpr int STAGES = HD == 64 ? 4 : 3;
+  static constexpr int BAR_BYTES = (1 + 3 * STAGES + 2 + 2 + 1 + 1) * 8 + 16;
+  static_assert(TAIL == 0 || TAIL == 16, "head_dim must be 64, 80 or 128");
+  static constexpr int smem_bytes(int table_floats) {
+    return 1024 + TILE * (1 + 2 * STAGES) + table_floats * 4 + BAR_BYTES;
+  }
+};
+
+// ---- MMA issue helpers (one thread) -----------------------------------------------------------------------------
+template <typename T, int HD>
+__device__ __forceinline__ void fmha_issue_qk(uint32_t d_tmem, uint32_t q_smem, uint32_t k_smem) {
+  using C = FmhaCfg<HD>;
+  constexpr uint32_t idesc = make_idesc_f16(T16<T>::kUmmaFormat, FM_BM, FM_BN);
+#pragma unroll
+  for (int s = 0; s < C::NS; ++s) {
+    const uint64_t a = make_smem_desc(q_smem + s * C::SLAB, 16, 1024, 2);
+    const uint64_t b = make_smem_desc(k_smem + s * C::SLAB, 16, 1024, 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16<1>(d_tmem, a + 2u * k, b + 2u * k, idesc, (s | k) ? 1u : 0u);
+  }
+  if constexpr (C::TAIL != 0) {
+    const uint64_t a = make_smem_desc(q_smem + C::NS * C::SLAB, 16, 256, 6);
+    const uint64_t b = make_smem_desc(k_smem + C::NS * C::SLAB, 16, 256, 6);
+    umma_f16<1>(d_tmem, a, b, idesc, 1u);
+  }
+}
+
+template <typename T, int HD>
+__device__ __forceinline__ void fmha_issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint32_t v_smem, bool first_tile) {
+  using C = FmhaCfg<HD>;
+  // B = V tile [128 keys x hd], hd contiguous: MN-major
+  constexpr uint32_t idesc_main = make_idesc_f16(T16<T>::kUmmaFormat, FM_BM, C::NS * 64) | (1u << 16);
+  constexpr uint32_t idesc_tail = make_idesc_f16(T16<T>::kUmmaFormat, FM_BM, 16) | (1u << 16);
+#pragma unroll
+  for (int ks = 0; ks < FM_BN / 16; ++ks) {
+    const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
+    const uint64_t b = make_smem_desc(v_smem + ks * 2048, C::SLAB, 1024, 2);
+    umma_f16_ts(o_tmem, p_tmem + ks * 8, b, idesc_main, acc);
+    if constexpr (C::TAIL != 0) {
+      const uint64_t bt = make_smem_desc(v_smem + C::NS * C::SLAB + ks * 512, 16, 256, 6);
+      umma_f16_ts(o_tmem + C::NS * 64, p_tmem + ks * 8, bt, idesc_tail, acc);
+    }
+  }
+}
+
+// RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
+template <typename T, int HD, int RP>
+__global__ void __launch_bounds__(FM_THREADS, 1)
+fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
+  using C = FmhaCfg<HD>;
+  constexpr int ST = C::STAGES;
+  extern __shared__ uint8_t fm_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fm_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + C::TILE;  // stage s: K at sKV + s*2*TILE, V right after
+  const int S = RP ? p.S : 0;
+  const int pstride = 2 * S + 1;  // odd: the 32 rows of a warp hit 32 different banks
+  float* tabs = reinterpret_cast<float*>(smem + C::TILE * (1 + 2 * ST));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tabs) + (RP ? FM_BM * pstride * 4 : 0));
+  bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* v_full = k_full + ST;
+  uint64_t* kv_empty = v_full + ST;
+  uint64_t* s_full = kv_empty + ST;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_done = p_full + 2;
+  uint64_t* pro_done = pv_done + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pro_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_qt = gridDim.x;
+  const int qt = p.causal ? (n_qt - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);  // heavy tiles first
+  const int m0 = qt * FM_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+
+  int k_end = p.seq_k;
+  if (p.causal) k_end = min(k_end, p.q_pos0 + m0 + FM_BM);
+  const int n_tiles = (k_end + FM_BN - 1) / FM_BN;
+  constexpr int kRP = RP ? 1 : 0;
+  constexpr int kChunkUnroll = (RP == 1) ? 1 : 4;  // the generic-grid bias path keeps one 32-column chunk live
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(pv_done, 1);
+    mbar_init(pro_done, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr, FM_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::TILE);
+#pragma unroll
+      for (int s = 0; s < C::NS; ++s) tma_load_4d(sQ + s * C::SLAB, &maps.q, q_full, s * 64, m0, h, b);
+      if constexpr (C::TAIL != 0) tma_load_4d(sQ + C::NS * C::SLAB, &maps.qt, q_full, C::NS * 64, m0, h, b);
+      if constexpr (RP != 0) {
+        // pipeline item 0: the two rel-pos tables take the place of a K and a V tile (rows >= 2S-1 are zero-filled)
+        uint8_t* sk = sKV;
+        uint8_t* sv = sk + C::TILE;
+        mbar_expect_tx(&k_full[0], C::TILE);
+#pragma unroll
+        for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.rh, &k_full[0], s * 64, 0, 0, 0);
+        if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.rht, &k_full[0], C::NS * 64, 0, 0, 0);
+        mbar_expect_tx(&v_full[0], C::TILE);
+#pragma unroll
+        for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.rw, &v_full[0], s * 64, 0, 0, 0);
+        if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.rwt, &v_full[0], C::NS * 64, 0, 0, 0);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int it = j + kRP;
+        const int st = it % ST;
+        const uint32_t ph = static_cast<uint32_t>(it / ST) & 1u;
+        mbar_wait(&kv_empty[st], ph ^ 1u);
+        uint8_t* sk = sKV + st * 2 * C::TILE;
+        uint8_t* sv = sk + C::TILE;
+        mbar_expect_tx(&k_full[st], C::TILE);
+#pragma unroll
+        for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.k, &k_full[st], s * 64, j * FM_BN, h, b);
+        if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.kt, &k_full[st], C::NS * 64, j * FM_BN, h, b);
+        mbar_expect_tx(&v_full[st], C::TILE);
+#pragma unroll
+        for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.v, &v_full[st], s * 64, j * FM_BN, h, b);
+        if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.vt, &v_full[st], C::NS * 64, j * FM_BN, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t q_s = smem_u32(sQ);
+      const uint32_t kv_s = smem_u32(sKV);
+      const uint32_t o_tmem = tmem_base + FM_COL_O;
+      mbar_wait(q_full, 0);
+      if constexpr (RP != 0) {
+        mbar_wait(&k_full[0], 0);
+        mbar_wait(&v_full[0], 0);
+        tc_fence_after();
+        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S, q_s, kv_s);                       // Ph = Q Rh^T
+        umma_commit<1>(&s_full[0]);
+        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + FM_BN, q_s, kv_s + C::TILE);     // Pw = Q Rw^T
+        umma_commit<1>(&s_full[1]);
+        umma_commit<1>(&kv_empty[0]);
+        mbar_wait(pro_done, 0);  // softmax threads have moved both tables out of TMEM
+      }
+      {
+        const int it = kRP, st = it % ST;
+        mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
+        tc_fence_after();
+        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S, q_s, kv_s + st * 2 * C::TILE);
+        umma_commit<1>(&s_full[0]);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          const int it = j + 1 + kRP, st = it % ST;
+          mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
+          tc_fence_after();
+          fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + ((j + 1) & 1) * FM_BN, q_s, kv_s + st * 2 * C::TILE);
+          umma_commit<1>(&s_full[(j + 1) & 1]);
+        }
+        const int it = j + kRP, st = it % ST;
+        mbar_wait(&v_full[st], static_cast<uint32_t>(it / ST) & 1u);
+        mbar_wait(&p_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);
+        tc_fence_after();
+        fmha_issue_pv<T, HD>(o_tmem, tmem_base + FM_COL_S + (j & 1) * FM_BN, kv_s + st * 2 * C::TILE + C::TILE, j == 0);
+        umma_commit<1>(&kv_empty[st]);
+        umma_commit<1>(pv_done);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;            // row inside the tile
+    const int qrow = m0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t o_taddr = tmem_base + lane_off + FM_COL_O;
+    const float sl2 = p.scale_log2;
+    float* Ah = tabs + row * pstride;
+    float* Aw = Ah + S;
+    float aw[RP == 2 ? 64 : 1];
+
+    if constexpr (RP != 0) {
+      constexpr float kLog2e = 1.4426950408889634f;
+      const int qr = min(qrow, p.seq_q - 1);
+      const int qh = qr / S, qw = qr - qh * S;
+      mbar_wait(&s_full[0], 0);
+      mbar_wait(&s_full[1], 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tb = 0; tb < 2; ++tb) {
+        const uint32_t ts = tmem_base + lane_off + FM_COL_S + tb * FM_BN;
+        float* dst = tb ? Aw : Ah;
+        const int base = (tb ? qw : qh) + S - 1;   // table column r  ->  index base - r
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 >= 2 * S - 1) break;
+          uint32_t r[32];
+          tmem_ld_32x32(ts + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int idx = base - (c * 32 + i);
+            if (idx >= 0 && idx < S) dst[idx] = __uint_as_float(r[i]) * kLog2e;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(pro_done);
+      if constexpr (RP == 2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) aw[i] = Aw[i];
+      }
+    }
+
+    float m_used = 0.f, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int buf = j & 1;
+      const uint32_t ts = tmem_base + lane_off + FM_COL_S + buf * FM_BN;
+      const int key0 = j * FM_BN;
+      const bool need_mask = (key0 + FM_BN > p.seq_k) || (p.causal && (key0 + FM_BN - 1 > p.q_pos0 + m0));
+      const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
+      float ah0 = 0.f, ah1 = 0.f;
+      if constexpr (RP == 2) {
+        ah0 = Ah[2 * j];
+        ah1 = Ah[2 * j + 1];
+      }
+      int kh0 = 0, kw0 = 0;
+      if constexpr (RP == 1) {
+        kh0 = key0 / S;
+        kw0 = key0 - kh0 * S;
+      }
+      mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) + kRP) & 1u);
+      tc_fence_after();
+
+      // score of column `col` of this tile in log2 units
+#define FMHA_SCORE(raw, c, i, kh, kw)                                                              \
+      ((RP == 0) ? (raw) * sl2                                                                      \
+       : (RP == 2) ? fmaf((raw), sl2, aw[(RP == 2) ? (((c) & 1) * 32 + (i)) : 0]) + (((c) >> 1) ? ah1 : ah0) \
+                   : fmaf((raw), sl2, Ah[min((kh), S - 1)] + Aw[(kw)]))
+
+      // ---- pass 1: row maximum ----
+      float mx = -INFINITY;
+      {
+        int kh = kh0, kw = kw0;
+#pragma unroll(kChunkUnroll)
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(ts + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
+            if (need_mask && (key0 + c * 32 + i >= key_lim)) x = -INFINITY;
+            mx = fmaxf(mx, x);
+            if constexpr (RP == 1) {
+              if (++kw == S) { kw = 0; ++kh; }
+            }
+          }
+        }
+      }
+      // ---- lazy rescale of O and the row sum ----
+      bool grow;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_used = (mx == -INFINITY) ? 0.f : mx;
+        grow = false;
+      } else {
+        grow = mx > m_used + FM_RESCALE_THRESHOLD;
+        if (grow) {
+          alpha = ex2_approx(m_used - mx);
+          m_used = mx;
+          l_run *= alpha;
+        }
+      }
+      if (__any_sync(0xffffffffu, grow)) {
+        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);  // O holds tiles 0..j-1
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld_32x16(o_taddr + c * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_32x16(o_taddr + c * 16, r);
+        }
+      }
+      // ---- pass 2: P = 2^(x - m), row sum, P -> TMEM (packed 16-bit, over the S columns already consumed) ----
+      {
+        int kh = kh0, kw = kw0;
+        float sum = 0.f;
+#pragma unroll(kChunkUnroll)
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(ts + c * 32, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0 = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
+            if (need_mask && (key0 + c * 32 + i >= key_lim)) x0 = -INFINITY;
+            if constexpr (RP == 1) {
+              if (++kw == S) { kw = 0; ++kh; }
+            }
+            float x1 = FMHA_SCORE(__uint_as_float(r[i + 1]), c, i + 1, kh, kw);
+            if (need_mask && (key0 + c * 32 + i + 1 >= key_lim)) x1 = -INFINITY;
+            if constexpr (RP == 1) {
+              if (++kw == S) { kw = 0; ++kh; }
+            }
+            const float p0 = ex2_approx(x0 - m_used);
+            const float p1 = ex2_approx(x1 - m_used);
+            sum += p0 + p1;
+            pk[i >> 1] = pack2<T>(p0, p1);
+          }
+          tmem_st_32x16(ts + c * 16, pk);
+        }
+        l_run += sum;
+      }
+#undef FMHA_SCORE
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[buf]);
+    }
+
+    // ---- epilogue: O / l -> global ----
+    mbar_wait(pv_done, static_cast<uint32_t>(n_tiles - 1) & 1u);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    T* orow = nullptr;
+    if (qrow < p.seq_q) {
+      if (p.o_row_map) {
+        const int dst = p.o_row_map[static_cast<int64_t>(b) * p.seq_q + qrow];
+        if (dst >= 0) orow = static_cast<T*>(p.o) + static_cast<int64_t>(dst) * p.o_rs + h * p.o_hs;
+      } else {
+        orow = static_cast<T*>(p.o) + b * p.o_bs + static_cast<int64_t>(qrow) * p.o_rs + h * p.o_hs;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x16(o_taddr + c * 16, r);
+      tmem_ld_wait();
+      if (orow) {
+        uint4 w0, w1;
+        w0.x = pack2<T>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+        w0.y = pack2<T>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+        w0.z = pack2<T>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+        w0.w = pack2<T>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+        w1.x = pack2<T>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+        w1.y = pack2<T>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+        w1.z = pack2<T>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+        w1.w = pack2<T>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+        *reinterpret_cast<uint4*>(orow + c * 16) = w0;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = w1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, FM_TMEM_COLS);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Host side
+// -----------------------------------------------------------------------------------------------------------------
+static int fmha_map(CUtensorMap* main_map, CUtensorMap* tail_map, const void* base, int hd, int64_t rows, int64_t heads,
+                    int64_t batch, int64_t rs, int64_t hs, int64_t bs) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(rows), static_cast<uint64_t>(heads),
+                            static_cast<uint64_t>(batch)};
+  // a dimension of extent 1 never uses its stride; keep it a valid multiple of 16 bytes
+  const uint64_t st[3] = {static_cast<uint64_t>(rs > 0 ? rs : hd) * 2, static_cast<uint64_t>(hs > 0 ? hs : hd) * 2,
+                          static_cast<uint64_t>(bs > 0 ? bs : hd) * 2};
+  int e = encode_tmap_4d(main_map, base, dims, st, 64, FM_BM, 128);
+  if (e) return e;
+  if (hd % 64) e = encode_tmap_4d(tail_map, base, dims, st, hd % 64, FM_BM, 32);
+  else *tail_map = *main_map;
+  return e;
+}
+
+template <typename T, int HD, int RP>
+static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int heads, cudaStream_t stream) {
+  using C = FmhaCfg<HD>;
+  const int smem = C::smem_bytes(RP ? FM_BM * (2 * p.S + 1) : 0);
+  auto kern = fmha_tcgen05_kernel<T, HD, RP>;
+  static int configured = 0;
+  if (smem > configured) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid((p.seq_q + FM_BM - 1) / FM_BM, heads, batch);
+  kern<<<grid, FM_THREADS, smem, stream>>>(maps, p);
+  return check_cuda(cudaGetLastError(), "fmha_tcgen05 launch");
+}
+
+bool fmha_supported(const AttnArgs& a, bool relpos, int S) {
+  if (a.head_dim != 64 && a.head_dim != 80 && a.head_dim != 128) return false;
+  if (a.dtype != DT_BF16 && a.dtype != DT_F16) return false;
+  if (a.batch > 65535 || a.heads > 65535) return false;
+  if (relpos && (S < 1 || S > 64 || a.causal)) return false;
+  if (relpos && FmhaCfg<80>::smem_bytes(FM_BM * (2 * S + 1)) > 227 * 1024) return false;
+  return true;
+}
+
+// rel_h / rel_w == nullptr: plain (optionally causal) attention.
+int fmha_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel_w, int S, const int32_t* o_row_map,
+             cudaStream_t stream) {
+  const bool relpos = rel_h != nullptr;
+  FmhaMaps maps;
+  int e;
+  if ((e = fmha_map(&maps.q, &maps.qt, a.q, a.head_dim, a.seq_q, a.heads, a.batch, a.q_rs, a.q_hs, a.q_bs))) return e;
+  if ((e = fmha_map(&maps.k, &maps.kt, a.k, a.head_dim, a.seq_k, a.heads, a.batch, a.k_rs, a.k_hs, a.k_bs))) return e;
+  if ((e = fmha_map(&maps.v, &maps.vt, a.v, a.head_dim, a.seq_k, a.heads, a.batch, a.v_rs, a.v_hs, a.v_bs))) return e;
+  if (relpos) {
+    if ((e = fmha_map(&maps.rh, &maps.rht, rel_h, a.head_dim, 2 * S - 1, 1, 1, a.head_dim, 0, 0))) return e;
+    if ((e = fmha_map(&maps.rw, &maps.rwt, rel_w, a.head_dim, 2 * S - 1, 1, 1, a.head_dim, 0, 0))) return e;
+  } else {
+    maps.rh = maps.rht = maps.rw = maps.rwt = maps.q;
+  }
+  FmhaParams p;
+  p.o = a.o; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.o_hs = a.o_hs;
+  p.o_row_map = o_row_map;
+  p.seq_q = a.seq_q; p.seq_k = a.seq_k; p.causal = a.causal; p.q_pos0 = a.q_pos0;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.S = S;
+  int st = ERR_UNSUPPORTED;
+#define ULLAVA_FMHA(TT)                                                                                   \
+  if (relpos) {                                                                                            \
+    if (a.head_dim == 80 && S == 64) st = fmha_launch<TT, 80, 2>(maps, p, a.batch, a.heads, stream);       \
+    else if (a.head_dim == 80) st = fmha_launch<TT, 80, 1>(maps, p, a.batch, a.heads, stream);             \
+    else if (a.head_dim == 64) st = fmha_launch<TT, 64, 1>(maps, p, a.batch, a.heads, stream);             \
+  } else {                                                                                                 \
+    if (a.head_dim == 64) st = fmha_launch<TT, 64, 0>(maps, p, a.batch, a.heads, stream);                  \
+    else if (a.head_dim == 80) st = fmha_launch<TT, 80, 0>(maps, p, a.batch, a.heads, stream);             \
+    else if (a.head_dim == 128) st = fmha_launch<TT, 128, 0>(maps, p, a.batch, a.heads, stream);           \
+  }
+  if (a.dtype == DT_BF16) { ULLAVA_FMHA(__nv_bfloat16) }
+  else { ULLAVA_FMHA(__half) }
+#undef ULLAVA_FMHA
+  if (st == ERR_UNSUPPORTED) set_last_error("fmha: head_dim %d / rel-pos combination not compiled", a.head_dim);
+  if (st == OK) ctx->launches++;
+  return st;
+}
+
+}  // namespace ullava

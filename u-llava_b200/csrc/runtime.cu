@@ -68,6 +68,34 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t 
   return OK;
 }
 
+int encode_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                   uint32_t box0, uint32_t box1, int swizzle_bytes) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return ERR_CUDA;
+  }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstride[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t box[4] = {box0, box1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4d) failed (%d): base=%p dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%ux%u sw=%d",
+                   static_cast<int>(r), base, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)dims[2], (unsigned long long)dims[3], (unsigned long long)strides_bytes[0],
+                   (unsigned long long)strides_bytes[1], (unsigned long long)strides_bytes[2], box0, box1, swizzle_bytes);
+    return ERR_CUDA;
+  }
+  return OK;
+}
+
 ProfScope::ProfScope(Context* c, cudaStream_t s, int cls, double flops, double bytes)
     : ctx(c), stream(s), idx(-1), launches0(c ? c->launches : 0) {
   if (!c || !c->prof_on) return;

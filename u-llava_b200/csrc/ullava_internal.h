@@ -19,6 +19,7 @@ struct ullava_ctx {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int64_t launches = 0;
+  int attn_impl = 0;  // 0 = tcgen05/TMEM flash attention where compiled (hd 64/80/128), 1 = force the mma.sync kernels
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
   bool prof_on = false;
   std::vector<ullava_prof_rec> prof;
@@ -66,6 +67,11 @@ int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* 
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
                          float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev = nullptr,
                          int max_ctx = 0);
+
+// fmha_sm100.cu -- tcgen05/TMEM flash attention (hd 64 / 80 / 128); rel_h == nullptr: no rel-pos bias
+bool fmha_supported(const AttnArgs& a, bool relpos, int S);
+int fmha_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel_w, int S, const int32_t* o_row_map,
+             cudaStream_t stream);
 
 // elementwise.cu
 int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld_qkv, void* kc, void* vc, int64_t cache_bs, int64_t cache_hs,

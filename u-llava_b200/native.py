@@ -94,6 +94,8 @@ _SIGNATURES = {
     "ullava_layernorm": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _i32, _i32, _vp]),
     "ullava_rmsnorm": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _f32, _i32, _vp]),
     "ullava_attention": (_i32, [_vp, C.POINTER(AttnArgs), _vp]),
+    "ullava_attention_relpos": (_i32, [_vp, C.POINTER(AttnArgs), _vp, _vp, _i32, _vp, _vp]),
+    "ullava_set_attention_impl": (_i32, [_vp, _i32]),
     "ullava_attention_decode": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32,
                                        _f32, _i32, _vp]),
     "ullava_rope_kvcache": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
@@ -289,6 +291,31 @@ class Context:
         a.scale = float(scale if scale is not None else D ** -0.5)
         a.dtype = dtype_code(q.dtype)
         self._chk(self.lib.ullava_attention(self.handle, C.byref(a), _stream()))
+        return out
+
+    def set_attention_impl(self, impl: int):
+        """0 = tcgen05/TMEM flash attention (default), 1 = warp-level mma.sync kernels (A/B measurements)."""
+        self._chk(self.lib.ullava_set_attention_impl(self.handle, int(impl)))
+
+    def attention_relpos(self, q, k, v, rel_h, rel_w, grid_side, scale=None, out=None, o_row_map=None):
+        """SAM ViT attention with decomposed rel-pos bias.  q,k,v: [B, S*S, H, D] views; rel_h/rel_w: [2S-1, D]."""
+        B, Sq, H, D = q.shape
+        if out is None:
+            out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
+        a = AttnArgs()
+        for name, t in (("q", q), ("k", k), ("v", v), ("o", out)):
+            assert t.stride(3) == 1
+            setattr(a, name, t.data_ptr())
+            setattr(a, name + "_bs", t.stride(0))
+            setattr(a, name + "_rs", t.stride(1))
+            setattr(a, name + "_hs", t.stride(2))
+        a.batch, a.heads, a.seq_q, a.seq_k, a.head_dim = B, H, Sq, k.shape[1], D
+        a.causal, a.q_pos0 = 0, 0
+        a.scale = float(scale if scale is not None else D ** -0.5)
+        a.dtype = dtype_code(q.dtype)
+        assert rel_h.is_contiguous() and rel_w.is_contiguous()
+        self._chk(self.lib.ullava_attention_relpos(self.handle, C.byref(a), rel_h.data_ptr(), rel_w.data_ptr(),
+                                                   int(grid_side), _ptr(o_row_map), _stream()))
         return out
 
     def attention_decode(self, q, k_cache, v_cache, ctx_len, scale=None, out=None):
