@@ -150,8 +150,9 @@ ULLAVA_API int ullava_attention_relpos(ullava_ctx* ctx, const ullava_attn_args* 
                                        int32_t grid_side, const int32_t* o_row_map, void* stream);
 
 /* Kernel selection for ullava_attention / ullava_attention_relpos and the model-level entry points:
- * 0 (default) = tcgen05/TMEM flash attention for head_dim 64 / 80 / 128, 1 = warp-level mma.sync kernels only
- * (kept for A/B measurements; both are sm_100a code, neither is a fallback to another device or library). */
+ * 0 (default) = per shape (tcgen05/TMEM flash attention for head_dim 64 / 80 / 128 with >= 32 rows and keys and for
+ * the 64 x 64 rel-pos grid; warp-level mma.sync kernels otherwise), 1 = warp-level kernels only, 2 = tcgen05/TMEM
+ * wherever it is compiled.  1 and 2 exist for A/B measurements and tests; all of it is sm_100a code. */
 ULLAVA_API int ullava_set_attention_impl(ullava_ctx* ctx, int32_t impl);
 
 /* Single-query (decode) attention against a KV cache [batch, heads, max_seq, head_dim]:

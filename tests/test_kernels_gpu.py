@@ -243,7 +243,11 @@ def test_flash_attention_warp_level_kernel(legacy_attention, dtype, B, H, Sq, Sk
 def test_flash_attention_tcgen05_tiles(ctx, dtype, B, H, Sq, Sk, D, causal, pos0):
     qkv = _rand((B, max(Sq, Sk), 3, H, D), dtype, seed=42)
     q, k, v = qkv[:, :Sq, 0], qkv[:, :Sk, 1], qkv[:, :Sk, 2]
-    out = ctx.attention(q, k, v, causal=causal, q_pos0=pos0)
+    ctx.set_attention_impl(2)
+    try:
+        out = ctx.attention(q, k, v, causal=causal, q_pos0=pos0)
+    finally:
+        ctx.set_attention_impl(0)
     _check(out, _attn_ref(q, k, v, causal, pos0, D ** -0.5), dtype, f"tcgen05 attention {B,H,Sq,Sk,D,causal}")
 
 
@@ -274,7 +278,7 @@ def _relpos_ref(q, k, v, rel_h, rel_w, S, scale):
     return (torch.softmax(attn, -1) @ vf).permute(0, 2, 1, 3)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("B,H,S,D", [(3, 2, 14, 80), (1, 2, 64, 80), (2, 2, 9, 64), (50, 16, 14, 80)])
 def test_attention_relpos(ctx, dtype, impl, B, H, S, D):

@@ -290,7 +290,7 @@ int attention_run(Context* ctx, const AttnArgs& a, cudaStream_t stream) {
   if (a.batch == 0 || a.seq_q == 0) return OK;
   // large tiles go to the tcgen05/TMEM kernel; tiny problems (a handful of query rows or keys, e.g. the SAM mask
   // decoder's 7 prompt tokens) would leave a 128 x 128 tile almost empty and stay on the warp-level kernel
-  if (ctx->attn_impl == 0 && fmha_supported(a, false, 0) && a.seq_q >= 32 && a.seq_k >= 32)
+  if (ctx->attn_impl != 1 && fmha_supported(a, false, 0) && (ctx->attn_impl == 2 || (a.seq_q >= 32 && a.seq_k >= 32)))
     return fmha_run(ctx, a, nullptr, nullptr, 0, nullptr, stream);
   FlashParams p;
   p.q = a.q; p.q_bs = a.q_bs; p.q_rs = a.q_rs; p.q_hs = a.q_hs;
@@ -576,7 +576,10 @@ int attention_relpos_run(Context* ctx, const AttnArgs& a, const void* rel_h, con
   const int64_t strides[] = {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs};
   for (int64_t st : strides) ULLAVA_REQUIRE(st % 8 == 0, "attention_relpos: strides must be multiples of 8 elements");
   if (a.batch == 0) return OK;
-  if (ctx->attn_impl == 0 && fmha_supported(a, true, S)) return fmha_run(ctx, a, rel_h, rel_w, S, o_row_map, stream);
+  // auto: the 64 x 64 global grid goes to the tcgen05/TMEM kernel; 14 x 14 windows (two key tiles per CTA, prologue
+  // dominated) are still faster on the warp-level kernel
+  if (ctx->attn_impl != 1 && fmha_supported(a, true, S) && (ctx->attn_impl == 2 || S == 64))
+    return fmha_run(ctx, a, rel_h, rel_w, S, o_row_map, stream);
   FlashParams p;
   p.q = a.q; p.q_bs = a.q_bs; p.q_rs = a.q_rs; p.q_hs = a.q_hs;
   p.k = a.k; p.k_bs = a.k_bs; p.k_rs = a.k_rs; p.k_hs = a.k_hs;

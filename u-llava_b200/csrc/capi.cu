@@ -40,7 +40,7 @@ int ullava_attention_relpos(ullava_ctx* ctx, const ullava_attn_args* args, const
 
 int ullava_set_attention_impl(ullava_ctx* ctx, int32_t impl) {
   CTX_CHECK("ullava_set_attention_impl");
-  if (impl != 0 && impl != 1) { set_last_error("ullava_set_attention_impl: impl must be 0 or 1"); return ERR_BAD_ARG; }
+  if (impl < 0 || impl > 2) { set_last_error("ullava_set_attention_impl: impl must be 0, 1 or 2"); return ERR_BAD_ARG; }
   ctx->attn_impl = impl;
   return OK;
 }

@@ -60,7 +60,7 @@ struct FmhaCfg {
   static constexpr int TAIL_BYTES = 128 * TAIL * 2;
   static constexpr int TILE = NS * SLAB + TAIL_BYTES;     // one Q / K / V tile
   static constexpr int STAGES = HD == 64 ? 4 : 3;
-  static constexpr int BAR_BYTES = (1 + 3 * STAGES + 2 + 2 + 1 + 1) * 8 + 16;
+  static constexpr int BAR_BYTES = (1 + 3 * STAGES + 2 + 2 + 1 + 1 + 1) * 8 + 16;
   static_assert(TAIL == 0 || TAIL == 16, "head_dim must be 64, 80 or 128");
   static constexpr int smem_bytes(int table_floats) {
     return 1024 + TILE * (1 + 2 * STAGES) + table_floats * 4 + BAR_BYTES;
@@ -104,6 +104,59 @@ __device__ __forceinline__ void fmha_issue_pv(uint32_t o_tmem, uint32_t p_tmem, 
   }
 }
 
+// ---- packed fp32 x2 arithmetic (sm_100: one issue slot for two lanes of work) -----------------------------------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// Lazy rescale of O (TMEM) and the running row sum when the row maximum of tile j (`mx`, log2 units) exceeds the
+// maximum in use by more than the threshold.  Warp-uniform control flow around the TMEM accesses.
+template <int HD>
+__device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, float& l_run, uint32_t o_taddr,
+                                             uint64_t* pv_done) {
+  bool grow;
+  float alpha = 1.f;
+  if (j == 0) {
+    m_used = (mx == -INFINITY) ? 0.f : mx;
+    grow = false;
+  } else {
+    grow = mx > m_used + FM_RESCALE_THRESHOLD;
+    if (grow) {
+      alpha = ex2_approx(m_used - mx);
+      m_used = mx;
+      l_run *= alpha;
+    }
+  }
+  if (__any_sync(0xffffffffu, grow)) {
+    mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);  // O holds tiles 0..j-1
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x16(o_taddr + c * 16, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+      tmem_st_32x16(o_taddr + c * 16, r);
+    }
+  }
+}
+
 // RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
 template <typename T, int HD, int RP>
 __global__ void __launch_bounds__(FM_THREADS, 1)
@@ -127,7 +180,8 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   uint64_t* p_full = s_full + 2;
   uint64_t* pv_done = p_full + 2;
   uint64_t* pro_done = pv_done + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pro_done + 1);
+  uint64_t* o_final = pro_done + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,6 +212,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     }
     mbar_init(pv_done, 1);
     mbar_init(pro_done, 128);
+    mbar_init(o_final, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_ptr, FM_TMEM_COLS);
@@ -244,6 +299,9 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         umma_commit<1>(&kv_empty[st]);
         umma_commit<1>(pv_done);
       }
+      // the epilogue needs its own single-phase barrier: after the last tile a softmax thread can be up to TWO
+      // completions behind pv_done (no s_full wait bounds it any more), which a parity wait cannot disambiguate
+      umma_commit<1>(o_final);
     }
   } else {
     // ===================== softmax / correction / epilogue: one thread per query row =====================
@@ -296,112 +354,175 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       const uint32_t ts = tmem_base + lane_off + FM_COL_S + buf * FM_BN;
       const int key0 = j * FM_BN;
       const bool need_mask = (key0 + FM_BN > p.seq_k) || (p.causal && (key0 + FM_BN - 1 > p.q_pos0 + m0));
-      const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
-      float ah0 = 0.f, ah1 = 0.f;
-      if constexpr (RP == 2) {
-        ah0 = Ah[2 * j];
-        ah1 = Ah[2 * j + 1];
-      }
-      int kh0 = 0, kw0 = 0;
-      if constexpr (RP == 1) {
-        kh0 = key0 / S;
-        kw0 = key0 - kh0 * S;
-      }
       mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) + kRP) & 1u);
       tc_fence_after();
 
-      // score of column `col` of this tile in log2 units
-#define FMHA_SCORE(raw, c, i, kh, kw)                                                              \
-      ((RP == 0) ? (raw) * sl2                                                                      \
-       : (RP == 2) ? fmaf((raw), sl2, aw[(RP == 2) ? (((c) & 1) * 32 + (i)) : 0]) + (((c) >> 1) ? ah1 : ah0) \
-                   : fmaf((raw), sl2, Ah[min((kh), S - 1)] + Aw[(kw)]))
-
-      // ---- pass 1: row maximum ----
-      float mx = -INFINITY;
-      {
-        int kh = kh0, kw = kw0;
-#pragma unroll(kChunkUnroll)
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(ts + c * 32, r);
-          tmem_ld_wait();
+      if (RP == 0 && !need_mask) {
+        // ---- fast path, no bias: the 128 raw scores stay in registers between the two passes ----
+        uint32_t r[128];
+        tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_32x32(ts + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+        tmem_ld_32x32(ts + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+        tmem_ld_wait();
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
-            if (need_mask && (key0 + c * 32 + i >= key_lim)) x = -INFINITY;
-            mx = fmaxf(mx, x);
-            if constexpr (RP == 1) {
-              if (++kw == S) { kw = 0; ++kh; }
+        for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            mxa[e] = fmaxf(mxa[e], fmaxf(__uint_as_float(r[i + 2 * e]), __uint_as_float(r[i + 2 * e + 1])));
+        }
+        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;  // scale > 0
+        fmha_rescale<HD>(j, mx, m_used, l_run, o_taddr, pv_done);
+        const uint64_t sl2v = pk2(sl2, sl2), nm = pk2(-m_used, -m_used);
+        uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x = ffma2(pk2(__uint_as_float(r[c * 32 + i]), __uint_as_float(r[c * 32 + i + 1])), sl2v, nm);
+            float x0, x1;
+            upk2(x, x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
+            pk[i >> 1] = pack2<T>(p0, p1);
+          }
+          tmem_st_32x16(ts + c * 16, pk);
+        }
+        float s0, s1, s2, s3;
+        upk2(sum[0], s0, s1);
+        upk2(sum[1], s2, s3);
+        l_run += (s0 + s1) + (s2 + s3);
+      } else if (RP == 2 && !need_mask) {
+        // ---- fast path, 64 x 64 grid: this tile is grid rows 2j and 2j+1; A_w (registers) is the same for both ----
+        const float ah0 = Ah[2 * j], ah1 = Ah[2 * j + 1];
+        const uint64_t sl2v = pk2(sl2, sl2);
+        float mxh[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t r[32];
+            tmem_ld_32x32(ts + hh * 64 + c2 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int kw = (RP == 2) ? c2 * 32 + i : 0;
+              const uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v, pk2(aw[kw], aw[kw + (RP == 2)]));
+              float x0, x1;
+              upk2(x, x0, x1);
+              mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(x0, x1));
             }
           }
+          mxh[hh] = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
         }
-      }
-      // ---- lazy rescale of O and the row sum ----
-      bool grow;
-      float alpha = 1.f;
-      if (j == 0) {
-        m_used = (mx == -INFINITY) ? 0.f : mx;
-        grow = false;
-      } else {
-        grow = mx > m_used + FM_RESCALE_THRESHOLD;
-        if (grow) {
-          alpha = ex2_approx(m_used - mx);
-          m_used = mx;
-          l_run *= alpha;
-        }
-      }
-      if (__any_sync(0xffffffffu, grow)) {
-        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);  // O holds tiles 0..j-1
-        tc_fence_after();
+        const float mx = fmaxf(mxh[0] + ah0, mxh[1] + ah1);
+        fmha_rescale<HD>(j, mx, m_used, l_run, o_taddr, pv_done);
+        uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < HD / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld_32x16(o_taddr + c * 16, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x16(o_taddr + c * 16, r);
-        }
-      }
-      // ---- pass 2: P = 2^(x - m), row sum, P -> TMEM (packed 16-bit, over the S columns already consumed) ----
-      {
-        int kh = kh0, kw = kw0;
-        float sum = 0.f;
-#pragma unroll(kChunkUnroll)
         for (int c = 0; c < 4; ++c) {
+          const float off = ((c >> 1) ? ah1 : ah0) - m_used;
+          const uint64_t offv = pk2(off, off);
           uint32_t r[32];
           tmem_ld_32x32(ts + c * 32, r);
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float x0 = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
-            if (need_mask && (key0 + c * 32 + i >= key_lim)) x0 = -INFINITY;
-            if constexpr (RP == 1) {
-              if (++kw == S) { kw = 0; ++kh; }
-            }
-            float x1 = FMHA_SCORE(__uint_as_float(r[i + 1]), c, i + 1, kh, kw);
-            if (need_mask && (key0 + c * 32 + i + 1 >= key_lim)) x1 = -INFINITY;
-            if constexpr (RP == 1) {
-              if (++kw == S) { kw = 0; ++kh; }
-            }
-            const float p0 = ex2_approx(x0 - m_used);
-            const float p1 = ex2_approx(x1 - m_used);
-            sum += p0 + p1;
+            const int kw = (RP == 2) ? (c & 1) * 32 + i : 0;
+            uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v, pk2(aw[kw], aw[kw + (RP == 2)]));
+            x = fadd2(x, offv);
+            float x0, x1;
+            upk2(x, x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
             pk[i >> 1] = pack2<T>(p0, p1);
           }
           tmem_st_32x16(ts + c * 16, pk);
         }
-        l_run += sum;
-      }
+        float s0, s1, s2, s3;
+        upk2(sum[0], s0, s1);
+        upk2(sum[1], s2, s3);
+        l_run += (s0 + s1) + (s2 + s3);
+      } else {
+        // ---- generic path: boundary tiles (key / causal mask) and rel-pos bias on an arbitrary grid ----
+        const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
+        float ah0 = 0.f, ah1 = 0.f;
+        if constexpr (RP == 2) {
+          ah0 = Ah[2 * j];
+          ah1 = Ah[2 * j + 1];
+        }
+        int kh0 = 0, kw0 = 0;
+        if constexpr (RP == 1) {
+          kh0 = key0 / S;
+          kw0 = key0 - kh0 * S;
+        }
+        // score of column `col` of this tile in log2 units
+#define FMHA_SCORE(raw, c, i, kh, kw)                                                              \
+        ((RP == 0) ? (raw) * sl2                                                                      \
+         : (RP == 2) ? fmaf((raw), sl2, aw[(RP == 2) ? (((c) & 1) * 32 + (i)) : 0]) + (((c) >> 1) ? ah1 : ah0) \
+                     : fmaf((raw), sl2, Ah[min((kh), S - 1)] + Aw[(kw)]))
+        float mx = -INFINITY;
+        {
+          int kh = kh0, kw = kw0;
+#pragma unroll(kChunkUnroll)
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(ts + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float x = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
+              if (key0 + c * 32 + i >= key_lim) x = -INFINITY;
+              mx = fmaxf(mx, x);
+              if constexpr (RP == 1) {
+                if (++kw == S) { kw = 0; ++kh; }
+              }
+            }
+          }
+        }
+        fmha_rescale<HD>(j, mx, m_used, l_run, o_taddr, pv_done);
+        {
+          int kh = kh0, kw = kw0;
+          float sum = 0.f;
+#pragma unroll(kChunkUnroll)
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(ts + c * 32, r);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float x0 = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
+              if (key0 + c * 32 + i >= key_lim) x0 = -INFINITY;
+              if constexpr (RP == 1) {
+                if (++kw == S) { kw = 0; ++kh; }
+              }
+              float x1 = FMHA_SCORE(__uint_as_float(r[i + 1]), c, i + 1, kh, kw);
+              if (key0 + c * 32 + i + 1 >= key_lim) x1 = -INFINITY;
+              if constexpr (RP == 1) {
+                if (++kw == S) { kw = 0; ++kh; }
+              }
+              const float p0 = ex2_approx(x0 - m_used);
+              const float p1 = ex2_approx(x1 - m_used);
+              sum += p0 + p1;
+              pk[i >> 1] = pack2<T>(p0, p1);
+            }
+            tmem_st_32x16(ts + c * 16, pk);
+          }
+          l_run += sum;
+        }
 #undef FMHA_SCORE
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
     }
 
     // ---- epilogue: O / l -> global ----
-    mbar_wait(pv_done, static_cast<uint32_t>(n_tiles - 1) & 1u);
+    mbar_wait(o_final, 0);
     tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
     T* orow = nullptr;

@@ -19,7 +19,7 @@ struct ullava_ctx {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int64_t launches = 0;
-  int attn_impl = 0;  // 0 = tcgen05/TMEM flash attention where compiled (hd 64/80/128), 1 = force the mma.sync kernels
+  int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
   bool prof_on = false;
   std::vector<ullava_prof_rec> prof;

@@ -294,7 +294,7 @@ class Context:
         return out
 
     def set_attention_impl(self, impl: int):
-        """0 = tcgen05/TMEM flash attention (default), 1 = warp-level mma.sync kernels (A/B measurements)."""
+        """0 = per shape (default), 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled."""
         self._chk(self.lib.ullava_set_attention_impl(self.handle, int(impl)))
 
     def attention_relpos(self, q, k, v, rel_h, rel_w, grid_side, scale=None, out=None, o_row_map=None):
