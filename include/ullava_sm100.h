@@ -109,6 +109,13 @@ typedef struct ullava_gemm_args {
 } ullava_gemm_args;
 ULLAVA_API int ullava_gemm(ullava_ctx* ctx, const ullava_gemm_args* args, void* stream);
 
+/* Products with M <= 32 (the decode step's nn.Linear calls) run a weight-streaming kernel that prefetches B (the
+ * weight matrix) before it synchronises with the preceding kernel of the stream (programmatic dependent launch).
+ * B must therefore not be produced by the immediately preceding kernel when that kernel is one of this library's
+ * norm / decode-attention / weight-streaming kernels -- true for every nn.Linear weight.  ullava_set_pdl(ctx, 0)
+ * turns the early launch off (plain stream order). */
+ULLAVA_API int ullava_set_pdl(ullava_ctx* ctx, int32_t enabled);
+
 /* ---- normalisation ---------------------------------------------------------------------
  * LayerNorm over the last dim (fp32 statistics): CLIP pre_layrnorm / layer_norm1/2
  * (hf:models/clip/modeling_clip.py:354-385,677), SAM TwoWayTransformer norms

@@ -109,6 +109,56 @@ def test_gemm_small_m_swap_ab(ctx, dtype, M, N, K):
     _check(out2, ref, dtype, f"no-swap gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("pdl", [True, False])
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (3, 300, 200), (17, 1000, 72), (32, 128, 64), (1, 128, 8192),
+                                   (9, 22016, 4096), (32, 32011, 512)])
+def test_gemm_stream_k_partition(ctx, pdl, M, N, K):
+    """Weight-streaming kernel: ragged N / K, a single unit, one tile cut across many CTAs (K = 8192, N = 128),
+    many tiles per CTA; repeated launches prove that the tile counters return to zero."""
+    dtype = torch.bfloat16
+    a = _rand((M, K), dtype, seed=21)
+    w = _rand((N, K), dtype, K ** -0.5, seed=22)
+    b = _rand((N,), dtype, seed=23)
+    ref = torch.relu(a.float() @ w.float().t() + b.float())
+    ctx.set_pdl(pdl)
+    try:
+        for it in range(3):
+            out = ctx.gemm(a, w, bias=b, epilogue=EPI_RELU)
+            _check(out, ref, dtype, f"stream gemm {M}x{N}x{K} launch {it}")
+    finally:
+        ctx.set_pdl(True)
+
+
+def test_gemm_stream_after_norm_chain(ctx):
+    """The decode chain rmsnorm -> GEMM -> GEMM(silu*mul) -> GEMM(+residual in place) back to back: with programmatic
+    dependent launch each GEMM prefetches weights under its predecessor and must still see its finished output."""
+    dtype = torch.bfloat16
+    B, H, F = 32, 1024, 2048
+    x = _rand((B, H), dtype, seed=24)
+    g = (_rand((H,), dtype, seed=25).float() * 0.1 + 1).to(dtype)
+    w1 = _rand((H, H), dtype, H ** -0.5, seed=26)
+    wg = _rand((F, H), dtype, H ** -0.5, seed=27)
+    wu = _rand((F, H), dtype, H ** -0.5, seed=28)
+    wgu = torch.stack([wg.view(F // 16, 16, H), wu.view(F // 16, 16, H)], dim=1).reshape(2 * F, H).contiguous()
+    wd = _rand((H, F), dtype, F ** -0.5, seed=29)
+    outs = []
+    for _ in range(4):
+        hid = x.clone()
+        xn = ctx.rmsnorm(hid, g, 1e-6)
+        h1 = ctx.gemm(xn, w1)
+        act = ctx.gemm(h1, wgu, epilogue=EPI_SILU_MUL)
+        ctx.gemm(act, wd, residual=hid, out=hid)
+        outs.append(hid)
+    xf = x.float()
+    xn_ref = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * g.float()).to(dtype).float()
+    h1_ref = (xn_ref @ w1.float().t()).to(dtype).float()
+    act_ref = (torch.nn.functional.silu(h1_ref @ wg.float().t()) * (h1_ref @ wu.float().t())).to(dtype).float()
+    ref = act_ref @ wd.float().t() + xf
+    for o in outs:
+        _check(o, ref, dtype, "norm->gemm chain", extra_abs=2e-2)
+        assert torch.equal(o, outs[0])
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("M", [4, 70])
 def test_gemm_lm_head_fp32_out(ctx, dtype, M):

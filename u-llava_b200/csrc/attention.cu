@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ kc, const T* __restrict__ vc,
                    int64_t cache_bs, int64_t cache_hs, T* __restrict__ o, int64_t o_bs, int ctx_len,
                    float scale_log2, const int32_t* __restrict__ ctx_dev) {
+  pdl_launch_dependents();  // the o-projection GEMM may start prefetching its weights under this kernel
   if (ctx_dev) ctx_len = *ctx_dev + 1;  // CUDA-graph decode: keys 0..pos are attended, pos read from device memory
   extern __shared__ float dec_smem[];   // [ctx_len] scores, then [groups][HD] partial outputs
   __shared__ float red[DEC_THREADS / 32];

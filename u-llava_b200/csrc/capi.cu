@@ -45,6 +45,12 @@ int ullava_set_attention_impl(ullava_ctx* ctx, int32_t impl) {
   return OK;
 }
 
+int ullava_set_pdl(ullava_ctx* ctx, int32_t enabled) {
+  CTX_CHECK("ullava_set_pdl");
+  ctx->pdl = enabled ? 1 : 0;
+  return OK;
+}
+
 int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q_bs, const void* k_cache, const void* v_cache,
                             int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
                             int32_t head_dim, int32_t ctx_len, float scale, int32_t dtype, void* stream) {

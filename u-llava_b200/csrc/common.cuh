@@ -187,6 +187,13 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// launch_dependents: the next kernel of the stream, IF it was launched with the programmatic-serialization attribute,
+// may start as soon as every CTA of this grid has executed this (or exited).  Only gemm_stream_kernel is launched that
+// way; everything it does before its own griddepcontrol.wait is independent of this grid (weight prefetch).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cluster ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -382,5 +389,27 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], c
                    uint32_t box0, uint32_t box1, int swizzle_bytes);
 
 int device_sm_count();
+
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the
+// stream is still running, once every CTA of the predecessor has executed griddepcontrol.launch_dependents (or
+// exited).  The kernel MUST execute griddepcontrol.wait before it touches global memory that the predecessor (or
+// anything before it) writes or reads-then-expects-unchanged.  With `pdl == false` this is a plain launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace ullava

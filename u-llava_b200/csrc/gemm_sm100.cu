@@ -520,6 +520,10 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
   p.ldr = a.ldr;
   CUtensorMap ta, tb;
 
+  if (swap && a.force_splits > 0) {
+    set_last_error("gemm: force_splits does not apply to the weight-streaming (M <= 32) path");
+    return ERR_BAD_ARG;
+  }
   if (!swap) {
     const int bn = a.force_bn ? a.force_bn : pick_bn_large(a.N);
     p.M = a.M; p.N = a.N; p.K = a.K;
@@ -535,12 +539,12 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
     st = encode_tmap_2d(&tb, a.B, 2, a.K, a.N, a.ldb * 2, BK, bn, true);
     if (st) return st;
     if (splits > 1) {
-      const size_t need = static_cast<size_t>(splits) * a.M * a.N * sizeof(float);
+      const size_t need = kStreamCounterBytes + static_cast<size_t>(splits) * a.M * a.N * sizeof(float);
       if (need > ctx->workspace_bytes) {
         set_last_error("gemm: split-K workspace too small (%zu > %zu)", need, ctx->workspace_bytes);
         return ERR_WORKSPACE;
       }
-      p.D = ctx->workspace; p.ldd = a.N;
+      p.D = static_cast<uint8_t*>(ctx->workspace) + kStreamCounterBytes; p.ldd = a.N;
     } else {
       p.D = a.D; p.ldd = a.ldd;
     }
@@ -553,12 +557,12 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
       dim3 g((a.M + 31) / 32, (a.N + 31) / 32);
       if (a.dtype == DT_BF16)
         splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(
-            reinterpret_cast<const float*>(ctx->workspace), splits, a.M, a.N, a.N, a.D, a.ldd,
+            reinterpret_cast<const float*>(p.D), splits, a.M, a.N, a.N, a.D, a.ldd,
             reinterpret_cast<const __nv_bfloat16*>(a.bias), reinterpret_cast<const __nv_bfloat16*>(a.residual), a.ldr,
             a.epilogue, a.out_f32, 0);
       else
         splitk_reduce_kernel<__half><<<g, 256, 0, stream>>>(
-            reinterpret_cast<const float*>(ctx->workspace), splits, a.M, a.N, a.N, a.D, a.ldd,
+            reinterpret_cast<const float*>(p.D), splits, a.M, a.N, a.N, a.D, a.ldd,
             reinterpret_cast<const __half*>(a.bias), reinterpret_cast<const __half*>(a.residual), a.ldr, a.epilogue,
             a.out_f32, 0);
       ctx->launches += 2;
@@ -568,59 +572,8 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
     return OK;
   }
 
-  // ---- swap-AB path: kernel computes P[N_out][Bpad] = W[N_out,K] * X[Bpad,K]^T ----
-  const int bn = a.M <= 16 ? 16 : 32;
-  p.M = a.N;   // weight rows
-  p.N = bn;    // padded batch (TMA zero-fills rows >= a.M of X)
-  p.K = a.K;
-  p.num_m = (a.N + BM - 1) / BM;
-  p.num_n = 1;
-  int splits;
-  if (a.force_splits > 0) {
-    splits = a.force_splits;
-  } else {
-    const int target = 2 * sms;
-    splits = (target + p.num_m - 1) / p.num_m;
-    const int max_splits = kb_total / 4 > 0 ? kb_total / 4 : 1;  // keep >= 4 k-blocks per CTA
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-  }
-  if (splits > kb_total) splits = kb_total;
-  p.kb_per_split = (kb_total + splits - 1) / splits;
-  splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  // force the workspace path even with one split: the reduce kernel performs the transpose + epilogue
-  p.splits = splits;
-  const size_t need = static_cast<size_t>(splits) * a.N * bn * sizeof(float);
-  if (need > ctx->workspace_bytes) {
-    set_last_error("gemm(swap): workspace too small (%zu > %zu)", need, ctx->workspace_bytes);
-    return ERR_WORKSPACE;
-  }
-  p.D = ctx->workspace;
-  p.ldd = bn;
-  p.bias = nullptr; p.residual = nullptr; p.epilogue = EPI_NONE; p.out_f32 = 1;
-  int st = encode_tmap_2d(&ta, a.B, 2, a.K, a.N, a.ldb * 2, BK, BM, true);
-  if (st) return st;
-  st = encode_tmap_2d(&tb, a.A, 2, a.K, a.M, a.lda * 2, BK, bn, true);
-  if (st) return st;
-  const int tiles = p.num_m * splits;
-  const int grid = tiles < sms ? tiles : sms;
-  // with splits == 1 the kernel takes its plain fp32 store path, which has the same [N_out][bn] layout
-  st = (a.dtype == DT_BF16) ? launch_bn<__nv_bfloat16>(bn, ta, tb, p, grid, stream)
-                            : launch_bn<__half>(bn, ta, tb, p, grid, stream);
-  if (st) return st;
-  dim3 g((a.N + 31) / 32, (bn + 31) / 32);
-  if (a.dtype == DT_BF16)
-    splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(
-        reinterpret_cast<const float*>(ctx->workspace), splits, a.N, bn, a.M, a.D, a.ldd,
-        reinterpret_cast<const __nv_bfloat16*>(a.bias), reinterpret_cast<const __nv_bfloat16*>(a.residual), a.ldr,
-        a.epilogue, a.out_f32, 1);
-  else
-    splitk_reduce_kernel<__half><<<g, 256, 0, stream>>>(
-        reinterpret_cast<const float*>(ctx->workspace), splits, a.N, bn, a.M, a.D, a.ldd,
-        reinterpret_cast<const __half*>(a.bias), reinterpret_cast<const __half*>(a.residual), a.ldr, a.epilogue,
-        a.out_f32, 1);
-  ctx->launches += 2;
-  return check_cuda(cudaGetLastError(), "splitk_reduce(swap) launch");
+  // ---- small-M (decode) products: dedicated weight-streaming kernel (gemm_stream_sm100.cu) ----
+  return gemm_stream_run(ctx, a, stream);
 }
 
 }  // namespace ullava

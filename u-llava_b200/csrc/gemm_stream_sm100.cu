@@ -1,0 +1,409 @@
+// Weight-streaming GEMM for the decode step (M <= 32 tokens):  D[M,N] = epi(X[M,K] * W[N,K]^T)
+//
+// Call sites (one token per sample, KV-cached decode): LLaMA q/k/v, o, gate/up, down projections and lm_head
+// (hf:models/llama/modeling_llama.py:171-291, models/ullava_core.py:325) as driven by generate()
+// (models/ullava.py:350-362).  2*M FLOP per 2-byte weight: HBM-bound, the job is to stream W exactly once at
+// full bandwidth.
+//
+// Design (B200, sm_100a):
+//   * swap-AB: the 128-row tcgen05 operand is a tile of W (K-major, TMA SWIZZLE_128B), the padded batch is the
+//     UMMA N (16 or 32; rows >= M of X are zero-filled by TMA), accumulators [128 weight rows x BN] in TMEM;
+//   * stream-K: the (weight tile, k-block) units are cut into gridDim.x equal contiguous ranges, one per SM, so
+//     every SM streams the same number of bytes whatever N and K are (no wave quantisation, no split-K heuristics);
+//   * a tile cut across CTAs is reduced IN the kernel: each contributor parks its fp32 partial in the L2-resident
+//     workspace and bumps the tile's counter; the last one to arrive adds the others' partials to its registers and
+//     runs the fused epilogue (bias / activation / SiLU*mul / residual, transposed store).  Nobody waits for anybody,
+//     and there is no second kernel;
+//   * programmatic dependent launch: weights do not depend on the previous kernel, so the producer warp fills the
+//     whole shared-memory ring with W tiles BEFORE griddepcontrol.wait and only then loads X; launched with the
+//     programmatic-serialization attribute this overlaps pipeline fill with the previous kernel's tail (the
+//     norm / rope / attention kernels of the decode step call griddepcontrol.launch_dependents at their start).
+//   * 5-deep TMA ring (80 KB of W in flight per SM, two CTAs of consecutive GEMMs can share an SM), warp-specialised like the large-M kernel: warp 0 producer,
+//     warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue; accumulator double buffered in TMEM.
+#include "common.cuh"
+#include "ullava_internal.h"
+
+namespace ullava {
+
+static constexpr int GS_BM = 128;     // weight rows per tile (UMMA M)
+static constexpr int GS_BK = 64;      // one SWIZZLE_128B row
+static constexpr int GS_STAGES = 8;     // 160 KB: one CTA per SM, 128 KB of W in flight
+static constexpr int GS_THREADS = 256;
+
+struct StreamParams {
+  void* D;
+  int64_t ldd;
+  const void* bias;
+  const void* residual;
+  int64_t ldr;
+  int M, N, K;        // M = valid batch rows (<= BN), N = weight rows
+  int epilogue, out_f32;
+  int num_t;          // weight tiles
+  int kb_total;       // k-blocks per tile
+  int units;          // num_t * kb_total (host guarantees units * gridDim.x < 2^31)
+  float* partials;    // [2 * gridDim.x][128][BN] fp32
+  int* counters;      // [num_t], zero between launches
+};
+
+__device__ __forceinline__ int gs_lo(int c, int U, int G) {
+  return static_cast<int>(static_cast<uint32_t>(c) * static_cast<uint32_t>(U) / static_cast<uint32_t>(G));
+}
+// CTA that owns unit u:  largest c with floor(c*U/G) <= u
+__device__ __forceinline__ int gs_owner(int u, int U, int G) {
+  return static_cast<int>((static_cast<uint32_t>(u + 1) * static_cast<uint32_t>(G) + static_cast<uint32_t>(U) - 1u) /
+                          static_cast<uint32_t>(U)) - 1;
+}
+
+template <int BN>
+struct StreamSmem {
+  static constexpr int kWBytes = GS_BM * GS_BK * 2;
+  static constexpr int kXBytes = BN * GS_BK * 2;
+  static constexpr int kStageBytes = kWBytes + kXBytes;
+  static constexpr int kBarOffset = GS_STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * GS_STAGES + 4) * 8 + 32 + 1024;
+};
+
+__device__ __forceinline__ float gs_act(float v, int epi) {
+  switch (epi) {
+    case EPI_RELU: return fmaxf(v, 0.f);
+    case EPI_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case EPI_QUICK_GELU: return __fdividef(v, 1.f + __expf(fminf(-1.702f * v, 80.f)));
+    default: return v;
+  }
+}
+
+// EK: 0 = bias / residual only, 1 = SiLU(gate) * up, 2 = bias + ReLU / GELU / quick-GELU + residual
+template <typename T, int BN, int EK>
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                   const StreamParams p) {
+  using S = StreamSmem<BN>;
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr uint32_t kIdesc = make_idesc_f16(T16<T>::kUmmaFormat, GS_BM, BN);
+
+  extern __shared__ uint8_t gs_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gs_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + GS_STAGES;
+  uint64_t* tmem_full = empty_bar + GS_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int U = p.units;
+  const int lo = gs_lo(blockIdx.x, U, G), hi = gs_lo(blockIdx.x + 1, U, G);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GS_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4 * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();  // the next kernel of the stream may start its own prologue / weight prefetch
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int pre_end = (hi - lo) < GS_STAGES ? hi : lo + GS_STAGES;
+      // ring fill with weights only: independent of whatever kernel precedes this one
+      for (int u = lo; u < pre_end; ++u) {
+        const int t = u / p.kb_total, kb = u - t * p.kb_total;
+        const int s = u - lo;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        tma_load_2d_hint(smem + s * S::kStageBytes, &tmW, &full_bar[s], kb * GS_BK, t * GS_BM, kEvictFirst);
+      }
+      pdl_wait();  // activations (and everything else) of the previous kernel are now visible
+      for (int u = lo; u < pre_end; ++u) {
+        const int t = u / p.kb_total, kb = u - t * p.kb_total;
+        const int s = u - lo;
+        tma_load_2d_hint(smem + s * S::kStageBytes + S::kWBytes, &tmX, &full_bar[s], kb * GS_BK, 0, kEvictLast);
+      }
+      stage = (pre_end - lo) % GS_STAGES;
+      phase = (pre_end - lo) == GS_STAGES ? 1u : 0u;
+      for (int u = pre_end; u < hi; ++u) {
+        const int t = u / p.kb_total, kb = u - t * p.kb_total;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sw = smem + stage * S::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        tma_load_2d_hint(sw, &tmW, &full_bar[stage], kb * GS_BK, t * GS_BM, kEvictFirst);
+        tma_load_2d_hint(sw + S::kWBytes, &tmX, &full_bar[stage], kb * GS_BK, 0, kEvictLast);
+        if (++stage == GS_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int u = lo;
+      while (u < hi) {
+        const int t = u / p.kb_total;
+        const int seg_end = min(hi, (t + 1) * p.kb_total);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int v = u; v < seg_end; ++v) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sw = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t a_desc = make_kmajor_sw128_desc(sw);
+          const uint64_t b_desc = make_kmajor_sw128_desc(sw + S::kWBytes);
+#pragma unroll
+          for (int k = 0; k < GS_BK / 16; ++k)
+            umma_f16<1>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (v > u || k > 0) ? 1u : 0u);
+          umma_commit<1>(&empty_bar[stage]);
+          if (++stage == GS_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit<1>(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        u = seg_end;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread = one weight row (output column), BN batch entries =====================
+    pdl_wait();  // no global write (output, partials, counters) before the previous kernel has fully finished
+    const int q = warp & 3;
+    const int etid = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* resid = reinterpret_cast<const T*>(p.residual);
+    int u = lo;
+    while (u < hi) {
+      const int t = u / p.kb_total;
+      const int t0 = t * p.kb_total;
+      const int seg_end = min(hi, t0 + p.kb_total);
+      const bool whole = (u == t0) && (seg_end == t0 + p.kb_total);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      float v[BN];
+      {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        if constexpr (BN == 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x16(taddr, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);  // accumulator is in registers: the MMA warp may reuse it
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+
+      bool do_epilogue = whole;
+      if (!whole) {
+        // park the partial, then find out whether this CTA is the last contributor of tile t
+        const int which = (lo >= t0) ? 0 : 1;  // 0: my range starts inside the tile, 1: it only ends there
+        float* mine = p.partials + (static_cast<size_t>(2 * blockIdx.x + which) * GS_BM + etid) * BN;
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        // release/acquire through the tile counter: the CTA barrier orders every thread's partial stores before
+        // thread 0's gpu-scope release, and the last arriver's acquire before every thread's loads (cumulativity)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int c_first = gs_owner(t0, U, G), c_last = gs_owner(t0 + p.kb_total - 1, U, G);
+        if (etid == 0) {
+          int old;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(p.counters + t) : "memory");
+          *last_flag = (old == c_last - c_first) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        do_epilogue = (*last_flag != 0);
+        if (do_epilogue) {
+          // sum ALL contributions (this CTA's own included) in CTA order, from memory: the result does not depend
+          // on which contributor happened to arrive last, so greedy decode stays bit-reproducible
+#pragma unroll
+          for (int i = 0; i < BN; ++i) v[i] = 0.f;
+          int c_lo = gs_lo(c_first, U, G);
+#pragma unroll 1
+          for (int c = c_first; c <= c_last; ++c) {
+            const int w = (c_lo >= t0) ? 0 : 1;
+            c_lo = gs_lo(c + 1, U, G);
+            const float* other = p.partials + (static_cast<size_t>(2 * c + w) * GS_BM + etid) * BN;
+            float4 f[BN / 4];
+#pragma unroll
+            for (int i = 0; i < BN / 4; ++i) f[i] = __ldcg(reinterpret_cast<const float4*>(other) + i);
+#pragma unroll
+            for (int i = 0; i < BN / 4; ++i) {
+              v[4 * i] += f[i].x; v[4 * i + 1] += f[i].y; v[4 * i + 2] += f[i].z; v[4 * i + 3] += f[i].w;
+            }
+          }
+          if (etid == 0) p.counters[t] = 0;  // ready for the next launch / graph replay
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // last_flag may be rewritten by the next segment
+      }
+
+      if (do_epilogue) {
+        // Compact, branch-free-per-element stores: this code runs once or twice per CTA, i.e. always from a cold
+        // instruction cache, so its size is what it costs.
+        const int n = t * GS_BM + etid;  // weight row = output column
+        const bool n_ok = n < p.N;
+        if (bias != nullptr && n_ok) {
+          const float bv = T16<T>::to_f(bias[n]);
+#pragma unroll
+          for (int i = 0; i < BN; ++i) v[i] += bv;
+        }
+        if constexpr (EK == 1) {
+          // SiLU(gate) * up.  W rows are packed in blocks of 32 = 16 gate rows + the 16 matching up rows: lanes 0-15
+          // hold gate, lanes 16-31 the partner up value; output column = block * 16 + lane
+          const int oc = ((t * GS_BM + q * 32) >> 1) + (lane & 15);
+          T* out = reinterpret_cast<T*>(p.D) + oc;
+          const bool st_ok = lane < 16 && n_ok;
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            const float up = __shfl_xor_sync(0xffffffffu, v[i], 16);
+            const float g = v[i];
+            const float o = __fdividef(g, 1.f + __expf(fminf(-g, 80.f))) * up;
+            if (st_ok && i < p.M) out[static_cast<int64_t>(i) * p.ldd] = T16<T>::from_f(o);
+          }
+        } else {
+          if constexpr (EK == 2) {
+#pragma unroll
+            for (int i = 0; i < BN; ++i) v[i] = gs_act(v[i], p.epilogue);
+          }
+          if (n_ok) {
+            // D may alias the residual (in-place x += f(x)): read every residual value before the first store so
+            // the loads are issued back to back instead of one full latency per row
+            if (resid != nullptr) {
+              float rr[BN];
+#pragma unroll
+              for (int i = 0; i < BN; ++i) rr[i] = i < p.M ? T16<T>::to_f(resid[static_cast<int64_t>(i) * p.ldr + n]) : 0.f;
+#pragma unroll
+              for (int i = 0; i < BN; ++i) v[i] += rr[i];
+            }
+            if (p.out_f32) {
+              float* out = reinterpret_cast<float*>(p.D) + n;
+#pragma unroll
+              for (int i = 0; i < BN; ++i)
+                if (i < p.M) out[static_cast<int64_t>(i) * p.ldd] = v[i];
+            } else {
+              T* out = reinterpret_cast<T*>(p.D) + n;
+#pragma unroll
+              for (int i = 0; i < BN; ++i)
+                if (i < p.M) out[static_cast<int64_t>(i) * p.ldd] = T16<T>::from_f(v[i]);
+            }
+          }
+        }
+      }
+      u = seg_end;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Host side
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T, int BN, int EK>
+static int stream_launch(const CUtensorMap& tw, const CUtensorMap& tx, const StreamParams& p, int grid, bool pdl,
+                         cudaStream_t stream) {
+  using S = StreamSmem<BN>;
+  auto kern = gemm_stream_kernel<T, BN, EK>;
+  static bool configured = false;
+  if (!configured) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  return check_cuda(launch_pdl(kern, dim3(grid), dim3(GS_THREADS), S::kTotal, stream, pdl, tw, tx, p),
+                    "gemm_stream_kernel launch");
+}
+
+template <typename T>
+static int stream_dispatch(int bn, int ek, const CUtensorMap& tw, const CUtensorMap& tx, const StreamParams& p, int grid,
+                           bool pdl, cudaStream_t stream) {
+  if (bn == 16) {
+    if (ek == 0) return stream_launch<T, 16, 0>(tw, tx, p, grid, pdl, stream);
+    if (ek == 1) return stream_launch<T, 16, 1>(tw, tx, p, grid, pdl, stream);
+    return stream_launch<T, 16, 2>(tw, tx, p, grid, pdl, stream);
+  }
+  if (ek == 0) return stream_launch<T, 32, 0>(tw, tx, p, grid, pdl, stream);
+  if (ek == 1) return stream_launch<T, 32, 1>(tw, tx, p, grid, pdl, stream);
+  return stream_launch<T, 32, 2>(tw, tx, p, grid, pdl, stream);
+}
+
+size_t gemm_stream_workspace_bytes(int sm_count) {
+  return kStreamCounterBytes + static_cast<size_t>(2) * sm_count * GS_BM * 32 * sizeof(float);
+}
+
+// a: the caller's GEMM (M <= 32 rows of X, N weight rows).  Uses ctx->workspace: [0, 64 KB) tile counters (kept at
+// zero between launches), then the partial tiles.
+int gemm_stream_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
+  const int bn = a.M <= 16 ? 16 : 32;
+  ULLAVA_REQUIRE(a.M <= 32, "gemm_stream: M = %d > 32", a.M);
+  if (a.epilogue == EPI_SILU_MUL) ULLAVA_REQUIRE((a.N % 32) == 0, "gemm_stream: SILU_MUL needs N %% 32 == 0");
+  StreamParams p{};
+  p.D = a.D; p.ldd = a.ldd; p.bias = a.bias; p.residual = a.residual; p.ldr = a.ldr;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.epilogue = a.epilogue; p.out_f32 = a.out_f32;
+  p.num_t = (a.N + GS_BM - 1) / GS_BM;
+  p.kb_total = (a.K + GS_BK - 1) / GS_BK;
+  const long long units = static_cast<long long>(p.num_t) * p.kb_total;
+  ULLAVA_REQUIRE(units * ctx->sm_count < (1ll << 31), "gemm_stream: %lld units exceed the 32-bit partition arithmetic", units);
+  p.units = static_cast<int>(units);
+  const int grid = p.units < ctx->sm_count ? p.units : ctx->sm_count;
+  const size_t need = kStreamCounterBytes + static_cast<size_t>(2) * grid * GS_BM * bn * sizeof(float);
+  if (need > ctx->workspace_bytes || static_cast<size_t>(p.num_t) * sizeof(int) > kStreamCounterBytes) {
+    set_last_error("gemm_stream: workspace too small (%zu > %zu) or too many tiles (%d)", need, ctx->workspace_bytes,
+                   p.num_t);
+    return ERR_WORKSPACE;
+  }
+  p.counters = reinterpret_cast<int*>(ctx->workspace);
+  p.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ctx->workspace) + kStreamCounterBytes);
+  CUtensorMap tw, tx;
+  int st = encode_tmap_2d(&tw, a.B, 2, a.K, a.N, a.ldb * 2, GS_BK, GS_BM, true);
+  if (st) return st;
+  st = encode_tmap_2d(&tx, a.A, 2, a.K, a.M, a.lda * 2, GS_BK, bn, true);
+  if (st) return st;
+  const bool pdl = ctx->pdl != 0;
+  const int ek = a.epilogue == EPI_SILU_MUL ? 1 : (a.epilogue == EPI_NONE ? 0 : 2);
+  st = a.dtype == DT_BF16 ? stream_dispatch<__nv_bfloat16>(bn, ek, tw, tx, p, grid, pdl, stream)
+                          : stream_dispatch<__half>(bn, ek, tw, tx, p, grid, pdl, stream);
+  if (st == OK) ctx->launches += 1;
+  return st;
+}
+
+}  // namespace ullava

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(512)
 norm_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ w, const T* __restrict__ b,
             T* __restrict__ y, int64_t ldy, int cols, float eps, int act, const int32_t* __restrict__ dst_rows) {
   __shared__ float red[32];
+  pdl_launch_dependents();  // a following weight-streaming GEMM may start prefetching its weights now
+  pdl_wait();               // launched with programmatic serialization: the producer of x must have finished
   const int row = blockIdx.x;
   const T* xr = x + static_cast<int64_t>(row) * ldx;
   // dst_rows (optional) scatters the output rows, e.g. SAM's window_partition fused into norm1
@@ -124,14 +126,15 @@ static int norm_launch(Context* ctx, const void* x, int64_t ldx, const void* w, 
   if (threads > 512) threads = 512;
   while (threads * kMaxVec < nvec) threads += 32;  // cannot trigger given the cols bound above
   if (dtype == DT_BF16) {
-    norm_kernel<__nv_bfloat16, kRms><<<rows, threads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w),
-        static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), ldy, cols, eps, act, dst_rows);
+    ULLAVA_CHECK_CUDA(launch_pdl(norm_kernel<__nv_bfloat16, kRms>, dim3(rows), dim3(threads), 0, stream, ctx->pdl != 0,
+                                 static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w),
+                                 static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(y), ldy, cols, eps,
+                                 act, dst_rows));
   } else if (dtype == DT_F16) {
-    norm_kernel<__half, kRms><<<rows, threads, 0, stream>>>(static_cast<const __half*>(x), ldx,
-                                                            static_cast<const __half*>(w),
-                                                            static_cast<const __half*>(b), static_cast<__half*>(y),
-                                                            ldy, cols, eps, act, dst_rows);
+    ULLAVA_CHECK_CUDA(launch_pdl(norm_kernel<__half, kRms>, dim3(rows), dim3(threads), 0, stream, ctx->pdl != 0,
+                                 static_cast<const __half*>(x), ldx, static_cast<const __half*>(w),
+                                 static_cast<const __half*>(b), static_cast<__half*>(y), ldy, cols, eps, act,
+                                 dst_rows));
   } else {
     set_last_error("norm: unsupported dtype %d", dtype);
     return ERR_UNSUPPORTED;

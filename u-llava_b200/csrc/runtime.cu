@@ -164,8 +164,14 @@ int ullava_set_workspace(ullava_ctx* ctx, void* ptr, size_t bytes) {
     set_last_error("ullava_set_workspace: pointer must be 256-byte aligned");
     return ERR_BAD_ARG;
   }
+  if (ptr != nullptr && bytes < kStreamCounterBytes) {
+    set_last_error("ullava_set_workspace: at least %zu bytes are needed", kStreamCounterBytes);
+    return ERR_BAD_ARG;
+  }
   ctx->workspace = ptr;
   ctx->workspace_bytes = bytes;
+  // tile-arrival counters of the weight-streaming GEMM live at the front and must start at zero
+  if (ptr != nullptr) ULLAVA_CHECK_CUDA(cudaMemset(ptr, 0, kStreamCounterBytes));
   return OK;
 }
 

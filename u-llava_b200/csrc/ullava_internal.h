@@ -19,6 +19,8 @@ struct ullava_ctx {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int64_t launches = 0;
+  int pdl = 1;        // decode GEMMs are launched with programmatic stream serialization (weight prefetch under the
+                      // previous kernel's tail); 0 = plain launches
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
   bool prof_on = false;
@@ -51,6 +53,13 @@ struct ProfScope {
 
 // gemm_sm100.cu
 int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream);
+
+// gemm_stream_sm100.cu -- M <= 32 weight-streaming GEMM (stream-K, in-kernel split reduction, PDL weight prefetch).
+// The first kStreamCounterBytes of the context workspace hold its per-tile arrival counters (zero between launches);
+// every other workspace user starts behind them.
+static constexpr size_t kStreamCounterBytes = 64 * 1024;
+int gemm_stream_run(Context* ctx, const GemmArgs& a, cudaStream_t stream);
+size_t gemm_stream_workspace_bytes(int sm_count);
 
 // norm.cu
 int layernorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,

@@ -96,6 +96,7 @@ _SIGNATURES = {
     "ullava_attention": (_i32, [_vp, C.POINTER(AttnArgs), _vp]),
     "ullava_attention_relpos": (_i32, [_vp, C.POINTER(AttnArgs), _vp, _vp, _i32, _vp, _vp]),
     "ullava_set_attention_impl": (_i32, [_vp, _i32]),
+    "ullava_set_pdl": (_i32, [_vp, _i32]),
     "ullava_attention_decode": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32,
                                        _f32, _i32, _vp]),
     "ullava_rope_kvcache": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
@@ -292,6 +293,10 @@ class Context:
         a.dtype = dtype_code(q.dtype)
         self._chk(self.lib.ullava_attention(self.handle, C.byref(a), _stream()))
         return out
+
+    def set_pdl(self, enabled: bool):
+        """Programmatic dependent launch for the decode (M <= 32) GEMMs: weight prefetch under the previous kernel."""
+        self._chk(self.lib.ullava_set_pdl(self.handle, int(bool(enabled))))
 
     def set_attention_impl(self, impl: int):
         """0 = per shape (default), 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled."""
