@@ -483,7 +483,7 @@ def run_b200(args):
                             "traffic": (traffic or {}).get("gemm_tensor"), "launches": gt["launches"],
                             "avg_launch_ms": gt["ms"] / max(gt["launches"], 1), "peak_source": peaks_src + ", sustained"}
         a_s = gs["bytes"] / max(gs["ms"], 1e-9) / 1e6
-        line["roofline_decode"] = {"kernel": "gemm_tcgen05_kernel swap-AB + splitk_reduce (decode weight streaming)",
+        line["roofline_decode"] = {"kernel": "gemm_stream_kernel (stream-K weight streaming, decode M <= 32)",
                                    "bound": "hbm", "achieved": a_s, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                    "frac": a_s / peaks["hbm_gbs"], "traffic": (traffic or {}).get("gemm_stream"),
                                    "launches": gs["launches"], "avg_launch_ms": gs["ms"] / max(gs["launches"], 1),

@@ -41,6 +41,10 @@ def main():
         ("llama_down_b16", 9728, 4096, 11008, native.EPI_NONE),
         ("llama_qkv_b32", 19456, 12288, 4096, native.EPI_NONE),
         ("square_8192", 8192, 8192, 8192, native.EPI_NONE),
+        ("sam_qkv_b8", 32768, 3840, 1280, native.EPI_NONE),
+        ("sam_proj_b8", 32768, 1280, 1280, native.EPI_NONE),
+        ("sam_fc1_b8", 32768, 5120, 1280, native.EPI_GELU),
+        ("sam_fc2_b8", 32768, 1280, 5120, native.EPI_NONE),
         ("decode_qkv_b8", 8, 12288, 4096, native.EPI_NONE),
         ("decode_gateup_b8", 8, 22016, 4096, native.EPI_SILU_MUL),
         ("decode_down_b8", 8, 4096, 11008, native.EPI_NONE),

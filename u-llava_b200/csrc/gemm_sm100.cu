@@ -10,7 +10,9 @@
 //     that the CTAs of one wave share A/B tiles through the 126 MB L2;
 //   * warp-specialised: warp0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, K-major
 //     64-element slabs), warp1 = single-thread tcgen05.mma issuer, warp2 = TMEM allocator,
-//     warps4-7 = epilogue (tcgen05.ld -> registers -> fused bias/activation/residual -> global);
+//     warps4-11 = epilogue (tcgen05.ld -> registers -> fused bias/activation/residual -> global), two warps per
+//     TMEM lane quadrant; the activation is a template parameter and uses MUFU-based GELU / sigmoid so that the
+//     epilogue of a 128 x 256 tile stays well under the tile's MMA time (a libm erff epilogue took 3.7x the MMA time);
 //   * 128 x BN fp32 accumulator lives in TMEM, double buffered (2*BN columns) so the epilogue
 //     of tile i overlaps the MMAs of tile i+1;
 //   * STAGES-deep shared-memory ring guarded by full/empty mbarriers; tcgen05.commit releases a
@@ -27,8 +29,9 @@ static constexpr int BM = 128;       // UMMA M (rows of A per tile)
 static constexpr int BK = 64;        // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
 static constexpr int GROUP_M = 8;    // rasterisation group
-static constexpr int kGemmThreads = 256;
-static constexpr int kEpiWarp0 = 4;  // first epilogue warp
+static constexpr int kGemmThreads = 384;
+static constexpr int kEpiWarp0 = 4;   // first epilogue warp
+static constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant, alternating 32-column chunks
 
 struct GemmKernelParams {
   void* D;
@@ -68,16 +71,47 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& sp
   n_blk = r / gm;
 }
 
-__device__ __forceinline__ float apply_act(float v, int epi) {
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(k x) = x / (1 + 2^(-k log2(e) x)): one MUFU.EX2 + one MUFU.RCP.  x -> -inf gives x * 0.
+__device__ __forceinline__ float fast_x_sigmoid(float x, float k_log2e) {
+  return x * rcp_approx(1.f + ex2_approx(-k_log2e * x));
+}
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) (nn.GELU, approximate='none'), erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7):  with a = |x|, s = a / sqrt 2, t = 1 / (1 + p s), E = poly(t) exp(-s^2) = 1 - erf(s):
+//   GELU(x) = max(x, 0) - 0.5 a E.          Max abs error 3.3e-7 over [-12, 12] (checked against math.erf).
+__device__ __forceinline__ float fast_gelu(float x) {
+  const float a = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678f, a, 1.f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = ex2_approx(a * a * -0.72134752f);  // exp(-x^2 / 2)
+  return fmaf(-0.5f * a, poly * t * e, fmaxf(x, 0.f));
+}
+
+template <int EPI>
+__device__ __forceinline__ float apply_act(float v) {
+  if constexpr (EPI == EPI_RELU) return fmaxf(v, 0.f);
+  else if constexpr (EPI == EPI_GELU) return fast_gelu(v);
+  else if constexpr (EPI == EPI_QUICK_GELU) return fast_x_sigmoid(v, 1.702f * 1.4426950408889634f);
+  else return v;
+}
+// runtime flavour for the (tiny) split-K reduce kernel
+__device__ __forceinline__ float apply_act_rt(float v, int epi) {
   switch (epi) {
     case EPI_RELU: return fmaxf(v, 0.f);
-    case EPI_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-    case EPI_QUICK_GELU: return __fdividef(v, 1.f + __expf(fminf(-1.702f * v, 80.f)));  // MUFU.EX2 + MUFU.RCP
+    case EPI_GELU: return fast_gelu(v);
+    case EPI_QUICK_GELU: return fast_x_sigmoid(v, 1.702f * 1.4426950408889634f);
     default: return v;
   }
 }
 
-template <typename T, int CH>
+template <typename T, int EPI, int CH>
 __device__ __forceinline__ void epilogue_store(float (&v)[CH], const GemmKernelParams& p, const T* bias, const T* resid,
                                                bool split_mode, int split, int row, int n0) {
 
@@ -112,15 +146,14 @@ __device__ __forceinline__ void epilogue_store(float (&v)[CH], const GemmKernelP
           }
         }
 
-        if (p.epilogue == EPI_SILU_MUL) {
+        if constexpr (EPI == EPI_SILU_MUL) {
           // weight rows are packed so that every 32-column chunk holds 16 gate columns followed by
           // the 16 matching up columns; output has N/2 columns.
           if constexpr (CH == 32) {
             float o[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float g = v[i];
-              o[i] = __fdividef(g, 1.f + __expf(fminf(-g, 80.f))) * v[16 + i];
+              o[i] = fast_x_sigmoid(v[i], 1.4426950408889634f) * v[16 + i];
             }
             const int on0 = n0 >> 1;
             if (p.out_f32) {
@@ -153,9 +186,9 @@ __device__ __forceinline__ void epilogue_store(float (&v)[CH], const GemmKernelP
           return;
         }
 
-        if (p.epilogue != EPI_NONE) {
+        if constexpr (EPI != EPI_NONE) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = apply_act(v[i], p.epilogue);
+          for (int i = 0; i < CH; ++i) v[i] = apply_act<EPI>(v[i]);
         }
 
         if (resid != nullptr) {
@@ -207,7 +240,7 @@ __device__ __forceinline__ void epilogue_store(float (&v)[CH], const GemmKernelP
         }
       }
 
-template <typename T, int BN, int STAGES>
+template <typename T, int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmKernelParams p) {
@@ -238,7 +271,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * 32);
+      mbar_init(&tmem_empty[a], kEpiWarps * 32);
     }
     fence_mbar_init();
   }
@@ -314,8 +347,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+    // ===================== epilogue (8 warps: TMEM lane quadrant = warp % 4, column chunks alternate) =====================
     const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const T* bias = reinterpret_cast<const T*>(p.bias);
@@ -331,7 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
       constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
 #pragma unroll 1
-      for (int c = 0; c < BN / CH; ++c) {
+      for (int c = half; c < BN / CH; c += 2) {
         float v[CH];
         if constexpr (CH == 32) {
           uint32_t r[32];
@@ -347,7 +381,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         }
         const int n0 = n_blk * BN + c * CH;
-        if (row_ok && n0 < p.N) epilogue_store<T, CH>(v, p, bias, resid, split_mode, split, row, n0);
+        if (row_ok && n0 < p.N) epilogue_store<T, EPI, CH>(v, p, bias, resid, split_mode, split, row, n0);
         __syncwarp();
       }
       tc_fence_before();
@@ -418,7 +452,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int R, int C
       if (c >= c_valid) continue;
       float v = tile[rr][tx];
       if (bias) v += T16<T>::to_f(bias[c]);
-      v = apply_act(v, epilogue);
+      v = apply_act_rt(v, epilogue);
       if (resid) v += T16<T>::to_f(resid[static_cast<int64_t>(r) * ldr + c]);
       if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(r) * ldo + c] = v;
       else reinterpret_cast<T*>(out)[static_cast<int64_t>(r) * ldo + c] = T16<T>::from_f(v);
@@ -446,7 +480,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int R, int C
       if (r >= R) continue;
       float v = tile[tx][cc];
       if (bias) v += T16<T>::to_f(bias[r]);
-      v = apply_act(v, epilogue);
+      v = apply_act_rt(v, epilogue);
       if (resid) v += T16<T>::to_f(resid[static_cast<int64_t>(c) * ldr + r]);
       if (out_f32) reinterpret_cast<float*>(out)[static_cast<int64_t>(c) * ldo + r] = v;
       else reinterpret_cast<T*>(out)[static_cast<int64_t>(c) * ldo + r] = T16<T>::from_f(v);
@@ -457,11 +491,11 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int R, int C
 // -----------------------------------------------------------------------------
 // Host side
 // -----------------------------------------------------------------------------
-template <typename T, int BN, int STAGES>
+template <typename T, int BN, int STAGES, int EPI>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
                           cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
-  auto kern = gemm_tcgen05_kernel<T, BN, STAGES>;
+  auto kern = gemm_tcgen05_kernel<T, BN, STAGES, EPI>;
   static bool configured = false;
   if (!configured) {
     ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -471,16 +505,30 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
 
-template <typename T>
+template <typename T, int EPI>
 static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
                      cudaStream_t stream) {
   switch (bn) {
-    case 256: return launch_variant<T, 256, 4>(ta, tb, p, grid, stream);
-    case 128: return launch_variant<T, 128, 6>(ta, tb, p, grid, stream);
-    case 64: return launch_variant<T, 64, 8>(ta, tb, p, grid, stream);
-    case 32: return launch_variant<T, 32, 8>(ta, tb, p, grid, stream);
-    case 16: return launch_variant<T, 16, 8>(ta, tb, p, grid, stream);
+    case 256: return launch_variant<T, 256, 4, EPI>(ta, tb, p, grid, stream);
+    case 128: return launch_variant<T, 128, 6, EPI>(ta, tb, p, grid, stream);
+    case 64: return launch_variant<T, 64, 8, EPI>(ta, tb, p, grid, stream);
+    case 32: return launch_variant<T, 32, 8, EPI>(ta, tb, p, grid, stream);
+    case 16: return launch_variant<T, 16, 8, EPI>(ta, tb, p, grid, stream);
     default: set_last_error("gemm: unsupported BN %d", bn); return ERR_UNSUPPORTED;
+  }
+}
+
+// the activation is compiled into the kernel; with split-K the kernel only parks fp32 partials (EPI_NONE)
+template <typename T>
+static int launch_epi(int epi, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+                      cudaStream_t stream) {
+  switch (epi) {
+    case EPI_NONE: return launch_bn<T, EPI_NONE>(bn, ta, tb, p, grid, stream);
+    case EPI_RELU: return launch_bn<T, EPI_RELU>(bn, ta, tb, p, grid, stream);
+    case EPI_GELU: return launch_bn<T, EPI_GELU>(bn, ta, tb, p, grid, stream);
+    case EPI_QUICK_GELU: return launch_bn<T, EPI_QUICK_GELU>(bn, ta, tb, p, grid, stream);
+    case EPI_SILU_MUL: return launch_bn<T, EPI_SILU_MUL>(bn, ta, tb, p, grid, stream);
+    default: set_last_error("gemm: unknown epilogue %d", epi); return ERR_BAD_ARG;
   }
 }
 
@@ -550,8 +598,9 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
     }
     const int tiles = p.num_m * p.num_n * splits;
     const int grid = tiles < sms ? tiles : sms;
-    st = (a.dtype == DT_BF16) ? launch_bn<__nv_bfloat16>(bn, ta, tb, p, grid, stream)
-                              : launch_bn<__half>(bn, ta, tb, p, grid, stream);
+    const int kepi = splits > 1 ? static_cast<int>(EPI_NONE) : a.epilogue;
+    st = (a.dtype == DT_BF16) ? launch_epi<__nv_bfloat16>(kepi, bn, ta, tb, p, grid, stream)
+                              : launch_epi<__half>(kepi, bn, ta, tb, p, grid, stream);
     if (st) return st;
     if (splits > 1) {
       dim3 g((a.M + 31) / 32, (a.N + 31) / 32);
