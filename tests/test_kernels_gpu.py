@@ -328,15 +328,19 @@ def _relpos_ref(q, k, v, rel_h, rel_w, S, scale):
     return (torch.softmax(attn, -1) @ vf).permute(0, 2, 1, 3)
 
 
+@pytest.mark.parametrize("packed_tables", [False, True])
 @pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("B,H,S,D", [(3, 2, 14, 80), (1, 2, 64, 80), (2, 2, 9, 64), (50, 16, 14, 80)])
-def test_attention_relpos(ctx, dtype, impl, B, H, S, D):
+def test_attention_relpos(ctx, dtype, impl, packed_tables, B, H, S, D):
     N = S * S
     qkv = _rand((B, N, 3, H, D), dtype, seed=46)
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     rel_h = _rand((2 * S - 1, D), dtype, scale=0.5, seed=47)
     rel_w = _rand((2 * S - 1, D), dtype, scale=0.5, seed=48)
+    if packed_tables:   # [Rh; Rw] in one buffer, as the model packs them (enables the single-pass window kernel)
+        both = torch.cat([rel_h, rel_w]).contiguous()
+        rel_h, rel_w = both[:2 * S - 1], both[2 * S - 1:]
     ctx.set_attention_impl(impl)
     try:
         out = ctx.attention_relpos(q, k, v, rel_h, rel_w, S)

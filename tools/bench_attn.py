@@ -46,8 +46,8 @@ def main():
         out = torch.empty((B, S, H, D), device="cuda", dtype=dt)
         flops = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
         if G:
-            rh = (torch.randn((2 * G - 1, D), device="cuda") * 0.3).to(dt)
-            rw = (torch.randn((2 * G - 1, D), device="cuda") * 0.3).to(dt)
+            both = (torch.randn((2 * (2 * G - 1), D), device="cuda") * 0.3).to(dt)
+            rh, rw = both[:2 * G - 1], both[2 * G - 1:]
             fn = lambda: ctx.attention_relpos(q, k, v, rh, rw, G, out=out)
         else:
             fn = lambda: ctx.attention(q, k, v, causal=causal, out=out)

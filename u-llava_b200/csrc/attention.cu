@@ -576,8 +576,10 @@ int attention_relpos_run(Context* ctx, const AttnArgs& a, const void* rel_h, con
   const int64_t strides[] = {a.q_bs, a.q_rs, a.q_hs, a.k_bs, a.k_rs, a.k_hs, a.v_bs, a.v_rs, a.v_hs, a.o_bs, a.o_rs, a.o_hs};
   for (int64_t st : strides) ULLAVA_REQUIRE(st % 8 == 0, "attention_relpos: strides must be multiples of 8 elements");
   if (a.batch == 0) return OK;
-  // auto: the 64 x 64 global grid goes to the tcgen05/TMEM kernel; 14 x 14 windows (two key tiles per CTA, prologue
-  // dominated) are still faster on the warp-level kernel
+  // 14 x 14 windows with head_dim 80 and back-to-back tables: dedicated single-pass kernel
+  if (ctx->attn_impl != 1 && fmha_window_supported(a, rel_h, rel_w, S)) return fmha_window_run(ctx, a, rel_h, o_row_map, stream);
+  // auto: the 64 x 64 global grid goes to the online-softmax tcgen05/TMEM kernel; other small grids (two key tiles per
+  // CTA, prologue dominated) are faster on the warp-level kernel
   if (ctx->attn_impl != 1 && fmha_supported(a, true, S) && (ctx->attn_impl == 2 || S == 64))
     return fmha_run(ctx, a, rel_h, rel_w, S, o_row_map, stream);
   FlashParams p;

@@ -104,26 +104,6 @@ __device__ __forceinline__ void fmha_issue_pv(uint32_t o_tmem, uint32_t p_tmem, 
   }
 }
 
-// ---- packed fp32 x2 arithmetic (sm_100: one issue slot for two lanes of work) -----------------------------------------
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // Lazy rescale of O (TMEM) and the running row sum when the row maximum of tile j (`mx`, log2 units) exceeds the
 // maximum in use by more than the threshold.  Warp-uniform control flow around the TMEM accesses.
 template <int HD>

@@ -82,6 +82,10 @@ bool fmha_supported(const AttnArgs& a, bool relpos, int S);
 int fmha_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel_w, int S, const int32_t* o_row_map,
              cudaStream_t stream);
 
+// fmha_window_sm100.cu -- SAM 14 x 14 windowed attention (hd 80), single pass, 2 CTAs per SM; needs [Rh; Rw] contiguous
+bool fmha_window_supported(const AttnArgs& a, const void* rel_h, const void* rel_w, int S);
+int fmha_window_run(Context* ctx, const AttnArgs& a, const void* rel_h, const int32_t* o_row_map, cudaStream_t stream);
+
 // elementwise.cu
 int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld_qkv, void* kc, void* vc, int64_t cache_bs, int64_t cache_hs,
                      int batch, int seq, int heads, int head_dim, int pos0, const float* cos_t, const float* sin_t,

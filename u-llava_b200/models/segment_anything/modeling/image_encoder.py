@@ -164,8 +164,11 @@ class ImageEncoderViT(nn.Module):
                 gmask |= 1 << i
             S = g if is_global else blk.window_size
             a = blk.attn
+            # [Rh; Rw] back to back in one buffer: the windowed-attention kernel loads both tables with one TMA box
+            rel_hw = torch.cat([self._rel_resized(a.rel_pos_h, S), self._rel_resized(a.rel_pos_w, S)]).detach().to(dt).contiguous()
+            n_rel = rel_hw.shape[0] // 2
             t += [blk.norm1.weight, blk.norm1.bias, a.qkv.weight, a.qkv.bias if a.qkv.bias is not None else z(3 * D),
-                  self._rel_resized(a.rel_pos_h, S), self._rel_resized(a.rel_pos_w, S), a.proj.weight, a.proj.bias,
+                  rel_hw[:n_rel], rel_hw[n_rel:], a.proj.weight, a.proj.bias,
                   blk.norm2.weight, blk.norm2.bias, blk.mlp.lin1.weight, blk.mlp.lin1.bias, blk.mlp.lin2.weight,
                   blk.mlp.lin2.bias]
             if not isinstance(blk.mlp.act, nn.GELU):
