@@ -203,7 +203,8 @@ def test_gemm_rejects_bad_arguments(ctx):
 # norms
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("rows,cols", [(577, 1024), (6, 256), (4096, 64), (33, 4096)])
+@pytest.mark.parametrize("rows,cols", [(577, 1024), (6, 256), (4096, 64), (33, 4096), (4100, 1280), (1031, 1024),
+                                       (2048, 256), (1025, 4096)])   # >= 1024 rows: warp-per-row kernel
 def test_layernorm(ctx, dtype, rows, cols):
     x = _rand((rows, cols), dtype, 2.0, seed=30) + 0.5
     w = _rand((cols,), dtype, seed=31)
@@ -217,7 +218,7 @@ def test_layernorm(ctx, dtype, rows, cols):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("rows,cols", [(608, 4096), (8, 4096), (5, 128)])
+@pytest.mark.parametrize("rows,cols", [(608, 4096), (8, 4096), (5, 128), (1216, 4096), (3000, 128)])
 def test_rmsnorm(ctx, dtype, rows, cols):
     x = _rand((rows, cols), dtype, 3.0, seed=33)
     w = _rand((cols,), dtype, seed=34)
