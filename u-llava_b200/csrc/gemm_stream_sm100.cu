@@ -27,7 +27,11 @@ namespace ullava {
 
 static constexpr int GS_BM = 128;     // weight rows per tile (UMMA M)
 static constexpr int GS_BK = 64;      // one SWIZZLE_128B row
-static constexpr int GS_STAGES = 8;     // 160 KB: one CTA per SM, 128 KB of W in flight
+static constexpr int GS_STAGES = 8;     // 160 KB: one CTA per SM (PDL then maps the next GEMM's CTAs 1:1 onto SMs),
+                                        // 128 KB of W in flight per SM.  Measured alternatives (decode-chain bench, B = 32):
+                                        // 5 stages x 2 CTAs/SM with 148 ranges 139 us/layer, with 296 ranges 151 us/layer,
+                                        // this configuration 109 us/layer.
+static constexpr int GS_CTAS_PER_SM = 1;
 static constexpr int GS_THREADS = 256;
 
 struct StreamParams {
@@ -74,7 +78,7 @@ __device__ __forceinline__ float gs_act(float v, int epi) {
 
 // EK: 0 = bias / residual only, 1 = SiLU(gate) * up, 2 = bias + ReLU / GELU / quick-GELU + residual
 template <typename T, int BN, int EK>
-__global__ void __launch_bounds__(GS_THREADS, 1)
+__global__ void __launch_bounds__(GS_THREADS, GS_CTAS_PER_SM)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                    const StreamParams p) {
   using S = StreamSmem<BN>;
@@ -367,7 +371,7 @@ static int stream_dispatch(int bn, int ek, const CUtensorMap& tw, const CUtensor
 }
 
 size_t gemm_stream_workspace_bytes(int sm_count) {
-  return kStreamCounterBytes + static_cast<size_t>(2) * sm_count * GS_BM * 32 * sizeof(float);
+  return kStreamCounterBytes + static_cast<size_t>(2) * GS_CTAS_PER_SM * sm_count * GS_BM * 32 * sizeof(float);
 }
 
 // a: the caller's GEMM (M <= 32 rows of X, N weight rows).  Uses ctx->workspace: [0, 64 KB) tile counters (kept at
@@ -382,9 +386,10 @@ int gemm_stream_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
   p.num_t = (a.N + GS_BM - 1) / GS_BM;
   p.kb_total = (a.K + GS_BK - 1) / GS_BK;
   const long long units = static_cast<long long>(p.num_t) * p.kb_total;
-  ULLAVA_REQUIRE(units * ctx->sm_count < (1ll << 31), "gemm_stream: %lld units exceed the 32-bit partition arithmetic", units);
+  ULLAVA_REQUIRE(units * GS_CTAS_PER_SM * ctx->sm_count < (1ll << 31), "gemm_stream: %lld units exceed the 32-bit partition arithmetic", units);
   p.units = static_cast<int>(units);
-  const int grid = p.units < ctx->sm_count ? p.units : ctx->sm_count;
+  const int slots = GS_CTAS_PER_SM * ctx->sm_count;
+  const int grid = p.units < slots ? p.units : slots;
   const size_t need = kStreamCounterBytes + static_cast<size_t>(2) * grid * GS_BM * bn * sizeof(float);
   if (need > ctx->workspace_bytes || static_cast<size_t>(p.num_t) * sizeof(int) > kStreamCounterBytes) {
     set_last_error("gemm_stream: workspace too small (%zu > %zu) or too many tiles (%d)", need, ctx->workspace_bytes,
