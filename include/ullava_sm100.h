@@ -116,6 +116,15 @@ ULLAVA_API int ullava_gemm(ullava_ctx* ctx, const ullava_gemm_args* args, void* 
  * turns the early launch off (plain stream order). */
 ULLAVA_API int ullava_set_pdl(ullava_ctx* ctx, int32_t enabled);
 
+/* Next-weight hint for a chain of M <= 32 products (the decode step is nn.Linear after nn.Linear,
+ * hf:models/llama/modeling_llama.py:171-333): the NEXT ullava_gemm call on this context that takes the
+ * weight-streaming path pulls the head of `next_weight` [n, k] (row stride ldb elements) into L2 while its own split
+ * reduction and epilogue run, so HBM stays busy across the kernel boundary.  A pure hint: results never depend on it;
+ * it is dropped by the next ullava_gemm call whatever path that takes.  ullava_llama_forward / _decode_step set it
+ * themselves.  ullava_set_weight_prefetch: 16 KB tiles per SM pulled ahead (0 = off, default 12). */
+ULLAVA_API int ullava_gemm_next_weight(ullava_ctx* ctx, const void* next_weight, int32_t n, int32_t k, int64_t ldb);
+ULLAVA_API int ullava_set_weight_prefetch(ullava_ctx* ctx, int32_t tiles_per_sm);
+
 /* ---- normalisation ---------------------------------------------------------------------
  * LayerNorm over the last dim (fp32 statistics): CLIP pre_layrnorm / layer_norm1/2
  * (hf:models/clip/modeling_clip.py:354-385,677), SAM TwoWayTransformer norms

@@ -159,6 +159,37 @@ def test_gemm_stream_after_norm_chain(ctx):
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize("tiles", [0, 12, 256])
+@pytest.mark.parametrize("nn,nk", [(4096, 4096), (300, 200), (128, 64), (22016, 4096)])
+def test_gemm_stream_next_weight_hint(ctx, tiles, nn, nk):
+    """ullava_gemm_next_weight is a pure hint: the L2 prefetch of the following GEMM's weights (ragged shapes, fewer
+    units than SMs, more tiles asked for than the next CTA's range holds) never changes a bit of either product."""
+    dtype = torch.bfloat16
+    M, N, K = 32, 4096, 1024
+    a = _rand((M, K), dtype, seed=31)
+    w = _rand((N, K), dtype, K ** -0.5, seed=32)
+    wn = _rand((nn, nk), dtype, nk ** -0.5, seed=33)
+    a2 = _rand((M, nk), dtype, seed=34)
+    base = ctx.gemm(a, w)
+    base2 = ctx.gemm(a2, wn)
+    _check(base, a.float() @ w.float().t(), dtype, "stream gemm")
+    ctx.set_weight_prefetch(tiles)
+    try:
+        for _ in range(2):
+            ctx.gemm_next_weight(wn)
+            out = ctx.gemm(a, w)
+            out2 = ctx.gemm(a2, wn)   # the hint was consumed by the call above: this launch prefetches nothing
+            assert torch.equal(out, base) and torch.equal(out2, base2)
+        ctx.gemm_next_weight(wn)
+        big = ctx.gemm(_rand((200, K), dtype, seed=35), w)   # large-M path drops the hint
+        assert big.shape == (200, N)
+        with pytest.raises(RuntimeError):
+            ctx.gemm_next_weight(wn[:, 1:])                   # misaligned / non-contiguous rows are rejected
+    finally:
+        ctx.set_weight_prefetch(12)
+        ctx.gemm_next_weight(None)
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("M", [4, 70])
 def test_gemm_lm_head_fp32_out(ctx, dtype, M):

@@ -28,12 +28,18 @@ def main():
     wbytes = sum(sum(t.numel() * 2 for k, t in l.items() if k.startswith("w")) for l in layers)
 
     def one_pass():
-        for l in layers:
+        # next-weight hints exactly as csrc/models.cu sets them inside the decode step (no hint across attention,
+        # which sits between qkv and o in the real step; here o follows qkv directly, so hint it as well)
+        for i, l in enumerate(layers):
             ctx.rmsnorm(hid, l["g1"], 1e-6, out=xn)
+            ctx.gemm_next_weight(l["wo"])
             ctx.gemm(xn, l["wqkv"], out=qkv)
+            ctx.gemm_next_weight(l["wgu"])
             ctx.gemm(qkv[:, :H], l["wo"], residual=hid, out=hid)
             ctx.rmsnorm(hid, l["g2"], 1e-6, out=xn)
+            ctx.gemm_next_weight(l["wd"])
             ctx.gemm(xn, l["wgu"], epilogue=native.EPI_SILU_MUL, out=act)
+            ctx.gemm_next_weight(layers[(i + 1) % L]["wqkv"])
             ctx.gemm(act, l["wd"], residual=hid, out=hid)
 
     if os.environ.get("NO_GRAPH"):   # for ncu: plain launches, two passes
@@ -42,8 +48,10 @@ def main():
         one_pass()
         torch.cuda.synchronize()
         return
-    for pdl in (True, False):
+    sweep = [(True, int(u)) for u in os.environ.get("PF_SWEEP", "0,12,0,12,24,0,24,48,0,48").split(",")] + [(False, 0)]
+    for pdl, pf in sweep:
         ctx.set_pdl(pdl)
+        ctx.set_weight_prefetch(pf)
         hid.normal_()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
@@ -63,10 +71,11 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
-        print(json.dumps({"chain": "llama7b_decode_gemms", "B": B, "pdl": pdl, "ms_per_pass": round(ms, 3),
+        print(json.dumps({"chain": "llama7b_decode_gemms", "B": B, "pdl": pdl, "prefetch_tiles_per_sm": pf, "ms_per_pass": round(ms, 3),
                           "us_per_layer": round(1e3 * ms / L, 1), "weight_GBps": round(wbytes / ms / 1e6, 1),
                           "frac_of_6554": round(wbytes / ms / 1e6 / 6554.2, 3)}), flush=True)
     ctx.set_pdl(True)
+    ctx.set_weight_prefetch(12)
 
 
 if __name__ == "__main__":

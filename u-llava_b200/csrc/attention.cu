@@ -604,6 +604,14 @@ int attention_relpos_run(Context* ctx, const AttnArgs& a, const void* rel_h, con
   return st;
 }
 
+// streaming 16-byte load: read once, do not keep in L1
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 // ---- decode attention --------------------------------------------------------------------------
 // One CTA per (head, sample).  Phase 1: scores (LPK lanes per key, 16 elements per lane) into shared
 // memory; phase 2: block softmax; phase 3: P V with 16-byte V loads, 128/(HD/8) key groups reduced
@@ -642,26 +650,40 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
     }
   }
   float lmax = -INFINITY;
-  for (int j0 = warp * KPW; j0 < ctx_len; j0 += (DEC_THREADS / 32) * KPW) {
-    const int j = j0 + kin;
-    float acc = 0.f;
-    if (j < ctx_len) {
-      const T* kr = kp + static_cast<int64_t>(j) * HD + sub * 16;
-      const uint4 a = *reinterpret_cast<const uint4*>(kr);
-      const uint4 c = *reinterpret_cast<const uint4*>(kr + 8);
-      const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  // KU key rows per lane in flight (2 x 16 B each): the loop is latency-bound otherwise (one CTA holds only 4 warps)
+  constexpr int KU = 4;
+  constexpr int KSTEP = (DEC_THREADS / 32) * KPW;
+  for (int j0 = warp * KPW; j0 < ctx_len; j0 += KU * KSTEP) {
+    uint4 ka[KU], kb[KU];
+#pragma unroll
+    for (int r = 0; r < KU; ++r) {
+      const int j = j0 + r * KSTEP + kin;
+      if (j < ctx_len) {
+        const T* kr = kp + static_cast<int64_t>(j) * HD + sub * 16;
+        ka[r] = ld_stream(reinterpret_cast<const uint4*>(kr));
+        kb[r] = ld_stream(reinterpret_cast<const uint4*>(kr + 8));
+      } else {
+        ka[r] = make_uint4(0u, 0u, 0u, 0u);
+        kb[r] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < KU; ++r) {
+      const int j = j0 + r * KSTEP + kin;
+      const uint32_t u[8] = {ka[r].x, ka[r].y, ka[r].z, ka[r].w, kb[r].x, kb[r].y, kb[r].z, kb[r].w};
+      float acc = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float2 f = unpack2<T>(u[e]);
         acc += f.x * qf[2 * e] + f.y * qf[2 * e + 1];
       }
-    }
 #pragma unroll
-    for (int off = LPK / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    acc *= scale_log2;
-    if (j < ctx_len) {
-      if (sub == 0) dec_smem[j] = acc;
-      lmax = fmaxf(lmax, acc);
+      for (int off = LPK / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      acc *= scale_log2;
+      if (j < ctx_len) {
+        if (sub == 0) dec_smem[j] = acc;
+        lmax = fmaxf(lmax, acc);
+      }
     }
   }
   lmax = warp_max(lmax);
@@ -697,15 +719,26 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
   constexpr int GROUPS = DEC_THREADS / TPR;
   const int grp = tid / TPR, dv = (tid % TPR) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j = grp; j < ctx_len; j += GROUPS) {
-    const float pj = T16<T>::to_f(T16<T>::from_f(dec_smem[j] * inv));
-    const uint4 a = *reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(j) * HD + dv);
-    const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+  constexpr int VU = 8;  // V rows per thread in flight (16 B each); rows are accumulated in increasing j
+  for (int j0 = grp; j0 < ctx_len; j0 += VU * GROUPS) {
+    uint4 va[VU];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack2<T>(u[e]);
-      acc[2 * e] += pj * f.x;
-      acc[2 * e + 1] += pj * f.y;
+    for (int r = 0; r < VU; ++r) {
+      const int j = j0 + r * GROUPS;
+      va[r] = j < ctx_len ? ld_stream(reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(j) * HD + dv))
+                          : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < VU; ++r) {
+      const int j = j0 + r * GROUPS;
+      const float pj = j < ctx_len ? T16<T>::to_f(T16<T>::from_f(dec_smem[j] * inv)) : 0.f;
+      const uint32_t u[4] = {va[r].x, va[r].y, va[r].z, va[r].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2<T>(u[e]);
+        acc[2 * e] += pj * f.x;
+        acc[2 * e + 1] += pj * f.y;
+      }
     }
   }
   __syncthreads();  // scores no longer needed: reuse shared memory for the cross-group reduction

@@ -51,6 +51,28 @@ int ullava_set_pdl(ullava_ctx* ctx, int32_t enabled) {
   return OK;
 }
 
+int ullava_gemm_next_weight(ullava_ctx* ctx, const void* next_weight, int32_t n, int32_t k, int64_t ldb) {
+  CTX_CHECK("ullava_gemm_next_weight");
+  if (next_weight != nullptr && (n <= 0 || k <= 0 || ldb < k || (ldb % 8) != 0 ||
+                                 (reinterpret_cast<uintptr_t>(next_weight) & 15) != 0)) {
+    set_last_error("ullava_gemm_next_weight: bad shape / stride / alignment (n=%d k=%d ldb=%lld)", n, k,
+                   static_cast<long long>(ldb));
+    return ERR_BAD_ARG;
+  }
+  ctx->next_w = next_weight; ctx->next_n = n; ctx->next_k = k; ctx->next_ldb = ldb;
+  return OK;
+}
+
+int ullava_set_weight_prefetch(ullava_ctx* ctx, int32_t tiles_per_sm) {
+  CTX_CHECK("ullava_set_weight_prefetch");
+  if (tiles_per_sm < 0 || tiles_per_sm > 256) {
+    set_last_error("ullava_set_weight_prefetch: tiles_per_sm must be in [0, 256]");
+    return ERR_BAD_ARG;
+  }
+  ctx->prefetch_units = tiles_per_sm;
+  return OK;
+}
+
 int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q_bs, const void* k_cache, const void* v_cache,
                             int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
                             int32_t head_dim, int32_t ctx_len, float scale, int32_t dtype, void* stream) {

@@ -164,6 +164,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       "l"(hint)
       : "memory");
 }
+// Prefetch of a 2D tile into L2 only (no shared-memory destination, no barrier): a hint, never a fault.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // 2-CTA (cta_group::2) flavour: executed by both CTAs of a pair, the transaction
 // bytes are signalled on the LEADER CTA's barrier (peer bit of the address cleared).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {

@@ -550,6 +550,7 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
     return ERR_BAD_ARG;
   }
   if (!swap) {
+    ctx->next_w = nullptr;  // the next-weight hint only applies to the weight-streaming kernel
     const int bn = a.force_bn ? a.force_bn : pick_bn_large(a.N);
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.num_m = (a.M + BM - 1) / BM;

@@ -45,8 +45,11 @@ struct StreamParams {
   int num_t;          // weight tiles
   int kb_total;       // k-blocks per tile
   int units;          // num_t * kb_total (host guarantees units * gridDim.x < 2^31)
-  float* partials;    // [2 * gridDim.x][128][BN] fp32
+  float* partials;    // [2 * gridDim.x][BN / 4][128] float4 (fp32 partial tiles, row-interleaved for coalescing)
   int* counters;      // [num_t], zero between launches
+  // next-weight L2 prefetch (tmP): partition of the NEXT GEMM's units over ITS grid; this CTA pulls units
+  // [lo' + pf_skip, lo' + pf_skip + pf_count) of the range CTA blockIdx.x of the next kernel will stream
+  int pf_kb_total, pf_units, pf_grid, pf_skip, pf_count;
 };
 
 __device__ __forceinline__ int gs_lo(int c, int U, int G) {
@@ -80,7 +83,7 @@ __device__ __forceinline__ float gs_act(float v, int epi) {
 template <typename T, int BN, int EK>
 __global__ void __launch_bounds__(GS_THREADS, GS_CTAS_PER_SM)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                   const StreamParams p) {
+                   const __grid_constant__ CUtensorMap tmP, const StreamParams p) {
   using S = StreamSmem<BN>;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr uint32_t kIdesc = make_idesc_f16(T16<T>::kUmmaFormat, GS_BM, BN);
@@ -153,6 +156,16 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (++stage == GS_STAGES) {
           stage = 0;
           phase ^= 1;
+        }
+      }
+      // All of this CTA's weights are in flight.  Keep HBM busy through the reduction / epilogue tail and the kernel
+      // boundary: pull the tiles the next GEMM's CTA on this SM will ask for right after its ring fill into L2.
+      if (p.pf_count > 0 && static_cast<int>(blockIdx.x) < p.pf_grid) {
+        const int plo = gs_lo(blockIdx.x, p.pf_units, p.pf_grid) + p.pf_skip;
+        const int phi = min(gs_lo(blockIdx.x + 1, p.pf_units, p.pf_grid), plo + p.pf_count);
+        for (int u = plo; u < phi; ++u) {
+          const int t = u / p.pf_kb_total, kb = u - t * p.pf_kb_total;
+          tma_prefetch_2d(&tmP, kb * GS_BK, t * GS_BM);
         }
       }
     }
@@ -238,9 +251,10 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       if (!whole) {
         // park the partial, then find out whether this CTA is the last contributor of tile t
         const int which = (lo >= t0) ? 0 : 1;  // 0: my range starts inside the tile, 1: it only ends there
-        float* mine = p.partials + (static_cast<size_t>(2 * blockIdx.x + which) * GS_BM + etid) * BN;
+        // slot layout [BN/4][128 rows] of float4: a warp's store / load covers 512 contiguous bytes
+        float4* mine = reinterpret_cast<float4*>(p.partials) + static_cast<size_t>(2 * blockIdx.x + which) * (GS_BM * BN / 4) + etid;
 #pragma unroll
-        for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < BN / 4; ++i) mine[i * GS_BM] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         // release/acquire through the tile counter: the CTA barrier orders every thread's partial stores before
         // thread 0's gpu-scope release, and the last arriver's acquire before every thread's loads (cumulativity)
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -257,18 +271,32 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           // on which contributor happened to arrive last, so greedy decode stays bit-reproducible
 #pragma unroll
           for (int i = 0; i < BN; ++i) v[i] = 0.f;
+          // two contributors in flight per step (one L2 round trip per pair instead of per contributor); the adds
+          // still happen in CTA order
           int c_lo = gs_lo(c_first, U, G);
 #pragma unroll 1
-          for (int c = c_first; c <= c_last; ++c) {
-            const int w = (c_lo >= t0) ? 0 : 1;
+          for (int c = c_first; c <= c_last; c += 2) {
+            const int w0 = (c_lo >= t0) ? 0 : 1;
             c_lo = gs_lo(c + 1, U, G);
-            const float* other = p.partials + (static_cast<size_t>(2 * c + w) * GS_BM + etid) * BN;
-            float4 f[BN / 4];
+            const bool two = c + 1 <= c_last;
+            const int w1 = (c_lo >= t0) ? 0 : 1;
+            c_lo = gs_lo(c + 2, U, G);
+            const float4* o0 = reinterpret_cast<const float4*>(p.partials) + static_cast<size_t>(2 * c + w0) * (GS_BM * BN / 4) + etid;
+            const float4* o1 = two ? reinterpret_cast<const float4*>(p.partials) + static_cast<size_t>(2 * (c + 1) + w1) * (GS_BM * BN / 4) + etid : o0;
+            float4 f[BN / 4], g[BN / 4];
 #pragma unroll
-            for (int i = 0; i < BN / 4; ++i) f[i] = __ldcg(reinterpret_cast<const float4*>(other) + i);
+            for (int i = 0; i < BN / 4; ++i) f[i] = __ldcg(o0 + i * GS_BM);
+#pragma unroll
+            for (int i = 0; i < BN / 4; ++i) g[i] = __ldcg(o1 + i * GS_BM);
 #pragma unroll
             for (int i = 0; i < BN / 4; ++i) {
               v[4 * i] += f[i].x; v[4 * i + 1] += f[i].y; v[4 * i + 2] += f[i].z; v[4 * i + 3] += f[i].w;
+            }
+            if (two) {
+#pragma unroll
+              for (int i = 0; i < BN / 4; ++i) {
+                v[4 * i] += g[i].x; v[4 * i + 1] += g[i].y; v[4 * i + 2] += g[i].z; v[4 * i + 3] += g[i].w;
+              }
             }
           }
           if (etid == 0) p.counters[t] = 0;  // ready for the next launch / graph replay
@@ -344,8 +372,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 // Host side
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T, int BN, int EK>
-static int stream_launch(const CUtensorMap& tw, const CUtensorMap& tx, const StreamParams& p, int grid, bool pdl,
-                         cudaStream_t stream) {
+static int stream_launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tp, const StreamParams& p,
+                         int grid, bool pdl, cudaStream_t stream) {
   using S = StreamSmem<BN>;
   auto kern = gemm_stream_kernel<T, BN, EK>;
   static bool configured = false;
@@ -353,21 +381,21 @@ static int stream_launch(const CUtensorMap& tw, const CUtensorMap& tx, const Str
     ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  return check_cuda(launch_pdl(kern, dim3(grid), dim3(GS_THREADS), S::kTotal, stream, pdl, tw, tx, p),
+  return check_cuda(launch_pdl(kern, dim3(grid), dim3(GS_THREADS), S::kTotal, stream, pdl, tw, tx, tp, p),
                     "gemm_stream_kernel launch");
 }
 
 template <typename T>
-static int stream_dispatch(int bn, int ek, const CUtensorMap& tw, const CUtensorMap& tx, const StreamParams& p, int grid,
-                           bool pdl, cudaStream_t stream) {
+static int stream_dispatch(int bn, int ek, const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tp,
+                           const StreamParams& p, int grid, bool pdl, cudaStream_t stream) {
   if (bn == 16) {
-    if (ek == 0) return stream_launch<T, 16, 0>(tw, tx, p, grid, pdl, stream);
-    if (ek == 1) return stream_launch<T, 16, 1>(tw, tx, p, grid, pdl, stream);
-    return stream_launch<T, 16, 2>(tw, tx, p, grid, pdl, stream);
+    if (ek == 0) return stream_launch<T, 16, 0>(tw, tx, tp, p, grid, pdl, stream);
+    if (ek == 1) return stream_launch<T, 16, 1>(tw, tx, tp, p, grid, pdl, stream);
+    return stream_launch<T, 16, 2>(tw, tx, tp, p, grid, pdl, stream);
   }
-  if (ek == 0) return stream_launch<T, 32, 0>(tw, tx, p, grid, pdl, stream);
-  if (ek == 1) return stream_launch<T, 32, 1>(tw, tx, p, grid, pdl, stream);
-  return stream_launch<T, 32, 2>(tw, tx, p, grid, pdl, stream);
+  if (ek == 0) return stream_launch<T, 32, 0>(tw, tx, tp, p, grid, pdl, stream);
+  if (ek == 1) return stream_launch<T, 32, 1>(tw, tx, tp, p, grid, pdl, stream);
+  return stream_launch<T, 32, 2>(tw, tx, tp, p, grid, pdl, stream);
 }
 
 size_t gemm_stream_workspace_bytes(int sm_count) {
@@ -403,10 +431,27 @@ int gemm_stream_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
   if (st) return st;
   st = encode_tmap_2d(&tx, a.A, 2, a.K, a.M, a.lda * 2, GS_BK, bn, true);
   if (st) return st;
+  // next-weight hint -> prefetch-only tensor map over the next GEMM's W (same 64 x 128 box)
+  CUtensorMap tp = tw;
+  if (ctx->next_w != nullptr && ctx->prefetch_units > 0 && ctx->next_n > 0 && ctx->next_k > 0) {
+    const int n_t = (ctx->next_n + GS_BM - 1) / GS_BM, n_kb = (ctx->next_k + GS_BK - 1) / GS_BK;
+    const long long n_units = static_cast<long long>(n_t) * n_kb;
+    if (n_units * slots < (1ll << 31) &&
+        encode_tmap_2d(&tp, ctx->next_w, 2, ctx->next_k, ctx->next_n, ctx->next_ldb * 2, GS_BK, GS_BM, true) == OK) {
+      p.pf_kb_total = n_kb;
+      p.pf_units = static_cast<int>(n_units);
+      p.pf_grid = p.pf_units < slots ? p.pf_units : slots;
+      p.pf_skip = GS_STAGES;  // the ring fill is issued by the next kernel itself, before its griddepcontrol.wait
+      p.pf_count = ctx->prefetch_units;
+    } else {
+      tp = tw;
+    }
+  }
+  ctx->next_w = nullptr;
   const bool pdl = ctx->pdl != 0;
   const int ek = a.epilogue == EPI_SILU_MUL ? 1 : (a.epilogue == EPI_NONE ? 0 : 2);
-  st = a.dtype == DT_BF16 ? stream_dispatch<__nv_bfloat16>(bn, ek, tw, tx, p, grid, pdl, stream)
-                          : stream_dispatch<__half>(bn, ek, tw, tx, p, grid, pdl, stream);
+  st = a.dtype == DT_BF16 ? stream_dispatch<__nv_bfloat16>(bn, ek, tw, tx, tp, p, grid, pdl, stream)
+                          : stream_dispatch<__half>(bn, ek, tw, tx, tp, p, grid, pdl, stream);
   if (st == OK) ctx->launches += 1;
   return st;
 }

@@ -34,6 +34,10 @@ static int gemm(Context* ctx, cudaStream_t s, int dtype, const void* A, int64_t 
   return gemm_run(ctx, a, s);
 }
 
+static inline void next_weight(Context* ctx, const void* w, int n, int k, int64_t ldb) {
+  ctx->next_w = w; ctx->next_n = n; ctx->next_k = k; ctx->next_ldb = ldb;
+}
+
 #define RUN(expr)              \
   do {                         \
     int _st = (expr);          \
@@ -121,7 +125,8 @@ size_t llama_scratch(int rows, int hidden, int ffn) {
   return t + 4096;
 }
 
-int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev) {
+int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev,
+                      const void* tail_w, int tail_n) {
   ULLAVA_REQUIRE(pos_dev == nullptr || a.seq == 1, "llama_forward: a device-side position needs seq == 1");
   ULLAVA_REQUIRE(a.weights && a.hidden && a.k_cache && a.v_cache && a.scratch && a.rope_cos && a.rope_sin,
                  "llama_forward: null pointer");
@@ -172,9 +177,18 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
       at.causal = 1; at.q_pos0 = a.pos0; at.scale = scale; at.dtype = dt;
       RUN(attention_run(ctx, at, s));
     }
+    // Decode (rows <= 32): each weight-streaming GEMM pulls the head of the NEXT weight matrix into L2 under its own
+    // tail.  (Not across the attention kernel: its KV stream would evict the lines before W_o is read.)
+    const bool hint = rows <= 32;
+    if (hint) next_weight(ctx, L[4], 2 * F, H, H);
     RUN(gemm(ctx, s, dt, att, H, L[2], H, a.hidden, H, rows, H, H, nullptr, EPI_NONE, a.hidden, H));
     RUN(rmsnorm_run(ctx, a.hidden, H, L[3], xn, H, rows, H, a.eps, dt, s));
+    if (hint) next_weight(ctx, L[5], H, F, F);
     RUN(gemm(ctx, s, dt, xn, H, L[4], H, act, F, rows, 2 * F, H, nullptr, EPI_SILU_MUL));
+    if (hint) {
+      if (l + 1 < a.layers) next_weight(ctx, a.weights[6 * (l + 1) + 1], 3 * H, H, H);
+      else if (tail_w) next_weight(ctx, tail_w, tail_n, H, H);
+    }
     RUN(gemm(ctx, s, dt, act, F, L[5], F, a.hidden, H, rows, H, F, nullptr, EPI_NONE, a.hidden, H));
   }
   if (a.final_out) {
@@ -194,7 +208,7 @@ int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_
   ULLAVA_REQUIRE(L.seq == 1 && L.final_out, "decode_step: llama.seq must be 1 and final_out set");
   ULLAVA_REQUIRE(a.pos_dev && a.embed_table && a.lm_head && a.cur_ids && a.logits, "decode_step: null pointer");
   RUN(embed_gather_run(ctx, a.cur_ids, a.embed_table, L.hidden, L.batch, L.hidden_size, a.vocab, L.dtype, s));
-  RUN(llama_forward_run(ctx, L, s, a.pos_dev));
+  RUN(llama_forward_run(ctx, L, s, a.pos_dev, a.lm_head, a.vocab));
   GemmArgs g{};
   g.A = L.final_out; g.lda = L.hidden_size; g.B = a.lm_head; g.ldb = L.hidden_size; g.D = a.logits; g.ldd = a.vocab;
   g.M = L.batch; g.N = a.vocab; g.K = L.hidden_size; g.dtype = L.dtype; g.out_f32 = 1; g.epilogue = EPI_NONE;

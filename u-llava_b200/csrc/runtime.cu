@@ -1,4 +1,5 @@
 // Context, error reporting and TMA-descriptor encoding for libullava_sm100.so.
+#include <cstdlib>
 #include "common.cuh"
 #include "ullava_internal.h"
 
@@ -146,6 +147,10 @@ int ullava_create(int device, ullava_ctx** out) {
   ullava_ctx* c = new ullava_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("ULLAVA_PREFETCH_UNITS")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 256) c->prefetch_units = v;
+  }
   *out = c;
   return OK;
 }

@@ -21,6 +21,13 @@ struct ullava_ctx {
   int64_t launches = 0;
   int pdl = 1;        // decode GEMMs are launched with programmatic stream serialization (weight prefetch under the
                       // previous kernel's tail); 0 = plain launches
+  // Next-weight hint for the weight-streaming GEMM (ullava_gemm_next_weight): the M <= 32 GEMM launched next on this
+  // context pulls the first tiles of THIS matrix into L2 while its own split reduction / epilogue tail runs, so HBM
+  // stays busy across the kernel boundary.  Consumed (cleared) by the next ullava_gemm call.
+  const void* next_w = nullptr;
+  int next_n = 0, next_k = 0;
+  int64_t next_ldb = 0;
+  int prefetch_units = 12;  // 16 KB tiles per SM pulled into L2 (0 = off); ULLAVA_PREFETCH_UNITS overrides at create
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
   bool prof_on = false;
@@ -119,7 +126,9 @@ size_t sam_encoder_scratch(int batch, int img, int patch, int embed_dim, int win
 // models.cu
 int vit_forward_run(Context* ctx, const ullava_vit_args& a, cudaStream_t stream);
 size_t vit_scratch(int batch, int img, int patch, int hidden, int ffn, int k_pad);
-int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev = nullptr);
+// tail_w/tail_n: weight [tail_n, H] of the GEMM the caller runs right after the stack (lm_head), prefetch hint only
+int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev = nullptr,
+                      const void* tail_w = nullptr, int tail_n = 0);
 int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_t s);
 size_t llama_scratch(int rows, int hidden, int ffn);
 

@@ -97,6 +97,8 @@ _SIGNATURES = {
     "ullava_attention_relpos": (_i32, [_vp, C.POINTER(AttnArgs), _vp, _vp, _i32, _vp, _vp]),
     "ullava_set_attention_impl": (_i32, [_vp, _i32]),
     "ullava_set_pdl": (_i32, [_vp, _i32]),
+    "ullava_gemm_next_weight": (_i32, [_vp, _vp, _i32, _i32, _i64]),
+    "ullava_set_weight_prefetch": (_i32, [_vp, _i32]),
     "ullava_attention_decode": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32,
                                        _f32, _i32, _vp]),
     "ullava_rope_kvcache": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
@@ -297,6 +299,18 @@ class Context:
     def set_pdl(self, enabled: bool):
         """Programmatic dependent launch for the decode (M <= 32) GEMMs: weight prefetch under the previous kernel."""
         self._chk(self.lib.ullava_set_pdl(self.handle, int(bool(enabled))))
+
+    def gemm_next_weight(self, w: Optional[torch.Tensor]):
+        """Hint: the next M <= 32 gemm() pulls the head of `w` ([N, K] nn.Linear weight of the GEMM after it) into L2."""
+        if w is None:
+            self._chk(self.lib.ullava_gemm_next_weight(self.handle, None, 0, 0, 0))
+        else:
+            assert w.dim() == 2 and w.stride(1) == 1
+            self._chk(self.lib.ullava_gemm_next_weight(self.handle, w.data_ptr(), w.shape[0], w.shape[1], w.stride(0)))
+
+    def set_weight_prefetch(self, tiles_per_sm: int):
+        """16 KB weight tiles per SM each decode GEMM pulls ahead for its successor (0 = off)."""
+        self._chk(self.lib.ullava_set_weight_prefetch(self.handle, int(tiles_per_sm)))
 
     def set_attention_impl(self, impl: int):
         """0 = per shape (default), 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled."""
