@@ -624,6 +624,7 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
                    int64_t cache_bs, int64_t cache_hs, T* __restrict__ o, int64_t o_bs, int ctx_len,
                    float scale_log2, const int32_t* __restrict__ ctx_dev) {
   pdl_launch_dependents();  // the o-projection GEMM may start prefetching its weights under this kernel
+  pdl_wait();               // launched with programmatic serialization: resident before the RoPE / KV-write kernel ends
   if (ctx_dev) ctx_len = *ctx_dev + 1;  // CUDA-graph decode: keys 0..pos are attended, pos read from device memory
   extern __shared__ float dec_smem[];   // [ctx_len] scores, then [groups][HD] partial outputs
   __shared__ float red[DEC_THREADS / 32];
@@ -757,7 +758,7 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
 template <typename T, int HD>
 static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
-                         cudaStream_t stream, const int32_t* ctx_dev, int max_ctx) {
+                         cudaStream_t stream, const int32_t* ctx_dev, int max_ctx, bool pdl) {
   constexpr int GROUPS = DEC_THREADS / (HD / 8);
   const int smem_ctx = ctx_dev ? max_ctx : ctx_len;  // with a device-side length the buffer covers the whole cache
   size_t smem = sizeof(float) * static_cast<size_t>(smem_ctx > GROUPS * HD ? smem_ctx : GROUPS * HD);
@@ -766,10 +767,10 @@ static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void
     ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   dim3 grid(heads, batch);
-  kern<<<grid, DEC_THREADS, smem, stream>>>(static_cast<const T*>(q), q_bs, static_cast<const T*>(kc),
-                                            static_cast<const T*>(vc), cache_bs, cache_hs, static_cast<T*>(o), o_bs,
-                                            ctx_len, scale * 1.4426950408889634f, ctx_dev);
-  return check_cuda(cudaGetLastError(), "attn_decode launch");
+  return check_cuda(launch_pdl(kern, grid, dim3(DEC_THREADS), smem, stream, pdl, static_cast<const T*>(q), q_bs,
+                               static_cast<const T*>(kc), static_cast<const T*>(vc), cache_bs, cache_hs,
+                               static_cast<T*>(o), o_bs, ctx_len, scale * 1.4426950408889634f, ctx_dev),
+                    "attn_decode launch");
 }
 
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
@@ -784,7 +785,7 @@ int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* 
   int st;
 #define ULLAVA_DEC(TT, HDIM) \
   st = decode_launch<TT, HDIM>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream, \
-                               ctx_dev, max_ctx)
+                               ctx_dev, max_ctx, ctx->pdl != 0)
   if (dtype == DT_BF16) {
     if (head_dim == 128) ULLAVA_DEC(__nv_bfloat16, 128);
     else if (head_dim == 64) ULLAVA_DEC(__nv_bfloat16, 64);

@@ -15,6 +15,10 @@ __global__ void __launch_bounds__(256)
 rope_kvcache_kernel(T* __restrict__ qkv, int64_t ld, T* __restrict__ kc, T* __restrict__ vc, int64_t cache_bs,
                     int64_t cache_hs, int seq, int heads, int hd, int pos0, const float* __restrict__ cos_t,
                     const float* __restrict__ sin_t, const int32_t* __restrict__ pos_dev) {
+  // Launched with programmatic serialization in the decode step: the CTA is resident (launch latency paid) while the
+  // QKV GEMM still runs; nothing is read before griddepcontrol.wait.
+  pdl_launch_dependents();
+  pdl_wait();
   if (pos_dev) pos0 = *pos_dev;  // CUDA-graph decode: the position lives in device memory
   const int row = blockIdx.x;
   const int b = row / seq, s = row - b * seq;
@@ -70,17 +74,19 @@ int rope_kvcache_run(Context* ctx, void* qkv, int64_t ld, void* kc, void* vc, in
   ULLAVA_REQUIRE(hd % 16 == 0 && ld % 8 == 0 && cache_bs % 8 == 0 && cache_hs % 8 == 0, "rope: bad alignment");
   const int rows = batch * seq;
   if (rows == 0) return OK;
+  const bool pdl = ctx->pdl != 0 && seq == 1;
+  cudaError_t e;
   if (dtype == DT_BF16)
-    rope_kvcache_kernel<__nv_bfloat16><<<rows, 256, 0, stream>>>(
-        static_cast<__nv_bfloat16*>(qkv), ld, static_cast<__nv_bfloat16*>(kc), static_cast<__nv_bfloat16*>(vc),
-        cache_bs, cache_hs, seq, heads, hd, pos0, cos_t, sin_t, pos_dev);
+    e = launch_pdl(rope_kvcache_kernel<__nv_bfloat16>, dim3(rows), dim3(256), 0, stream, pdl,
+                   static_cast<__nv_bfloat16*>(qkv), ld, static_cast<__nv_bfloat16*>(kc),
+                   static_cast<__nv_bfloat16*>(vc), cache_bs, cache_hs, seq, heads, hd, pos0, cos_t, sin_t, pos_dev);
   else if (dtype == DT_F16)
-    rope_kvcache_kernel<__half><<<rows, 256, 0, stream>>>(static_cast<__half*>(qkv), ld, static_cast<__half*>(kc),
-                                                          static_cast<__half*>(vc), cache_bs, cache_hs, seq, heads,
-                                                          hd, pos0, cos_t, sin_t, pos_dev);
+    e = launch_pdl(rope_kvcache_kernel<__half>, dim3(rows), dim3(256), 0, stream, pdl, static_cast<__half*>(qkv), ld,
+                   static_cast<__half*>(kc), static_cast<__half*>(vc), cache_bs, cache_hs, seq, heads, hd, pos0, cos_t,
+                   sin_t, pos_dev);
   else { set_last_error("rope: unsupported dtype"); return ERR_UNSUPPORTED; }
   ctx->launches++;
-  return check_cuda(cudaGetLastError(), "rope_kvcache launch");
+  return check_cuda(e, "rope_kvcache launch");
 }
 
 // ---------------------------------------------------------------------------------------------
