@@ -317,6 +317,10 @@ typedef struct ullava_decode_args {
   void* hid_buf; int64_t hid_bs;            /* device [B, hid_bs / H, H] 16-bit or NULL (hid_bs in elements) */
   uint8_t* finished;            /* device [B] or NULL */
   int32_t eos_id, pad_id;       /* eos_id < 0: never stop */
+  /* sampling (do_sample = temperature > 0, models/ullava.py:350-362): uniforms != NULL selects ullava_sample_step
+   * instead of the argmax; uniforms[pos * uniforms_ld + b] in [0, 1) is the draw of row b at position pos */
+  const float* uniforms; int64_t uniforms_ld;
+  float temperature, top_p;
 } ullava_decode_args;
 ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, void* stream);
 /* The bookkeeping tail of a step on its own (used once after the prefill, with *pos_dev = P - 1):
@@ -324,6 +328,53 @@ ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_arg
 ULLAVA_API int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, int64_t* cur_ids,
                        int64_t* seqs, int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
                        uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, void* stream);
+
+/* Sampling flavour of the same tail (temperature > 0; top_p in (0, 1) filters like TopPLogitsWarper, 0 or 1 = off):
+ * scores = logits / temperature, nucleus filter, then ONE draw per row by inverse CDF in vocabulary order with the
+ * caller's uniform number uniforms[pos * uniforms_ld + b] (pos = *pos_dev, 0 if pos_dev is NULL).  torch.multinomial's
+ * random stream is not reproducible outside torch: parity is on the filtered distribution (probs_out, optional
+ * [rows, cols] fp32, receives it) and on the inverse-CDF draw.  Replaces the sampling branch of
+ * GenerationMixin.generate as called by models/ullava.py:350-362. */
+ULLAVA_API int ullava_sample_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, float temperature,
+                       float top_p, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
+                       int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
+                       uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, float* probs_out,
+                       void* stream);
+
+/* ---- evaluation metrics on the device (evaluation/tools.py, evaluation/eval_ullava.py:41-102) -----------------
+ * ullava_mask_iou_counts: intersectionAndUnionGPU (evaluation/tools.py:29-41) with K = 2, for n masks of hw pixels
+ * in one launch.  pred_kind: 0 = fp32 mask logits (label = logit > 0, the callers' threshold, eval_ullava.py:65),
+ * 1 = int32 labels, 2 = uint8 labels; target_kind: 1 = int32, 2 = uint8; pixels whose target == ignore_index are
+ * dropped.  counts [n, 6] int32 = area_intersection[0..1], area_union[0..1], area_target[0..1] (exact integers). */
+ULLAVA_API int ullava_mask_iou_counts(ullava_ctx* ctx, const void* pred, int32_t pred_kind, const void* target, int32_t target_kind,
+                           int32_t n, int64_t hw, int32_t ignore_index, int32_t* counts, void* stream);
+/* The meter arithmetic of validate() (evaluation/eval_ullava.py:66-86) for a batch of images: image i owns the
+ * masks offsets[i] .. offsets[i+1]-1 of `counts`.  state: 8 doubles on the device = intersection sum[2], union
+ * sum[2], acc_iou sum[2], images, masks (ciou = state[1] / (state[3] + 1e-10), giou = state[5] / state[7]). */
+ULLAVA_API int ullava_seg_meter_update(ullava_ctx* ctx, const int32_t* counts, const int32_t* offsets, int32_t n_images,
+                            double* state, void* stream);
+/* bbox_iou (evaluation/tools.py:13-26): iou[i] = torchvision box_iou(pred[i] * 1000, gt[i] * 1000), xyxy, dtype
+ * ULLAVA_BF16 / ULLAVA_F16 / 2 (fp32) with torchvision's rounding points.  meter (optional, 3 doubles on the device:
+ * hits, boxes, scratch): hits += #{iou > 0.5}, boxes += n. */
+ULLAVA_API int ullava_box_iou_diag(ullava_ctx* ctx, const void* pred, const void* gt, int32_t n, int32_t dtype, float* iou,
+                        double* meter, void* stream);
+
+/* ---- image preprocessing on the device (dataset/processors/clip_processor.py, dataset/tools/mask_toolbox.py) ---
+ * ullava_resize_u8: PIL.Image.resize of an RGB uint8 HWC image, bit-exact with Pillow's 8-bit resampler (separable,
+ * antialiased, 22-bit fixed-point taps); filter 0 = BILINEAR (ResizeLongestSide.apply_image,
+ * models/segment_anything/utils/transforms.py:29-37), 1 = BICUBIC (CLIPImageProcessor.resize). */
+ULLAVA_API size_t ullava_resize_u8_scratch_bytes(int32_t h, int32_t w, int32_t out_h, int32_t out_w);
+ULLAVA_API int ullava_resize_u8(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, uint8_t* dst, int32_t out_h, int32_t out_w,
+                     int32_t filter, void* scratch, size_t scratch_bytes, void* stream);
+/* CLIPImageProcessor.preprocess after the resize: center crop (top, left, size) -> x * rescale (double product
+ * rounded to fp32) -> (x - mean[c]) / std[c] in fp32 -> 16-bit [3, size, size].  mean / std: host float[3]. */
+ULLAVA_API int ullava_clip_preprocess(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, int32_t top, int32_t left,
+                           int32_t size, const float* mean, const float* std, double rescale, void* out, int32_t dtype,
+                           void* stream);
+/* SegToolBox.preprocess (dataset/tools/mask_toolbox.py:15-25): (x - mean) / std in fp32, zero padding to
+ * [3, sam_size, sam_size], 16-bit. */
+ULLAVA_API int ullava_sam_preprocess(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, int32_t sam_size, const float* mean,
+                          const float* std, void* out, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,225 @@
+"""GPU parity of the kernels on either side of the hot path, through the C ABI and
+the host mirrors of the reference modules, against oracle/callers_oracle.py and the fixtures the REAL reference wrote
+(tests/golden/callers_*.npz).  Integer / byte work and the exactly-rounded fp32 elementwise chains are compared
+bit for bit; the sampling kernel is compared on the filtered distribution (1e-5) and on its inverse-CDF draw."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import native
+from oracle import callers_oracle as O
+from tests.util_models import build_tiny_core, load_golden, oracle_inputs_core
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f2: evaluation metrics
+# ---------------------------------------------------------------------------------------------------------------
+def test_mask_iou_counts_match_reference_fixture(ctx):
+    z, meta = load_golden("callers_metrics")
+    for i in range(meta["n_images"]):
+        logits = torch.from_numpy(z[f"logits_{i}"]).cuda()
+        gt = torch.from_numpy(z[f"gt_{i}"]).cuda()
+        ref = torch.from_numpy(z[f"counts_{i}"].astype(np.int32))
+        assert torch.equal(ctx.mask_iou_counts(logits, gt).cpu(), ref)                       # fp32 logits, uint8 gt
+        labels = (logits > 0).to(torch.int32)
+        assert torch.equal(ctx.mask_iou_counts(labels, gt.to(torch.int32)).cpu(), ref)       # int32 / int32
+        assert torch.equal(ctx.mask_iou_counts(labels.to(torch.uint8), gt).cpu(), ref)       # uint8 / uint8
+
+
+@pytest.mark.parametrize("n,h,w", [(5, 336, 336), (1, 480, 640), (3, 37, 41), (10, 1, 1)])
+def test_mask_iou_counts_vs_oracle(ctx, n, h, w):
+    g = torch.Generator().manual_seed(n * 100 + h)
+    logits = torch.randn((n, h, w), generator=g)
+    gt = (torch.rand((n, h, w), generator=g) > 0.5).to(torch.uint8)
+    gt[torch.rand((n, h, w), generator=g) > 0.93] = 255
+    gt[0][torch.rand((h, w), generator=g) > 0.97] = 7          # a label outside {0, 1, ignore}: histc drops it
+    got = ctx.mask_iou_counts(logits.cuda(), gt.cuda()).cpu().numpy()
+    for m in range(n):
+        a_i, a_u, a_t = O.intersection_and_union((logits[m] > 0).numpy().astype(np.int32), gt[m].numpy(), 2, 255)
+        assert np.array_equal(got[m], np.concatenate([a_i, a_u, a_t]))
+
+
+def test_seg_meter_reproduces_reference_validate(ctx):
+    """The device meters over the reference's synthetic dataset give validate()'s ciou / giou / prec@0.5 exactly,
+    whatever the batching of the updates."""
+    from evaluation.tools import SegMeter, intersectionAndUnionGPU, bbox_iou
+    z, meta = load_golden("callers_metrics")
+    n = meta["n_images"]
+    items = [dict(p=torch.from_numpy(z[f"logits_{i}"]).cuda(), g=torch.from_numpy(z[f"gt_{i}"]).cuda(),
+                  pb=torch.from_numpy(z[f"pred_boxes_{i}"]).cuda(), gb=torch.from_numpy(z[f"gt_boxes_{i}"]).cuda())
+             for i in range(n)]
+    for chunks in ([[0], [1], [2], [3], [4]], [[0, 1, 2, 3, 4]], [[0, 1], [2, 3, 4]]):
+        meter = SegMeter(0)
+        for ch in chunks:
+            meter.update([items[i]["p"] for i in ch], [items[i]["g"] for i in ch], [items[i]["pb"] for i in ch],
+                         [items[i]["gb"] for i in ch])
+        r = meter.result()
+        assert r["ciou"] == meta["ciou"] and r["giou"] == meta["giou"] and r["prec05"] == meta["prec05"], (r, meta)
+        assert r["images"] == n
+    # the drop-in functions of evaluation/tools.py
+    a_i, a_u, a_t = intersectionAndUnionGPU((items[0]["p"][0] > 0).int(), items[0]["g"][0].int(), 2, ignore_index=255)
+    assert torch.equal(torch.cat([a_i, a_u, a_t]).cpu(), torch.from_numpy(z["counts_0"][0].astype(np.int32)))
+    r = bbox_iou(items[0]["pb"][:1], items[0]["gb"][:1])
+    assert r["miou"] == z["box_iou_0"][0] and r["num"] == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_box_iou_diag_bit_exact(ctx, dtype):
+    g = torch.Generator().manual_seed(5)
+    p = torch.rand((333, 4), generator=g)
+    p[:, 2:] = p[:, :2] + torch.rand((333, 2), generator=g) * 0.5
+    q = p + torch.randn((333, 4), generator=g) * 0.05
+    q[7] = p[7] + 2.0                                   # disjoint boxes: iou 0
+    p, q = p.to(dtype), q.to(dtype)
+    ref = O.box_iou_diag(p, q).float()
+    meter = torch.zeros(3, dtype=torch.float64, device="cuda")
+    got = ctx.box_iou_diag(p.cuda(), q.cuda(), meter=meter).cpu()
+    assert torch.equal(got.nan_to_num(-1), ref.nan_to_num(-1))
+    assert meter[:2].tolist() == [float((ref > 0.5).sum()), 333.0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f3: preprocessing
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w,oh,ow", [(480, 640, 768, 1024), (500, 333, 1024, 682), (640, 480, 448, 336),
+                                       (1080, 1920, 336, 597), (97, 53, 31, 200), (300, 300, 300, 150),
+                                       (64, 48, 64, 48), (1, 7, 5, 3)])
+@pytest.mark.parametrize("bicubic", [False, True])
+def test_resize_u8_is_pillow_exact(ctx, h, w, oh, ow, bicubic):
+    from PIL import Image
+    img = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.array(Image.fromarray(img).resize((ow, oh), Image.BICUBIC if bicubic else Image.BILINEAR))
+    got = ctx.resize_u8(torch.from_numpy(img).cuda(), oh, ow, bicubic).cpu().numpy()
+    assert np.array_equal(got, ref), f"max diff {np.abs(got.astype(int) - ref.astype(int)).max()}"
+    if h * w < 400 * 400:
+        assert np.array_equal(got, O.pil_resize(img, oh, ow, bicubic))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_seg_toolbox_matches_reference_fixture(ctx, dtype):
+    from dataset.tools.mask_toolbox import SegToolBox
+    z, meta = load_golden("callers_preprocess")
+    tool = SegToolBox(dtype=dtype)
+    for i, case in enumerate(meta["cases"]):
+        img = z[f"img_{i}"]
+        resized = tool.apply_image(img)
+        assert hashlib.sha256(resized.cpu().numpy().tobytes()).hexdigest() == case["resized_sha256"]
+        x, resize = tool(img)
+        assert list(resize) == case["resized"] and list(x.shape) == case["sam_shape"]
+        ref32 = O.sam_preprocess(O.sam_apply_image(img))
+        assert hashlib.sha256(np.ascontiguousarray(ref32).tobytes()).hexdigest() == case["sam_sha256"]
+        assert torch.equal(x.cpu(), torch.from_numpy(ref32).to(dtype))   # the reference casts the fp32 tensor (tools.py:55-67)
+        # the reference's calling convention: CHW uint8 tensor in
+        x2 = tool.preprocess(resized.permute(2, 0, 1))
+        assert torch.equal(x2, x)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("h,w,pad", [(480, 640, False), (640, 480, True), (336, 336, False), (500, 333, True),
+                                     (97, 53, False)])
+def test_clip_processor_matches_oracle(ctx, dtype, h, w, pad):
+    from dataset.processors.clip_processor import CLIPProcessor
+    img = np.random.default_rng(h + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    proc = CLIPProcessor(aspect_ratio="pad" if pad else None, size=336, dtype=dtype)
+    got = proc(img)
+    ref = torch.from_numpy(O.clip_preprocess(img, 336, pad=pad)).to(dtype)
+    assert got.shape == (3, 336, 336) and torch.equal(got.cpu(), ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f4: sampling
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V", [32011, 997, 64])
+@pytest.mark.parametrize("temperature,top_p", [(0.2, None), (0.2, 0.7), (1.0, 0.9), (0.7, 0.3), (1.5, 1.0)])
+def test_sample_step_distribution_and_draw(ctx, V, temperature, top_p):
+    B = 6
+    g = torch.Generator().manual_seed(V + int(temperature * 10))
+    logits = torch.randn((B, V), generator=g) * 3
+    u = torch.rand((1, B), generator=g)
+    u[0, 0], u[0, 1] = 0.0, 0.9999999
+    probs = torch.empty((B, V), dtype=torch.float32, device="cuda")
+    ids = torch.empty((B,), dtype=torch.int64, device="cuda")
+    ctx.sample_step(logits.cuda(), temperature, top_p, u.cuda(), ids, probs_out=probs)
+    probs, ids = probs.cpu().double().numpy(), ids.cpu().numpy()
+    for b in range(B):
+        ref = O.filtered_distribution(logits[b].numpy(), temperature, top_p)
+        # kept set: identical except for tokens whose ascending cumulative mass sits within rounding of the cut
+        diff = np.nonzero((probs[b] > 0) != (ref > 0))[0]
+        diff = np.array([t for t in diff if ref[t] > 1e-30], dtype=np.int64)   # fp32 exp underflows to 0, fp64 does not
+        if len(diff):
+            full = O.filtered_distribution(logits[b].numpy(), temperature, None)
+            order = np.argsort(full, kind="stable")
+            cum = np.cumsum(full[order])
+            pos = {int(t): k for k, t in enumerate(order)}
+            assert all(abs(cum[pos[int(t)]] - (1 - top_p)) < 1e-5 for t in diff), diff
+        else:
+            assert np.abs(probs[b] - ref).max() < 1e-5
+        assert abs(probs[b].sum() - 1) < 1e-4
+        # the draw: inverse CDF of the kernel's own distribution, in vocabulary order
+        cdf = np.cumsum(probs[b])
+        i, t = int(ids[b]), float(u[0, b]) * cdf[-1]
+        assert probs[b][i] > 0 and cdf[i] - probs[b][i] <= t + 1e-5 and t <= cdf[i] + 1e-5, (i, t, cdf[i], probs[b][i])
+        if not len(diff):
+            j = O.sample_inverse_cdf(logits[b].numpy(), temperature, top_p, float(u[0, b]))
+            if j != i:   # only when u * Z falls within fp32 rounding of a CDF step
+                assert abs(i - j) <= max(2, V // 1000) or min(abs(t - cdf[i]), abs(t - (cdf[i] - probs[b][i]))) < 1e-5
+
+
+def test_sample_step_statistics_and_bookkeeping(ctx):
+    """20 000 draws of one small distribution follow it (5 sigma per bin); eos / pad / sequence bookkeeping as in
+    ullava_greedy_step."""
+    V, N = 50, 20000
+    g = torch.Generator().manual_seed(3)
+    logits = (torch.randn((1, V), generator=g) * 2).expand(N, V).contiguous()
+    u = torch.rand((1, N), generator=g)
+    ids = torch.empty((N,), dtype=torch.int64, device="cuda")
+    ctx.sample_step(logits.cuda(), 0.8, 0.9, u.cuda(), ids)
+    p = O.filtered_distribution(logits[0].numpy(), 0.8, 0.9)
+    freq = np.bincount(ids.cpu().numpy(), minlength=V) / N
+    assert np.all(np.abs(freq - p) <= 5 * np.sqrt(p * (1 - p) / N) + 1e-9)
+    assert np.all(freq[p == 0] == 0)
+    # bookkeeping: row 1 already finished -> pad; a row drawing eos becomes finished; seqs[:, pos + 1], ++pos
+    B, H = 3, 16
+    lg = torch.full((B, V), -30.0)
+    lg[0, 5] = lg[1, 6] = lg[2, 7] = 30.0
+    pos = torch.tensor([4], dtype=torch.int32, device="cuda")
+    uni = torch.full((8, B), 0.5, device="cuda")
+    cur = torch.zeros((B,), dtype=torch.int64, device="cuda")
+    seqs = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+    fin = torch.tensor([0, 1, 0], dtype=torch.uint8, device="cuda")
+    final_h = torch.randn((B, H), device="cuda").to(torch.bfloat16)
+    hid = torch.zeros((B, 7, H), dtype=torch.bfloat16, device="cuda")
+    ctx.sample_step(lg.cuda(), 1.0, None, uni, cur, seqs, final_h, hid, fin, eos_id=7, pad_id=99, pos_dev=pos)
+    assert cur.tolist() == [5, 99, 7] and seqs[:, 5].tolist() == [5, 99, 7] and fin.tolist() == [0, 1, 1]
+    assert int(pos) == 5 and torch.equal(hid[:, 4], final_h)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_generate_sampling_on_device(ctx, dtype):
+    """do_sample generate: reproducible under a seeded generator, equal to greedy when the temperature is tiny, and
+    the graph-replayed session agrees with the per-step host loop (stopping_criteria path) given the same uniforms."""
+    model, sd, cfg = build_tiny_core(dtype)
+    ids, images = oracle_inputs_core(2)
+    ids, images = ids.cuda(), images.cuda().to(dtype)
+    greedy = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=False)
+    cold = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1e-4,
+                          generator=torch.Generator("cuda").manual_seed(1))
+    assert torch.equal(greedy, cold)
+    a = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1.0, top_p=0.9,
+                       generator=torch.Generator("cuda").manual_seed(7))
+    b = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1.0, top_p=0.9,
+                       generator=torch.Generator("cuda").manual_seed(7))
+    c = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1.0, top_p=0.9,
+                       generator=torch.Generator("cuda").manual_seed(8))
+    assert torch.equal(a, b) and a.shape == (2, ids.shape[1] + 8)
+    assert torch.equal(a[:, :ids.shape[1]], ids) and int(a.max()) < model.config.vocab_size
+    assert not torch.equal(a, c)
+    # evaluate()'s default (temperature = 0.2) also runs on the device path
+    out = model.generate(input_ids=ids, images=images, max_new_tokens=4, do_sample=True, temperature=0.2,
+                         output_hidden_states=True, return_dict_in_generate=True)
+    assert out.sequences.shape == (2, ids.shape[1] + 4) and out.hidden_states[-1][-1].shape[1] == ids.shape[1] + 3

@@ -184,6 +184,62 @@ int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t
                          eos_id, pad_id, pos_dev, static_cast<cudaStream_t>(stream));
 }
 
+int ullava_sample_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, float temperature,
+                       float top_p, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
+                       int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
+                       uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, float* probs_out,
+                       void* stream) {
+  CTX_CHECK("ullava_sample_step");
+  return sample_step_run(ctx, logits, ld, rows, cols, temperature, top_p, uniforms, uniforms_ld, cur_ids, seqs, seqs_ld,
+                         final_h, hid_buf, hid_bs, hdim, finished, eos_id, pad_id, pos_dev, probs_out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int ullava_mask_iou_counts(ullava_ctx* ctx, const void* pred, int32_t pred_kind, const void* target, int32_t target_kind,
+                           int32_t n, int64_t hw, int32_t ignore_index, int32_t* counts, void* stream) {
+  CTX_CHECK("ullava_mask_iou_counts");
+  return mask_iou_counts_run(ctx, pred, pred_kind, target, target_kind, n, hw, ignore_index, counts,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int ullava_seg_meter_update(ullava_ctx* ctx, const int32_t* counts, const int32_t* offsets, int32_t n_images,
+                            double* state, void* stream) {
+  CTX_CHECK("ullava_seg_meter_update");
+  return seg_meter_update_run(ctx, counts, offsets, n_images, state, static_cast<cudaStream_t>(stream));
+}
+
+int ullava_box_iou_diag(ullava_ctx* ctx, const void* pred, const void* gt, int32_t n, int32_t dtype, float* iou,
+                        double* meter, void* stream) {
+  CTX_CHECK("ullava_box_iou_diag");
+  return box_iou_diag_run(ctx, pred, gt, n, dtype, iou, meter, static_cast<cudaStream_t>(stream));
+}
+
+size_t ullava_resize_u8_scratch_bytes(int32_t h, int32_t w, int32_t out_h, int32_t out_w) {
+  if (h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0) return 0;
+  return resize_u8_scratch(h, w, out_h, out_w);
+}
+
+int ullava_resize_u8(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, uint8_t* dst, int32_t out_h, int32_t out_w,
+                     int32_t filter, void* scratch, size_t scratch_bytes, void* stream) {
+  CTX_CHECK("ullava_resize_u8");
+  return resize_u8_run(ctx, src, h, w, dst, out_h, out_w, filter, scratch, scratch_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int ullava_clip_preprocess(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, int32_t top, int32_t left,
+                           int32_t size, const float* mean, const float* std, double rescale, void* out, int32_t dtype,
+                           void* stream) {
+  CTX_CHECK("ullava_clip_preprocess");
+  return clip_preprocess_run(ctx, src, h, w, top, left, size, mean, std, rescale, out, dtype,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int ullava_sam_preprocess(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, int32_t sam_size, const float* mean,
+                          const float* std, void* out, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_sam_preprocess");
+  return sam_preprocess_run(ctx, src, h, w, sam_size, mean, std, out, dtype, static_cast<cudaStream_t>(stream));
+}
+
 size_t ullava_llama_scratch_bytes(int32_t rows, int32_t hidden_size, int32_t ffn) {
   return llama_scratch(rows, hidden_size, ffn);
 }

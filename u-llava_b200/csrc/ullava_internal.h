@@ -112,6 +112,29 @@ int copy_rows_run(Context* ctx, const void* src, int64_t sbs, int64_t srs, void*
                   int batch, int rows, int cols, int dtype, cudaStream_t stream);
 int argmax_run(Context* ctx, const float* logits, int64_t ld, int64_t* out, int rows, int cols, cudaStream_t stream);
 
+// sampling.cu -- temperature / top-p step (inverse CDF over the filtered distribution, one uniform per row)
+int sample_step_run(Context* ctx, const float* logits, int64_t ld, int rows, int cols, float temperature, float top_p,
+                    const float* uniforms, int64_t uni_ld, int64_t* cur_ids, int64_t* seqs, int64_t seqs_ld,
+                    const void* final_h, void* hid_buf, int64_t hid_bs, int hdim, uint8_t* finished, int eos_id,
+                    int pad_id, int32_t* pos_dev, float* probs_out, cudaStream_t stream);
+
+// eval_ops.cu -- metrics of evaluation/eval_ullava.py:validate on the device
+int mask_iou_counts_run(Context* ctx, const void* pred, int pred_kind, const void* target, int target_kind, int n,
+                        int64_t hw, int ignore, int32_t* counts, cudaStream_t s);
+int seg_meter_update_run(Context* ctx, const int32_t* counts, const int32_t* offsets, int n_images, double* state,
+                         cudaStream_t s);
+int box_iou_diag_run(Context* ctx, const void* pred, const void* gt, int n, int dtype, float* iou, double* meter,
+                     cudaStream_t s);
+
+// preprocess.cu -- Pillow-exact uint8 resize, CLIP / SAM normalisation
+size_t resize_u8_scratch(int h, int w, int oh, int ow);
+int resize_u8_run(Context* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int filter,
+                  void* scratch, size_t scratch_bytes, cudaStream_t s);
+int clip_preprocess_run(Context* ctx, const uint8_t* src, int h, int w, int top, int left, int size,
+                        const float* mean, const float* stdv, double rescale, void* out, int dtype, cudaStream_t s);
+int sam_preprocess_run(Context* ctx, const uint8_t* src, int h, int w, int S, const float* mean, const float* stdv,
+                       void* out, int dtype, cudaStream_t s);
+
 // sam_decoder.cu
 int sam_mask_decoder_run(Context* ctx, const ullava_sam_decoder_args& a, cudaStream_t stream);
 size_t sam_mask_decoder_scratch(int n);

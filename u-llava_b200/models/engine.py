@@ -239,6 +239,8 @@ class DecodeSession:
         self.graph = None
         self.graph_nodes = 0
         self.eos_id, self.pad_id = -1, 0
+        self.sampling = None      # None = greedy, else (temperature, top_p)
+        self.uniforms = None      # [max_seq, batch] fp32: the draw of row b at position pos (ullava_sample_step)
         self.args = None
 
     def _build_args(self):
@@ -254,14 +256,24 @@ class DecodeSession:
         a.hid_buf = self.hid_buf.data_ptr() if self.hid_buf is not None else None
         a.hid_bs = self.hid_buf.stride(0) if self.hid_buf is not None else 0
         a.finished, a.eos_id, a.pad_id = self.finished.data_ptr(), self.eos_id, self.pad_id
+        if self.sampling is not None:
+            a.uniforms, a.uniforms_ld = self.uniforms.data_ptr(), self.uniforms.stride(0)
+            a.temperature, a.top_p = float(self.sampling[0]), float(self.sampling[1])
         self.args = a
 
-    def begin(self, input_ids: torch.Tensor, eos_id, pad_id: int):
+    def begin(self, input_ids: torch.Tensor, eos_id, pad_id: int, sampling=None, generator=None):
+        """sampling: None (greedy) or (temperature, top_p); the uniforms of every position are drawn here, once per
+        generate() call, from `generator` (torch's default CUDA generator when None)."""
         eos = -1 if eos_id is None else int(eos_id)
-        if self.args is None or eos != self.eos_id or int(pad_id) != self.pad_id:
-            self.eos_id, self.pad_id = eos, int(pad_id)
+        if sampling is not None:
+            sampling = (float(sampling[0]), float(sampling[1]) if sampling[1] is not None else 1.0)
+            if self.uniforms is None:
+                self.uniforms = torch.empty((self.max_seq, self.batch), dtype=torch.float32, device=self.stack.device)
+            self.uniforms.uniform_(0.0, 1.0, generator=generator)
+        if self.args is None or eos != self.eos_id or int(pad_id) != self.pad_id or sampling != self.sampling:
+            self.eos_id, self.pad_id, self.sampling = eos, int(pad_id), sampling
             self._build_args()
-            self.graph = None  # eos / pad ids are baked into the captured kernel arguments
+            self.graph = None  # eos / pad ids and the sampling parameters are baked into the captured kernel arguments
         P = input_ids.shape[1]
         self.cache.length = 0
         self.finished.zero_()
@@ -272,8 +284,12 @@ class DecodeSession:
         """Greedy token after the prefill: lm_head on the last prompt position + the step bookkeeping at pos = P-1."""
         self.ctx.gemm(last_final, self.lm_head, out=self.logits)
         self.pos.fill_(prompt_len - 1)
-        self.ctx.greedy_step(self.logits, self.cur_ids, self.seqs, last_final, self.hid_buf, self.finished, self.eos_id,
-                             self.pad_id, self.pos)
+        if self.sampling is not None:
+            self.ctx.sample_step(self.logits, self.sampling[0], self.sampling[1], self.uniforms, self.cur_ids, self.seqs,
+                                 last_final, self.hid_buf, self.finished, self.eos_id, self.pad_id, self.pos)
+        else:
+            self.ctx.greedy_step(self.logits, self.cur_ids, self.seqs, last_final, self.hid_buf, self.finished,
+                                 self.eos_id, self.pad_id, self.pos)
 
     def steps(self, n: int, use_graph: bool = True) -> int:
         """Runs n decode steps; returns the number of native kernels launched through graph REPLAYS (eager

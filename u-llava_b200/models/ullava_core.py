@@ -297,7 +297,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
     def generate(self, input_ids=None, images=None, videos=None, max_new_tokens=32, num_beams=1, top_p=None,
                  do_sample=False, temperature=1.0, output_hidden_states=False, return_dict_in_generate=False,
                  no_repeat_ngram_size=None, stopping_criteria=None, eos_token_id=None, pad_token_id=None,
-                 attention_mask=None, use_cache=True, **kwargs):
+                 attention_mask=None, use_cache=True, generator=None, **kwargs):
         """Greedy / sampling generation with a KV cache (replaces HF GenerationMixin.generate for the
         path used by UllavaForCausalLM.evaluate, models/ullava.py:349-365, and inference_ullava_core.py:73-80).
 
@@ -324,9 +324,11 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         H = self.config.hidden_size
         T = P + max_new_tokens
         greedy = not (do_sample and temperature and temperature > 0)
-        if greedy and stopping_criteria is None and max_new_tokens >= 1:
+        sampling = None if greedy else (float(temperature), top_p)
+        if stopping_criteria is None and max_new_tokens >= 1:
             return self._generate_greedy_device(ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id,
-                                                pad_token_id, output_hidden_states, return_dict_in_generate)
+                                                pad_token_id, output_hidden_states, return_dict_in_generate,
+                                                sampling=sampling, generator=generator)
         cache = stack.new_cache(B, T)
         table = self.model.embed_tokens.weight.detach()
         w = self.lm_head.weight.detach()
@@ -350,8 +352,11 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         n_done = T
         for t in range(max_new_tokens):
             ctx.gemm(last, w, out=logits)
-            if do_sample and temperature and temperature > 0:
-                nxt = _sample(logits, temperature, top_p)
+            if sampling is not None:
+                # one uniform number per row, inverse-CDF draw on the device (ullava_sample_step)
+                u = torch.rand((1, B), dtype=torch.float32, device=logits.device, generator=generator)
+                nxt = torch.empty((B,), dtype=torch.int64, device=logits.device)
+                ctx.sample_step(logits, sampling[0], sampling[1], u, nxt)
             else:
                 nxt = ctx.argmax(logits)
             if eos_token_id is not None:
@@ -381,8 +386,9 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=cache)
 
     def _generate_greedy_device(self, ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id, pad_token_id,
-                                output_hidden_states, return_dict_in_generate):
-        """Greedy loop with all per-step state on the device: prefill, then max_new_tokens-1 replays of ONE
+                                output_hidden_states, return_dict_in_generate, sampling=None, generator=None):
+        """Greedy (or, with `sampling` = (temperature, top_p), sampling) loop with all per-step state on the device:
+        prefill, then max_new_tokens-1 replays of ONE
         captured decode-step graph (the position is read from device memory).  The host only synchronises to
         test for EOS (every 8 steps, and only when an eos id is set)."""
         B, P = input_ids.shape
@@ -391,7 +397,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         table = self.model.embed_tokens.weight.detach()
         w = self.lm_head.weight.detach()
         sess = stack.decode_session(ctx, B, T, table, w, bool(output_hidden_states))
-        sess.begin(input_ids, eos_token_id, pad_token_id)
+        sess.begin(input_ids, eos_token_id, pad_token_id, sampling=sampling, generator=generator)
         _, embeds = self.embed_images_videos(input_ids, images, videos)
         self._mark("vit_projector_splice")
         final, _ = stack.run(ctx, embeds.view(B * P, H), sess.cache, B, P)
@@ -443,19 +449,6 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
                              "use_cache": kwargs.get("use_cache"), "attention_mask": attention_mask,
                              "images": images, "videos": videos})
         return model_inputs
-
-
-def _sample(logits: torch.Tensor, temperature: float, top_p: Optional[float]) -> torch.Tensor:
-    """Temperature / nucleus sampling on the device (HF TemperatureLogitsWarper + TopPLogitsWarper order).
-    Host-side glue on [B, V] fp32 logits; the default parity path is greedy (temperature=0)."""
-    scores = logits / temperature
-    if top_p is not None and top_p < 1.0:
-        sorted_logits, sorted_idx = torch.sort(scores, descending=False)
-        cum = sorted_logits.softmax(-1).cumsum(-1)
-        remove = cum <= (1 - top_p)
-        remove[..., -1:] = False
-        scores = scores.masked_fill(remove.scatter(1, sorted_idx, remove), float("-inf"))
-    return torch.multinomial(scores.softmax(-1), 1).squeeze(1)
 
 
 AutoConfig.register("ullava_core", UllavaCoreConfig)

@@ -77,7 +77,8 @@ class LlamaArgs(C.Structure):
 class DecodeArgs(C.Structure):
     _fields_ = [("llama", LlamaArgs), ("pos_dev", _vp), ("embed_table", _vp), ("vocab", _i32), ("lm_head", _vp),
                 ("cur_ids", _vp), ("logits", _vp), ("seqs", _vp), ("seqs_ld", _i64), ("hid_buf", _vp),
-                ("hid_bs", _i64), ("finished", _vp), ("eos_id", _i32), ("pad_id", _i32)]
+                ("hid_bs", _i64), ("finished", _vp), ("eos_id", _i32), ("pad_id", _i32),
+                ("uniforms", _vp), ("uniforms_ld", _i64), ("temperature", _f32), ("top_p", _f32)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/ullava_sm100.h
@@ -122,6 +123,16 @@ _SIGNATURES = {
     "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
     "ullava_greedy_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
                                   _vp, _vp]),
+    "ullava_sample_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64,
+                                  _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "ullava_mask_iou_counts": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp]),
+    "ullava_seg_meter_update": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "ullava_box_iou_diag": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "ullava_resize_u8_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "ullava_resize_u8": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "ullava_clip_preprocess": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32),
+                                      C.c_double, _vp, _i32, _vp]),
+    "ullava_sam_preprocess": (_i32, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _i32, _vp]),
 }
 
 _lib = None
@@ -489,6 +500,84 @@ class Context:
             seqs.stride(0) if seqs is not None else 0, _ptr(final_h), _ptr(hid_buf),
             hid_buf.stride(0) if hid_buf is not None else 0, final_h.shape[-1] if final_h is not None else 8,
             _ptr(finished), int(eos_id), int(pad_id), pos_dev.data_ptr(), _stream()))
+
+    def sample_step(self, logits, temperature, top_p, uniforms, cur_ids, seqs=None, final_h=None, hid_buf=None,
+                    finished=None, eos_id=-1, pad_id=0, pos_dev=None, probs_out=None):
+        """Temperature / top-p draw per row by inverse CDF with the caller's uniforms[pos, b]; bookkeeping as
+        greedy_step.  probs_out (optional [rows, cols] fp32) receives the filtered, renormalised distribution."""
+        rows, cols = logits.shape
+        assert uniforms.dtype == torch.float32 and uniforms.dim() == 2 and uniforms.stride(1) == 1
+        self._chk(self.lib.ullava_sample_step(
+            self.handle, logits.data_ptr(), logits.stride(0), rows, cols, float(temperature),
+            float(top_p if top_p is not None else 1.0), uniforms.data_ptr(), uniforms.stride(0), cur_ids.data_ptr(),
+            _ptr(seqs), seqs.stride(0) if seqs is not None else 0, _ptr(final_h), _ptr(hid_buf),
+            hid_buf.stride(0) if hid_buf is not None else 0, final_h.shape[-1] if final_h is not None else 8,
+            _ptr(finished), int(eos_id), int(pad_id), _ptr(pos_dev), _ptr(probs_out), _stream()))
+
+    # ---- evaluation metrics (evaluation/tools.py, evaluation/eval_ullava.py) -------------------
+    _KIND = {torch.float32: 0, torch.int32: 1, torch.uint8: 2}
+
+    def mask_iou_counts(self, pred: torch.Tensor, target: torch.Tensor, ignore_index: int = 255, out=None):
+        """pred [n, ...] fp32 logits (label = logit > 0) or int32 / uint8 labels; target [n, ...] int32 / uint8.
+        Returns int32 [n, 6] = area_intersection[0:2], area_union[0:2], area_target[0:2] (K = 2)."""
+        assert pred.shape == target.shape and pred.is_contiguous() and target.is_contiguous()
+        assert target.dtype in (torch.int32, torch.uint8), target.dtype
+        n = pred.shape[0]
+        hw = pred[0].numel() if n else 1
+        if out is None:
+            out = torch.empty((n, 6), dtype=torch.int32, device=pred.device)
+        self._chk(self.lib.ullava_mask_iou_counts(self.handle, pred.data_ptr(), self._KIND[pred.dtype],
+                                                  target.data_ptr(), self._KIND[target.dtype], n, hw,
+                                                  int(ignore_index), out.data_ptr(), _stream()))
+        return out
+
+    def seg_meter_update(self, counts: torch.Tensor, offsets: torch.Tensor, state: torch.Tensor):
+        """state (8 fp64 on the device) += validate()'s per-image sums; offsets int32 [n_images + 1]."""
+        assert counts.dtype == torch.int32 and offsets.dtype == torch.int32 and state.dtype == torch.float64
+        assert state.numel() >= 8
+        self._chk(self.lib.ullava_seg_meter_update(self.handle, counts.data_ptr(), offsets.data_ptr(),
+                                                   offsets.numel() - 1, state.data_ptr(), _stream()))
+
+    def box_iou_diag(self, pred: torch.Tensor, gt: torch.Tensor, meter: Optional[torch.Tensor] = None):
+        """iou[i] = torchvision box_iou(pred[i] * 1000, gt[i] * 1000) (xyxy); meter (3 fp64): hits(>0.5), boxes."""
+        assert pred.shape == gt.shape and pred.shape[-1] == 4 and pred.dtype == gt.dtype
+        pred, gt = pred.contiguous(), gt.contiguous()
+        n = pred.numel() // 4
+        dt = F32 if pred.dtype == torch.float32 else dtype_code(pred.dtype)
+        iou = torch.empty((n,), dtype=torch.float32, device=pred.device)
+        self._chk(self.lib.ullava_box_iou_diag(self.handle, pred.data_ptr(), gt.data_ptr(), n, dt, iou.data_ptr(),
+                                               _ptr(meter), _stream()))
+        return iou
+
+    # ---- image preprocessing (dataset/processors/clip_processor.py, dataset/tools/mask_toolbox.py) -----------
+    def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, bicubic: bool) -> torch.Tensor:
+        """PIL.Image.resize of a uint8 [H, W, 3] device image (BICUBIC or BILINEAR), bit-exact with Pillow."""
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
+        h, w = int(img.shape[0]), int(img.shape[1])
+        out = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device=img.device)
+        nbytes = int(self.lib.ullava_resize_u8_scratch_bytes(h, w, out_h, out_w))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=img.device)
+        self._chk(self.lib.ullava_resize_u8(self.handle, img.data_ptr(), h, w, out.data_ptr(), out_h, out_w,
+                                            1 if bicubic else 0, scratch.data_ptr(), nbytes, _stream()))
+        return out
+
+    def clip_preprocess(self, img: torch.Tensor, top: int, left: int, size: int, mean, std, dtype,
+                        rescale: float = 1 / 255) -> torch.Tensor:
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
+        out = torch.empty((3, size, size), dtype=dtype, device=img.device)
+        m, s = (_f32 * 3)(*[float(v) for v in mean]), (_f32 * 3)(*[float(v) for v in std])
+        self._chk(self.lib.ullava_clip_preprocess(self.handle, img.data_ptr(), img.shape[0], img.shape[1], top, left,
+                                                  size, m, s, float(rescale), out.data_ptr(), dtype_code(dtype),
+                                                  _stream()))
+        return out
+
+    def sam_preprocess(self, img: torch.Tensor, sam_size: int, mean, std, dtype) -> torch.Tensor:
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()
+        out = torch.empty((3, sam_size, sam_size), dtype=dtype, device=img.device)
+        m, s = (_f32 * 3)(*[float(v) for v in mean]), (_f32 * 3)(*[float(v) for v in std])
+        self._chk(self.lib.ullava_sam_preprocess(self.handle, img.data_ptr(), img.shape[0], img.shape[1], sam_size, m,
+                                                 s, out.data_ptr(), dtype_code(dtype), _stream()))
+        return out
 
     def fill_llama_args(self, a: "LlamaArgs", weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq,
                         pos0, cfg: dict, rope_cos, rope_sin, final_out=None, all_hidden=None):
