@@ -205,6 +205,10 @@ ULLAVA_API int ullava_splice_rows(ullava_ctx* ctx, void* embeds, const void* fea
 ULLAVA_API int ullava_copy_rows(ullava_ctx* ctx, const void* src, int64_t src_bs, int64_t src_rs, void* dst, int64_t dst_bs,
                      int64_t dst_rs, int32_t batch, int32_t rows, int32_t cols, int32_t dtype, void* stream);
 /* Greedy token: out[r] = argmax_c logits[r, c] over fp32 logits (first index on ties, like torch.argmax). */
+/* encode_video pooling (models/ullava_core.py:160-180): feats [batch, frames, patches, dim] 16-bit ->
+ * out [batch, frames + patches, dim]: temporal means (over patches) first, then spatial means (over frames). */
+ULLAVA_API int ullava_video_pool(ullava_ctx* ctx, const void* feats, void* out, int32_t batch, int32_t frames, int32_t patches,
+                      int32_t dim, int32_t dtype, void* stream);
 ULLAVA_API int ullava_argmax(ullava_ctx* ctx, const float* logits, int64_t ld, int64_t* out, int32_t rows, int32_t cols,
                   void* stream);
 

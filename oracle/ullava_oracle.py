@@ -99,20 +99,39 @@ def project(sd: SD, feats: torch.Tensor, cfg: dict, prefix: str = "") -> torch.T
     raise NotImplementedError
 
 
+def encode_video(sd: SD, videos: torch.Tensor, cfg: dict, prefix: str = "") -> torch.Tensor:
+    """UllavaCoreForCausalLM.encode_video (models/ullava_core.py:160-180): [bs, C, T, H, W] -> per-frame patch
+    features, temporal means (over patches) followed by spatial means (over frames): [bs, T + N, D]."""
+    bs, c, t, h, w = videos.shape
+    frames = videos.permute(0, 2, 1, 3, 4).reshape(bs * t, c, h, w)
+    f = encode_image(sd, frames, cfg, prefix)
+    f = f.view(bs, t, f.shape[1], f.shape[2])
+    return torch.cat([f.mean(dim=2), f.mean(dim=1)], dim=1)
+
+
 def embed_images(sd: SD, input_ids: torch.Tensor, images: Optional[torch.Tensor], cfg: dict,
-                 prefix: str = "") -> torch.Tensor:
-    """embed_images_videos, image branch (models/ullava_core.py:182-277): token embeddings with the
-    num_patch rows after <img_beg> overwritten by projected image features."""
+                 prefix: str = "", videos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """embed_images_videos (models/ullava_core.py:182-277): token embeddings with the rows after <img_beg> /
+    <vid_beg> overwritten by projected image / video features."""
     emb = sd[prefix + "model.embed_tokens.weight"][input_ids]
     ids = cfg["mm_token_ids"]
     feats = encode_image(sd, images, cfg, prefix) if images is not None else None
+    vfeats = encode_video(sd, videos, cfg, prefix) if videos is not None else None
     out = []
-    img_i = 0
+    img_i = vid_i = 0
     for b in range(input_ids.shape[0]):
         cur = emb[b]
         n_s = int((input_ids[b] == ids["IMG_START"]).sum())
         n_e = int((input_ids[b] == ids["IMG_END"]).sum())
-        assert n_s == n_e, "Number of image start and end tokens should be the same"
+        n_vs = int((input_ids[b] == ids["VID_START"]).sum())
+        n_ve = int((input_ids[b] == ids["VID_END"]).sum())
+        assert n_s == n_e and n_vs == n_ve, "Number of image start and end tokens should be the same"
+        if n_s == 0 and n_vs > 0:   # video branch (:248-269)
+            pos = int(torch.where(input_ids[b] == ids["VID_START"])[0][0])
+            f = project(sd, vfeats[vid_i], cfg, prefix)
+            out.append(torch.cat([cur[:pos + 1], f, cur[pos + f.shape[0] + 1:]], dim=0))
+            vid_i += 1
+            continue
         if n_s == 0:
             out.append(cur)  # text only: dummy projector term is exactly zero (:213-220)
             continue
@@ -195,13 +214,13 @@ def llama_layers(sd: SD, x: torch.Tensor, cfg: dict, prefix: str = "", past: Opt
 
 
 def core_forward(sd: SD, cfg: dict, input_ids: torch.Tensor, images: Optional[torch.Tensor] = None,
-                 past=None, prefix: str = "", collect_hidden: bool = False):
+                 past=None, prefix: str = "", collect_hidden: bool = False, videos: Optional[torch.Tensor] = None):
     """UllavaCoreForCausalLM.forward (models/ullava_core.py:279-355) without the loss.
     Returns dict(logits [B,S,V], last_hidden [B,S,H], past, hidden_states)."""
     if input_ids.shape[1] == 1 and past is not None:
         x = sd[prefix + "model.embed_tokens.weight"][input_ids]  # decode step: vision tower skipped (:188-189)
     else:
-        x = embed_images(sd, input_ids, images, cfg, prefix)
+        x = embed_images(sd, input_ids, images, cfg, prefix, videos)
     h, new_past, hs = llama_layers(sd, x, cfg, prefix, past, collect_hidden)
     logits = F.linear(h, sd[prefix + "lm_head.weight"])
     return {"logits": logits, "last_hidden": h, "past": new_past, "hidden_states": hs}

@@ -154,6 +154,37 @@ def preprocess():
     save("callers_preprocess", arrays, meta)
 
 
+def tiny_core_video():
+    """UllavaCoreForCausalLM.forward on a batch mixing a video row and an image row (reference
+    models/ullava_core.py:160-180,248-269), tiny config, seeded synthetic weights: logits + encode_video output."""
+    import models as ref_models
+    from oracle.synth import synth_normal, synth_state_dict, synth_ids
+    from tests import configs as C
+    with open(os.path.join(HERE, "tiny_core.json")) as f:
+        meta = json.load(f)
+    cfg = ref_models.UllavaCoreConfig(**C.TINY_LLM)
+    cfg._attn_implementation = "eager"
+    cfg.vision_config._attn_implementation = "eager"
+    m = ref_models.UllavaCoreForCausalLM(cfg).eval().float()
+    m.load_state_dict(synth_state_dict(meta["shapes"], meta["seed"]), strict=True)
+    T, N = 3, 4                      # frames, patches per 28 x 28 frame
+    videos = synth_normal("videos", (1, 3, T, 28, 28))
+    images = synth_normal("images", (1, 3, 28, 28))
+    ids_img = C.tiny_prompt(1)
+    L = ids_img.shape[1]
+    vid = [1] + synth_ids("vhead", (1, 2), 3, 300)[0].tolist() + [C.MM_IDS["VID_START"]] + \
+          [C.MM_IDS["VID_PATCH"]] * (T + N) + [C.MM_IDS["VID_END"]]
+    vid = vid + synth_ids("vtail", (1, L - len(vid)), 3, 300)[0].tolist()
+    ids = torch.cat([torch.tensor([vid], dtype=torch.int64), ids_img], 0)
+    with torch.no_grad():
+        out = m(input_ids=ids, images=images, videos=videos, return_dict=True)
+        vf = m.encode_video(videos)
+    save("tiny_core_video", {"ids": ids.numpy(), "logits": out.logits.numpy(), "video_features": vf.numpy()},
+         {"frames": T, "patches": N, "seed": meta["seed"],
+          "source": "models/ullava_core.py forward + encode_video, unmodified, transformers eager, fp32 CPU"})
+
+
 if __name__ == "__main__":
     metrics()
     preprocess()
+    tiny_core_video()

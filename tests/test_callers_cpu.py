@@ -111,6 +111,24 @@ def test_filtered_distribution_matches_hf_warpers(temperature, top_p):
             assert p[i] > 0 and cdf[i] > u * cdf[-1] - 1e-12 and (cdf[i] - p[i]) <= u * cdf[-1] + 1e-12
 
 
+def test_video_branch_of_the_oracle_matches_reference():
+    """encode_video + the video branch of embed_images_videos (models/ullava_core.py:160-180,248-269): logits of a
+    batch mixing a video row and an image row, as the real reference computed them."""
+    from oracle import ullava_oracle as U
+    from oracle.synth import synth_normal, synth_state_dict
+    from tests import configs as C
+    z, meta = _load("tiny_core_video")
+    _, core = _load("tiny_core")
+    sd = synth_state_dict(core["shapes"], meta["seed"])
+    cfg = dict(C.TINY_LLM)
+    videos = synth_normal("videos", (1, 3, meta["frames"], 28, 28))
+    images = synth_normal("images", (1, 3, 28, 28))
+    vf = U.encode_video(sd, videos, cfg)
+    assert np.abs(vf.numpy() - z["video_features"]).max() < 2e-4
+    out = U.core_forward(sd, cfg, torch.from_numpy(z["ids"]), images, videos=videos)
+    assert np.abs(out["logits"].numpy() - z["logits"]).max() < 2e-4
+
+
 def test_host_mirrors_import_without_gpu_and_fail_loudly():
     """The evaluation / dataset mirrors import on a CPU box, and every entry point raises (no fallback) without CUDA."""
     import native

@@ -132,7 +132,39 @@ def test_clip_processor_matches_oracle(ctx, dtype, h, w, pad):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# f4: sampling
+# f4: video path + sampling
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("bs,t,n,d", [(2, 8, 256, 1024), (1, 3, 4, 64), (3, 1, 7, 128)])
+def test_video_pool_kernel(ctx, dtype, bs, t, n, d):
+    g = torch.Generator().manual_seed(t * n)
+    feats = torch.randn((bs, t, n, d), generator=g).to(dtype).cuda()
+    got = ctx.video_pool(feats).float()
+    f32 = feats.float()
+    ref = torch.cat([f32.mean(dim=2), f32.mean(dim=1)], dim=1)
+    assert got.shape == (bs, t + n, d)
+    # fp32 accumulation + one rounding to the 16-bit type: half an ulp of the output (2^-9 bf16, 2^-12 fp16)
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert bool(((got - ref).abs() <= ulp * ref.abs() + 1e-6).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_video_and_image_rows_match_reference_golden(ctx, dtype):
+    """A batch mixing a <vid_beg> row and an <img_beg> row through UllavaCoreForCausalLM.forward(videos=...)."""
+    from oracle.synth import synth_normal
+    z, meta = load_golden("tiny_core_video")
+    model, sd, cfg = build_tiny_core(dtype)
+    videos = synth_normal("videos", (1, 3, meta["frames"], 28, 28)).cuda().to(dtype)
+    images = synth_normal("images", (1, 3, 28, 28)).cuda().to(dtype)
+    vf = model.encode_video(videos)
+    assert np.abs(vf.float().cpu().numpy() - z["video_features"]).max() < (2e-2 if dtype == torch.float16 else 8e-2)
+    out = model(input_ids=torch.from_numpy(z["ids"]).cuda(), images=images, videos=videos, return_dict=True)
+    err = np.abs(out.logits.float().cpu().numpy() - z["logits"]).max()
+    assert err < (1e-2 if dtype == torch.float16 else 8e-2), err
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sampling
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("V", [32011, 997, 64])
 @pytest.mark.parametrize("temperature,top_p", [(0.2, None), (0.2, 0.7), (1.0, 0.9), (0.7, 0.3), (1.5, 1.0)])

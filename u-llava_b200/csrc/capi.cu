@@ -184,6 +184,12 @@ int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t
                          eos_id, pad_id, pos_dev, static_cast<cudaStream_t>(stream));
 }
 
+int ullava_video_pool(ullava_ctx* ctx, const void* feats, void* out, int32_t batch, int32_t frames, int32_t patches,
+                      int32_t dim, int32_t dtype, void* stream) {
+  CTX_CHECK("ullava_video_pool");
+  return video_pool_run(ctx, feats, out, batch, frames, patches, dim, dtype, static_cast<cudaStream_t>(stream));
+}
+
 int ullava_sample_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, float temperature,
                        float top_p, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
                        int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,

@@ -267,6 +267,59 @@ int splice_rows_run(Context* ctx, void* embeds, const void* feats, const int32_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Video pooling (UllavaCoreForCausalLM.encode_video, models/ullava_core.py:160-180): per-frame patch features
+// feats [bs, T, N, D] -> out [bs, T + N, D]; rows 0..T-1 = mean over the N patches of frame t (temporal features),
+// rows T..T+N-1 = mean over the T frames of patch n (spatial features).  fp32 accumulation, one rounding.
+// One CTA per output row, 8 columns per thread, 16-byte loads that are contiguous across the CTA.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+video_pool_kernel(const T* __restrict__ feats, T* __restrict__ out, int frames, int patches, int dim) {
+  const int b = blockIdx.y, r = blockIdx.x;
+  const bool temporal = r < frames;
+  const int count = temporal ? patches : frames;
+  const int64_t step = temporal ? dim : static_cast<int64_t>(patches) * dim;
+  const T* base = feats + static_cast<int64_t>(b) * frames * patches * dim +
+                  (temporal ? static_cast<int64_t>(r) * patches * dim : static_cast<int64_t>(r - frames) * dim);
+  const float inv = 1.0f / static_cast<float>(count);
+  for (int c = threadIdx.x * 8; c < dim; c += blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < count; ++i) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + i * step + c);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2<T>(u[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+    uint4 o;
+    o.x = pack2<T>(acc[0] * inv, acc[1] * inv); o.y = pack2<T>(acc[2] * inv, acc[3] * inv);
+    o.z = pack2<T>(acc[4] * inv, acc[5] * inv); o.w = pack2<T>(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * (frames + patches) + r) * dim + c) = o;
+  }
+}
+
+int video_pool_run(Context* ctx, const void* feats, void* out, int batch, int frames, int patches, int dim, int dtype,
+                   cudaStream_t stream) {
+  ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 2.0 * batch * (2.0 * frames * patches + frames + patches) * dim);
+  ULLAVA_REQUIRE(feats && out, "video_pool: null pointer");
+  ULLAVA_REQUIRE(frames > 0 && patches > 0 && dim > 0 && dim % 8 == 0, "video_pool: bad shape");
+  if (batch == 0) return OK;
+  dim3 grid(frames + patches, batch);
+  if (dtype == DT_BF16)
+    video_pool_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(feats),
+                                                             static_cast<__nv_bfloat16*>(out), frames, patches, dim);
+  else if (dtype == DT_F16)
+    video_pool_kernel<__half><<<grid, 128, 0, stream>>>(static_cast<const __half*>(feats), static_cast<__half*>(out),
+                                                      frames, patches, dim);
+  else { set_last_error("video_pool: unsupported dtype"); return ERR_UNSUPPORTED; }
+  ctx->launches++;
+  return check_cuda(cudaGetLastError(), "video_pool launch");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Greedy argmax over fp32 logits, first index wins ties.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)

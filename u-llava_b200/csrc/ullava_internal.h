@@ -110,6 +110,8 @@ int splice_rows_run(Context* ctx, void* embeds, const void* feats, const int32_t
                     int n_patch, int dim, int dtype, cudaStream_t stream);
 int copy_rows_run(Context* ctx, const void* src, int64_t sbs, int64_t srs, void* dst, int64_t dbs, int64_t drs,
                   int batch, int rows, int cols, int dtype, cudaStream_t stream);
+int video_pool_run(Context* ctx, const void* feats, void* out, int batch, int frames, int patches, int dim, int dtype,
+                   cudaStream_t stream);
 int argmax_run(Context* ctx, const float* logits, int64_t ld, int64_t* out, int rows, int cols, cudaStream_t stream);
 
 // sampling.cu -- temperature / top-p step (inverse CDF over the filtered distribution, one uniform per row)

@@ -156,13 +156,11 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
 
     def encode_video(self, video_clip_tensors):
         """[bs, C, T, H, W] -> temporal+spatial pooled features [bs, T + num_patches, hidden]
-        (reference :160-180).  The frames go through the native ViT; the two mean-poolings are glue."""
+        (reference :160-180).  The frames go through the native ViT, the two mean-poolings through ullava_video_pool."""
         bs, c, t, h, w = video_clip_tensors.shape
         frames = video_clip_tensors.permute(0, 2, 1, 3, 4).reshape(bs * t, c, h, w)
         feats = self.encode_image(frames).view(bs, t, -1, self.vision_encoder.config.hidden_size)
-        spatial = feats.float().mean(dim=1).to(feats.dtype)
-        temporal = feats.float().mean(dim=2).to(feats.dtype)
-        return torch.cat([temporal, spatial], dim=1)
+        return self._ctx().video_pool(feats)
 
     def embed_images_videos(self, input_ids=None, images=None, videos=None):
         if input_ids.shape[1] == 1:

@@ -110,6 +110,7 @@ _SIGNATURES = {
     "ullava_splice_rows": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ullava_copy_rows": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
     "ullava_argmax": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp]),
+    "ullava_video_pool": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ullava_sam_mask_decoder": (_i32, [_vp, C.POINTER(SamDecoderArgs), _vp]),
     "ullava_sam_mask_decoder_scratch_bytes": (_sz, [_i32]),
     "ullava_sam_postprocess": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
@@ -500,6 +501,15 @@ class Context:
             seqs.stride(0) if seqs is not None else 0, _ptr(final_h), _ptr(hid_buf),
             hid_buf.stride(0) if hid_buf is not None else 0, final_h.shape[-1] if final_h is not None else 8,
             _ptr(finished), int(eos_id), int(pad_id), pos_dev.data_ptr(), _stream()))
+
+    def video_pool(self, feats: torch.Tensor) -> torch.Tensor:
+        """feats [bs, T, N, D] -> [bs, T + N, D]: temporal means then spatial means (encode_video)."""
+        bs, t, n, d = feats.shape
+        feats = feats.contiguous()
+        out = torch.empty((bs, t + n, d), dtype=feats.dtype, device=feats.device)
+        self._chk(self.lib.ullava_video_pool(self.handle, feats.data_ptr(), out.data_ptr(), bs, t, n, d,
+                                             dtype_code(feats.dtype), _stream()))
+        return out
 
     def sample_step(self, logits, temperature, top_p, uniforms, cur_ids, seqs=None, final_h=None, hid_buf=None,
                     finished=None, eos_id=-1, pad_id=0, pos_dev=None, probs_out=None):
