@@ -28,7 +28,7 @@ namespace ullava {
 static constexpr int BM = 128;       // UMMA M (rows of A per tile)
 static constexpr int BK = 64;        // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 static constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
-static constexpr int GROUP_M = 8;    // rasterisation group
+static constexpr int kDefaultGroupM = 8;    // rasterisation group (ctx->group_m overrides)
 static constexpr int kGemmThreads = 384;
 static constexpr int kEpiWarp0 = 4;   // first epilogue warp
 static constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant, alternating 32-column chunks
@@ -46,6 +46,7 @@ struct GemmKernelParams {
   int kb_total;       // ceil(K / 64)
   int kb_per_split;   // k-blocks handled by one split
   int splits;         // >1: D is an fp32 workspace [splits][M][N], epilogue deferred
+  int group_m;        // rasterisation group: M tiles swept together over N (their A panel stays L2 resident)
 };
 
 template <int BN, int STAGES>
@@ -58,7 +59,8 @@ struct GemmSmem {
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& split, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int GROUP_M, int& split, int& m_blk,
+                                            int& n_blk) {
   const int per_split = num_m * num_n;
   split = t / per_split;
   int r = t - split * per_split;
@@ -267,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int split, m_blk, n_blk;
-        tile_coords(t, p.num_m, p.num_n, split, m_blk, n_blk);
+        tile_coords(t, p.num_m, p.num_n, p.group_m, split, m_blk, n_blk);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -293,7 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int split, m_blk, n_blk;
-        tile_coords(t, p.num_m, p.num_n, split, m_blk, n_blk);
+        tile_coords(t, p.num_m, p.num_n, p.group_m, split, m_blk, n_blk);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -334,7 +336,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool split_mode = p.splits > 1;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int split, m_blk, n_blk;
-      tile_coords(t, p.num_m, p.num_n, split, m_blk, n_blk);
+      tile_coords(t, p.num_m, p.num_n, p.group_m, split, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
@@ -538,6 +540,17 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
                     (a.out_f32 ? 4.0 : 2.0) * a.M * out_cols);
   GemmKernelParams p{};
   p.kb_total = kb_total;
+  // Rasterisation group.  While a group of M tiles sweeps over N its A panel stays in L2 and B streams through, so B
+  // is read from DRAM num_m / group_m times: when B is too large to live in L2 beside the panel (LLaMA qkv / gate-up
+  // / down at prefill: 100 / 180 / 90 MB) a taller group cuts those re-reads (3.6 -> ~1 GB on gate/up, +6-7 % on
+  // tools/bench_gemm.py), as long as the panel itself (group_m x 128 x K x 2 B) stays well inside L2.
+  p.group_m = kDefaultGroupM;
+  if (2.0 * a.N * a.K >= 48e6) {
+    int g = 32;
+    while (g > kDefaultGroupM && 256.0 * g * a.K > 48e6) g /= 2;
+    p.group_m = g;
+  }
+  if (ctx->group_m > 0) p.group_m = ctx->group_m;
   p.epilogue = a.epilogue;
   p.out_f32 = a.out_f32;
   p.bias = a.bias;
