@@ -407,7 +407,7 @@ def run_b200(args):
         return
 
     sampler = ClockSampler(physical_gpu_index(local))
-    if rank == 0:
+    if rank == 0 and not os.environ.get("ULLAVA_BENCH_NO_CLOCKS"):
         sampler.start()
     ms_res, launches, res = timed(step_resident, args.warmup, args.steps)
     clocks = sampler.stop() if rank == 0 else None

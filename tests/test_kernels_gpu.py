@@ -65,6 +65,40 @@ def test_gemm_shapes(ctx, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K,epi", [(4096, 4096, 1024, EPI_NONE), (5000, 2000, 136, EPI_GELU),
+                                       (9728, 1024, 4096, EPI_NONE), (4933, 2312, 1288, EPI_QUICK_GELU),
+                                       (37 * 256 + 1, 1280, 64, EPI_RELU)])
+def test_gemm_cta_pair_kernel(ctx, dtype, M, N, K, epi):
+    """Shapes with >= 148 tiles of 256 x 256 run on CTA pairs (tcgen05 cta_group::2): ragged M (second CTA of a pair
+    partly or fully out of range), ragged N and K, every fused epilogue, in-place residual."""
+    a = _rand((M, K), dtype, seed=41)
+    w = _rand((N, K), dtype, K ** -0.5, seed=42)
+    b = _rand((N,), dtype, seed=43)
+    r = _rand((M, N), dtype, seed=44)
+    ref = _act_ref(a.float() @ w.float().t() + b.float(), epi) + r.float()
+    out = ctx.gemm(a, w, bias=b, residual=r, epilogue=epi)
+    _check(out, ref, dtype, f"pair gemm {M}x{N}x{K} epi {epi}")
+    single = ctx.gemm(a, w, bias=b, residual=r, epilogue=epi, force_bn=256)   # single-CTA kernel, same K order
+    assert torch.equal(out, single), "CTA-pair and single-CTA kernels must round identically"
+    r2 = r.clone()
+    ctx.gemm(a, w, bias=b, residual=r2, epilogue=epi, out=r2)
+    assert torch.equal(r2, out)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_cta_pair_silu_mul(ctx, dtype):
+    M, K, F = 4864, 512, 2048
+    a = _rand((M, K), dtype, seed=45)
+    wg = _rand((F, K), dtype, K ** -0.5, seed=46)
+    wu = _rand((F, K), dtype, K ** -0.5, seed=47)
+    packed = torch.stack([wg.view(F // 16, 16, K), wu.view(F // 16, 16, K)], dim=1).reshape(2 * F, K).contiguous()
+    out = ctx.gemm(a, packed, epilogue=EPI_SILU_MUL)
+    g, u = a.float() @ wg.float().t(), a.float() @ wu.float().t()
+    _check(out, torch.nn.functional.silu(g) * u, dtype, "pair silu_mul")
+    assert torch.equal(out, ctx.gemm(a, packed, epilogue=EPI_SILU_MUL, force_bn=256))
+
+
+@pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("epi", [EPI_NONE, EPI_RELU, EPI_GELU, EPI_QUICK_GELU])
 def test_gemm_bias_act_residual(ctx, dtype, epi):
     M, N, K = 700, 1024, 512

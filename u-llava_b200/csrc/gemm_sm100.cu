@@ -381,6 +381,176 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // -----------------------------------------------------------------------------
+// CTA-pair flavour (tcgen05 cta_group::2): one 256 x 256 output tile per PAIR of SMs.
+// Each CTA of the pair stages its own 128 rows of A and HALF of the B tile (128 weight rows); the leader's
+// single MMA thread issues M = 256 instructions that read both halves of B from the two shared memories and
+// write 128 accumulator rows into each CTA's TMEM.  Per output tile each SM therefore moves (128 + 128) x K
+// operand bytes instead of (128 + 256) x K: 1/3 less L2 -> SM traffic for the same math, which is what bounds the
+// 128 x 256 single-CTA tile (85 FLOP per operand byte -> ~19 TB/s of L2 bandwidth at tensor peak).
+// Barriers: TMA of both CTAs completes on the LEADER's full barrier; tcgen05.commit multicasts to the empty /
+// tmem_full barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
+// -----------------------------------------------------------------------------
+static constexpr int kPairStages = 6;   // 6 x (16 KB A + 16 KB B half) = 192 KB
+static constexpr int kPairBM = 256, kPairBN = 256;
+
+struct PairSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = (kPairBN / 2) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kPairStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kPairStages + 4) * 8 + 16 + 1024;
+};
+
+template <typename T, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmKernelParams p) {
+  using S = PairSmem;
+  constexpr int STAGES = kPairStages;
+  constexpr int BN = kPairBN;
+  constexpr uint32_t kIdesc = make_idesc_f16(T16<T>::kUmmaFormat, kPairBM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.num_m * p.num_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's copy is the live one: one arrive.expect_tx for both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);   // one multicast tcgen05.commit per use, in each CTA
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * kEpiWarps);  // leader's copy: one elected arrive per epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<2>(tmem_ptr, 512);
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        int split, m_blk, n_blk;
+        tile_coords(t, p.num_m, p.num_n, p.group_m, split, m_blk, n_blk);
+        const int row_a = m_blk * kPairBM + static_cast<int>(rank) * BM;
+        const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_2sm(sa + S::kABytes, &tmB, &full_bar[stage], kb * BK, row_b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t a_desc = make_kmajor_sw128_desc(sa);
+          const uint64_t b_desc = make_kmajor_sw128_desc(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16<2>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit<2>(&empty_bar[stage]);   // frees the slot in BOTH CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit<2>(&tmem_full[acc]);       // accumulators of both CTAs complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* resid = reinterpret_cast<const T*>(p.residual);
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      int split, m_blk, n_blk;
+      tile_coords(t, p.num_m, p.num_n, p.group_m, split, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kPairBM + static_cast<int>(rank) * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        float v[32];
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < p.N) epilogue_store<T, EPI, 32>(v, p, bias, resid, false, 0, row, n0);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster(&tmem_empty[acc], 0);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves while the peer may still read its shared memory or signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
+// -----------------------------------------------------------------------------
 // Split-K reduce + epilogue.  partial: fp32 [splits][R][C].
 //   transpose == 0: out[r][c]   (R = M rows, C = N cols)
 //   transpose == 1: out[c][r]   (swap-AB: R = weight rows (N_out), C = padded batch; out is [batch][N_out])
@@ -497,6 +667,32 @@ static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const
   }
 }
 
+template <typename T, int EPI>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+                       cudaStream_t stream) {
+  auto kern = gemm_tcgen05_pair_kernel<T, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, PairSmem::kTotal, stream>>>(ta, tb, p);   // __cluster_dims__(2, 1, 1): grid is even
+  return check_cuda(cudaGetLastError(), "gemm_tcgen05_pair_kernel launch");
+}
+
+template <typename T>
+static int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
+                           cudaStream_t stream) {
+  switch (epi) {
+    case EPI_NONE: return launch_pair<T, EPI_NONE>(ta, tb, p, grid, stream);
+    case EPI_RELU: return launch_pair<T, EPI_RELU>(ta, tb, p, grid, stream);
+    case EPI_GELU: return launch_pair<T, EPI_GELU>(ta, tb, p, grid, stream);
+    case EPI_QUICK_GELU: return launch_pair<T, EPI_QUICK_GELU>(ta, tb, p, grid, stream);
+    case EPI_SILU_MUL: return launch_pair<T, EPI_SILU_MUL>(ta, tb, p, grid, stream);
+    default: set_last_error("gemm: unknown epilogue %d", epi); return ERR_BAD_ARG;
+  }
+}
+
 // the activation is compiled into the kernel; with split-K the kernel only parks fp32 partials (EPI_NONE)
 template <typename T>
 static int launch_epi(int epi, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
@@ -564,6 +760,30 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
   }
   if (!swap) {
     ctx->next_w = nullptr;  // the next-weight hint only applies to the weight-streaming kernel
+    // CTA-pair kernel (256 x 256 tile per two SMs) for the large products: enough pair tiles to fill the machine
+    const bool pair_ok = !a.force_bn && a.force_splits <= 1 && ctx->gemm_pair != 0 && a.N >= 256 &&
+                         static_cast<long long>((a.M + kPairBM - 1) / kPairBM) * ((a.N + kPairBN - 1) / kPairBN) >=
+                             2ll * (sms / 2);
+    if (pair_ok) {
+      p.M = a.M; p.N = a.N; p.K = a.K;
+      p.num_m = (a.M + kPairBM - 1) / kPairBM;
+      p.num_n = (a.N + kPairBN - 1) / kPairBN;
+      p.kb_per_split = kb_total;
+      p.splits = 1;
+      p.D = a.D; p.ldd = a.ldd;
+      p.group_m = (p.group_m + 1) / 2;   // groups are counted in 256-row tiles here
+      int st = encode_tmap_2d(&ta, a.A, 2, a.K, a.M, a.lda * 2, BK, BM, true);
+      if (st) return st;
+      st = encode_tmap_2d(&tb, a.B, 2, a.K, a.N, a.ldb * 2, BK, kPairBN / 2, true);
+      if (st) return st;
+      const int tiles = p.num_m * p.num_n;
+      const int grid = 2 * (tiles < sms / 2 ? tiles : sms / 2);
+      st = (a.dtype == DT_BF16) ? launch_pair_epi<__nv_bfloat16>(a.epilogue, ta, tb, p, grid, stream)
+                                : launch_pair_epi<__half>(a.epilogue, ta, tb, p, grid, stream);
+      if (st) return st;
+      ctx->launches += 1;
+      return OK;
+    }
     const int bn = a.force_bn ? a.force_bn : pick_bn_large(a.N);
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.num_m = (a.M + BM - 1) / BM;

@@ -151,6 +151,7 @@ int ullava_create(int device, ullava_ctx** out) {
     const int v = atoi(e);
     if (v >= 0 && v <= 256) c->prefetch_units = v;
   }
+  if (const char* e = getenv("ULLAVA_GEMM_PAIR")) c->gemm_pair = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("ULLAVA_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0 && v <= 1024) c->group_m = v;

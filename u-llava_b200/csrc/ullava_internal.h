@@ -28,6 +28,7 @@ struct ullava_ctx {
   int next_n = 0, next_k = 0;
   int64_t next_ldb = 0;
   int prefetch_units = 12;  // 16 KB tiles per SM pulled into L2 (0 = off); ULLAVA_PREFETCH_UNITS overrides at create
+  int gemm_pair = 1;  // large-M GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles); ULLAVA_GEMM_PAIR=0 turns it off
   int group_m = 0;    // 0 = default rasterisation group of the large-M GEMM; ULLAVA_GROUP_M overrides at create (tuning)
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
