@@ -477,7 +477,7 @@ def run_b200(args):
             with open(tpath) as f:
                 traffic = json.load(f)
         a_t = gt["flops"] / max(gt["ms"], 1e-9) / 1e9
-        line["roofline"] = {"kernel": "gemm_tcgen05_kernel (large-M, prefill / ViT / SAM-decoder GEMMs)",
+        line["roofline"] = {"kernel": "gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel (large-M GEMMs: ViT, prefill, SAM encoder + decoder)",
                             "bound": "tensor", "achieved": a_t, "peak": peaks["bf16_tflops_sustained"],
                             "unit": "TFLOP/s", "frac": a_t / peaks["bf16_tflops_sustained"],
                             "traffic": (traffic or {}).get("gemm_tensor"), "launches": gt["launches"],
