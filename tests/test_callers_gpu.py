@@ -83,6 +83,56 @@ def test_box_iou_diag_bit_exact(ctx, dtype):
     assert meter[:2].tolist() == [float((ref > 0.5).sum()), 333.0]
 
 
+def test_validate_batched_right_padded_equals_per_image(ctx):
+    """evaluation.eval_ullava.validate on the tiny model: a right-padded batch of 2 (different prompt lengths, the
+    reference collator's pad_sequence layout) gives the same ciou / giou / prec@0.5 as the reference's batch-1 loop
+    shape, and the meters match the oracle's restatement of validate() fed with the model's own masks."""
+    from evaluation.eval_ullava import validate
+    from tests import configs as C
+    from tests.util_models import build_tiny_full, oracle_inputs_full
+    dtype = torch.bfloat16
+    model, sd, cfg = build_tiny_full(dtype)
+    ids, images, images_sam, sizes, resizes = oracle_inputs_full()
+    g = torch.Generator().manual_seed(9)
+    items = []
+    for b in range(2):
+        row = ids[b] if b == 0 else ids[b][:-1]                       # second prompt one token shorter -> padded
+        n_seg, n_loc = int((row == C.SEG_ID).sum()), int((row == C.LOC_ID).sum())
+        gt = (torch.rand((n_seg,) + tuple(sizes[b]), generator=g) > 0.5).float()
+        gt[torch.rand(gt.shape, generator=g) > 0.9] = 255.0
+        box = torch.rand((n_loc, 2), generator=g) * 0.5
+        items.append(dict(input_ids=row, labels=row.clone(), image=images[b], image_sam=images_sam[b], seg_mask=gt,
+                          raw_size=sizes[b], resize=resizes[b], boxes=torch.cat([box, box + 0.3], 1)))
+
+    def collate(instances):   # dataset/collators/base_collator.py:107-123 (GroundingCollator)
+        pad = lambda key, v: torch.nn.utils.rnn.pad_sequence([i[key] for i in instances], batch_first=True, padding_value=v)
+        input_ids = pad("input_ids", 0)
+        return dict(input_ids=input_ids, labels=pad("labels", -100), attention_mask=input_ids.ne(0),
+                    images=torch.stack([i["image"] for i in instances]),
+                    images_sam=torch.stack([i["image_sam"] for i in instances]),
+                    mask_list=[i["seg_mask"] for i in instances], size_list=[i["raw_size"] for i in instances],
+                    resize_list=[i["resize"] for i in instances], bbox_list=[i["boxes"] for i in instances])
+
+    one = validate(model, items, collate, dtype, batch_size=1, num_workers=0, verbose=False)
+    two = validate(model, items, collate, dtype, batch_size=2, num_workers=0, verbose=False)
+    assert all(np.isfinite(v) for v in one) and one[0] > 0
+    # the padded batch takes the same kernels row for row; a pixel exactly at the threshold may still flip
+    assert abs(one[0] - two[0]) < 0.5 and abs(one[1] - two[1]) < 0.5 and one[2] == two[2], (one, two)
+    # oracle restatement of validate() on the masks / boxes the model produced
+    counts, hits = [], []
+    for it in items:
+        from evaluation.tools import dict_to_cuda
+        out = model(**dict_to_cuda(collate([it]), dtype), inference=True)
+        pm = out["pred_masks"][0].float().cpu().numpy()
+        gt = it["seg_mask"].numpy()
+        counts.append(np.stack([np.concatenate(O.intersection_and_union((pm[m] > 0).astype(np.int32), gt[m], 2, 255))
+                                for m in range(pm.shape[0])]))
+        iou = O.box_iou_diag(out["pred_boxes"][0].cpu(), it["boxes"].to(dtype))
+        hits.append((iou > 0.5).tolist())
+    ref = O.validate_meters(counts, hits)
+    assert one[0] == ref["ciou"] and one[1] == ref["giou"] and one[2] == ref["prec05"], (one, ref)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # f3: preprocessing
 # ---------------------------------------------------------------------------------------------------------------
