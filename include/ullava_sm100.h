@@ -177,6 +177,16 @@ ULLAVA_API int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q
                             int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
                             int32_t head_dim, int32_t ctx_len, float scale, int32_t dtype, void* stream);
 
+/* Decode step, fused: RoPE of the new token's q and k, the KV-cache write of its k and v (row ctx_len - 1) and the
+ * single-query attention over rows 0 .. ctx_len - 1, in one kernel (what ullava_rope_kvcache followed by
+ * ullava_attention_decode compute for seq == 1; ullava_llama_forward / _decode_step use this form).
+ * qkv: packed [B, 3 * heads * head_dim] rows (row stride ld_qkv); rope_cos / rope_sin fp32 [max_seq, head_dim / 2];
+ * pos_dev (optional): device int32, ctx_len = *pos_dev + 1 (CUDA-graph replay; max_seq then bounds the score buffer). */
+ULLAVA_API int ullava_attention_decode_rope(ullava_ctx* ctx, const void* qkv, int64_t ld_qkv, void* k_cache, void* v_cache,
+                                 int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
+                                 int32_t head_dim, int32_t ctx_len, const int32_t* pos_dev, int32_t max_seq,
+                                 const float* rope_cos, const float* rope_sin, float scale, int32_t dtype, void* stream);
+
 /* RoPE (rotate-half, hf:models/llama/modeling_llama.py:74-168) applied to the q and k thirds of a
  * packed QKV buffer [rows, 3*heads*head_dim]; rotated k and the untouched v are scattered into the
  * KV cache [batch, heads, max_seq, head_dim] at position pos0 + (row % seq); rotated q is written

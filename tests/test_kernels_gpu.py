@@ -449,6 +449,31 @@ def _rope_tables(max_pos, hd, theta=10000.0):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,D,ctx_len,max_seq", [(2, 32, 128, 609, 672), (32, 32, 128, 672, 672), (3, 4, 64, 5, 16),
+                                                   (2, 2, 16, 1, 8), (1, 2, 32, 8, 8)])
+def test_decode_attention_fused_rope_matches_two_kernels(ctx, dtype, B, H, D, ctx_len, max_seq):
+    """ullava_attention_decode_rope == ullava_rope_kvcache (one new token) followed by ullava_attention_decode: same
+    cache contents and the same output, with the position given by value and through device memory (graph replay)."""
+    g = torch.Generator(device="cuda").manual_seed(ctx_len * 7 + D)
+    qkv = torch.randn((B, 3 * H * D), generator=g, device="cuda").to(dtype)
+    kc = torch.randn((B, H, max_seq, D), generator=g, device="cuda").to(dtype)
+    vc = torch.randn((B, H, max_seq, D), generator=g, device="cuda").to(dtype)
+    pos = ctx_len - 1
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device="cuda").float() / D))
+    fr = torch.arange(max_seq, device="cuda").float()[:, None] * inv[None, :]
+    cos, sin = fr.cos().contiguous(), fr.sin().contiguous()
+    qkv_a, kc_a, vc_a = qkv.clone(), kc.clone(), vc.clone()
+    ctx.rope_kvcache(qkv_a, kc_a, vc_a, B, 1, pos, cos, sin)
+    ref = ctx.attention_decode(qkv_a[:, :H * D], kc_a, vc_a, ctx_len)
+    for use_dev in (False, True):
+        kc_b, vc_b = kc.clone(), vc.clone()
+        pos_dev = torch.tensor([pos], dtype=torch.int32, device="cuda") if use_dev else None
+        out = ctx.attention_decode_rope(qkv, kc_b, vc_b, 0 if use_dev else ctx_len, cos, sin, pos_dev=pos_dev)
+        assert torch.equal(kc_b, kc_a) and torch.equal(vc_b, vc_a), "fused kernel wrote a different cache row"
+        assert torch.equal(out, ref), (out.float() - ref.float()).abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("B,S,H,D,pos0", [(2, 37, 4, 128, 0), (3, 1, 2, 64, 11), (1, 5, 2, 16, 3)])
 def test_rope_kvcache(ctx, dtype, B, S, H, D, pos0):
     max_seq = pos0 + S + 3

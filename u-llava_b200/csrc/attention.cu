@@ -618,22 +618,71 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 // through shared memory.  HBM-bound: K and V are each read exactly once.
 static constexpr int DEC_THREADS = 128;
 
-template <typename T, int HD>
+// kRope: the kernel also does the step's RoPE + KV-cache write (rope_kvcache_kernel for one new token per sample):
+// q points at the PACKED qkv row [q | k | v] (each `qkv_hd` = heads * HD wide); the first HD/4 threads rotate q and k
+// of this (sample, head) with the cos / sin row of position ctx_len - 1 (rotate_half,
+// hf:models/llama/modeling_llama.py:137-168; same expressions and one rounding to T as rope_kvcache_kernel), write
+// rotated k and v into cache row ctx_len - 1 and keep q, k, v in shared memory; the cached rows 0 .. ctx_len - 2 are
+// streamed as before and the new row is taken from shared memory.  One kernel less per layer of the decode step.
+template <typename T, int HD, bool kRope>
 __global__ void __launch_bounds__(DEC_THREADS)
-attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ kc, const T* __restrict__ vc,
+attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, T* __restrict__ kc, T* __restrict__ vc,
                    int64_t cache_bs, int64_t cache_hs, T* __restrict__ o, int64_t o_bs, int ctx_len,
-                   float scale_log2, const int32_t* __restrict__ ctx_dev) {
+                   float scale_log2, const int32_t* __restrict__ ctx_dev, const float* __restrict__ cos_t,
+                   const float* __restrict__ sin_t, int qkv_hd) {
   pdl_launch_dependents();  // the o-projection GEMM may start prefetching its weights under this kernel
-  pdl_wait();               // launched with programmatic serialization: resident before the RoPE / KV-write kernel ends
+  pdl_wait();               // launched with programmatic serialization: resident before its predecessor ends
   if (ctx_dev) ctx_len = *ctx_dev + 1;  // CUDA-graph decode: keys 0..pos are attended, pos read from device memory
   extern __shared__ float dec_smem[];   // [ctx_len] scores, then [groups][HD] partial outputs
   __shared__ float red[DEC_THREADS / 32];
   __shared__ float bcast[2];
+  __shared__ __align__(16) T s_new[kRope ? 3 * HD : 8];   // rotated q, rotated k, v of the new token
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* qp = q + b * q_bs + h * HD;
   const T* kp = kc + b * cache_bs + h * cache_hs;
   const T* vp = vc + b * cache_bs + h * cache_hs;
+  const int ctx_main = kRope ? ctx_len - 1 : ctx_len;   // rows read from the cache
+
+  if constexpr (kRope) {
+    constexpr int half = HD / 2, NP = HD / 16;   // NP (lo, hi) chunk pairs of 8 elements per vector
+    const int pos = ctx_len - 1;
+    if (tid < 2 * NP) {
+      const bool is_k = tid >= NP;
+      const int j = (is_k ? tid - NP : tid) * 8;
+      const T* src = qp + (is_k ? qkv_hd : 0);
+      const float* cs = cos_t + static_cast<int64_t>(pos) * half;
+      const float* sn = sin_t + static_cast<int64_t>(pos) * half;
+      const uint4 lo = *reinterpret_cast<const uint4*>(src + j);
+      const uint4 hi = *reinterpret_cast<const uint4*>(src + j + half);
+      const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, u[4] = {hi.x, hi.y, hi.z, hi.w};
+      uint32_t ol[4], ou[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack2<T>(l[e]), c = unpack2<T>(u[e]);
+        const float c0 = cs[j + 2 * e], c1 = cs[j + 2 * e + 1];
+        const float s0 = sn[j + 2 * e], s1 = sn[j + 2 * e + 1];
+        ol[e] = pack2<T>(a.x * c0 - c.x * s0, a.y * c1 - c.y * s1);
+        ou[e] = pack2<T>(c.x * c0 + a.x * s0, c.y * c1 + a.y * s1);
+      }
+      const uint4 vlo = make_uint4(ol[0], ol[1], ol[2], ol[3]), vhi = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+      T* dst = s_new + (is_k ? HD : 0);
+      *reinterpret_cast<uint4*>(dst + j) = vlo;
+      *reinterpret_cast<uint4*>(dst + j + half) = vhi;
+      if (is_k) {
+        T* d = kc + b * cache_bs + h * cache_hs + static_cast<int64_t>(pos) * HD + j;
+        *reinterpret_cast<uint4*>(d) = vlo;
+        *reinterpret_cast<uint4*>(d + half) = vhi;
+      }
+    } else if (tid < 2 * NP + HD / 8) {
+      const int e = (tid - 2 * NP) * 8;
+      const uint4 v = *reinterpret_cast<const uint4*>(qp + 2 * qkv_hd + e);
+      *reinterpret_cast<uint4*>(s_new + 2 * HD + e) = v;
+      *reinterpret_cast<uint4*>(vc + b * cache_bs + h * cache_hs + static_cast<int64_t>(pos) * HD + e) = v;
+    }
+    __syncthreads();
+    qp = s_new;   // the rotated query
+  }
 
   constexpr int LPK = HD / 16;             // lanes per key
   constexpr int KPW = 32 / LPK;            // keys per warp iteration
@@ -654,12 +703,12 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
   // KU key rows per lane in flight (2 x 16 B each): the loop is latency-bound otherwise (one CTA holds only 4 warps)
   constexpr int KU = 4;
   constexpr int KSTEP = (DEC_THREADS / 32) * KPW;
-  for (int j0 = warp * KPW; j0 < ctx_len; j0 += KU * KSTEP) {
+  for (int j0 = warp * KPW; j0 < ctx_main; j0 += KU * KSTEP) {
     uint4 ka[KU], kb[KU];
 #pragma unroll
     for (int r = 0; r < KU; ++r) {
       const int j = j0 + r * KSTEP + kin;
-      if (j < ctx_len) {
+      if (j < ctx_main) {
         const T* kr = kp + static_cast<int64_t>(j) * HD + sub * 16;
         ka[r] = ld_stream(reinterpret_cast<const uint4*>(kr));
         kb[r] = ld_stream(reinterpret_cast<const uint4*>(kr + 8));
@@ -681,10 +730,29 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
 #pragma unroll
       for (int off = LPK / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
       acc *= scale_log2;
-      if (j < ctx_len) {
+      if (j < ctx_main) {
         if (sub == 0) dec_smem[j] = acc;
         lmax = fmaxf(lmax, acc);
       }
+    }
+  }
+  if constexpr (kRope) {
+    if (warp == 0) {   // the new key, from shared memory (its cache row was written by this CTA, not read back)
+      const T* kr = s_new + HD + sub * 16;
+      const uint4 a = *reinterpret_cast<const uint4*>(kr);
+      const uint4 c = *reinterpret_cast<const uint4*>(kr + 8);
+      const uint32_t u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 f = unpack2<T>(u[e]);
+        acc += f.x * qf[2 * e] + f.y * qf[2 * e + 1];
+      }
+#pragma unroll
+      for (int off = LPK / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      acc *= scale_log2;
+      if (lane == 0) dec_smem[ctx_len - 1] = acc;
+      lmax = fmaxf(lmax, acc);
     }
   }
   lmax = warp_max(lmax);
@@ -721,19 +789,33 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
   const int grp = tid / TPR, dv = (tid % TPR) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   constexpr int VU = 8;  // V rows per thread in flight (16 B each); rows are accumulated in increasing j
-  for (int j0 = grp; j0 < ctx_len; j0 += VU * GROUPS) {
+  for (int j0 = grp; j0 < ctx_main; j0 += VU * GROUPS) {
     uint4 va[VU];
 #pragma unroll
     for (int r = 0; r < VU; ++r) {
       const int j = j0 + r * GROUPS;
-      va[r] = j < ctx_len ? ld_stream(reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(j) * HD + dv))
-                          : make_uint4(0u, 0u, 0u, 0u);
+      va[r] = j < ctx_main ? ld_stream(reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(j) * HD + dv))
+                           : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int r = 0; r < VU; ++r) {
       const int j = j0 + r * GROUPS;
-      const float pj = j < ctx_len ? T16<T>::to_f(T16<T>::from_f(dec_smem[j] * inv)) : 0.f;
+      const float pj = j < ctx_main ? T16<T>::to_f(T16<T>::from_f(dec_smem[j] * inv)) : 0.f;
       const uint32_t u[4] = {va[r].x, va[r].y, va[r].z, va[r].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack2<T>(u[e]);
+        acc[2 * e] += pj * f.x;
+        acc[2 * e + 1] += pj * f.y;
+      }
+    }
+  }
+  if constexpr (kRope) {
+    // the new value row: last row of its group, exactly where the cache loop would have added it
+    if (grp == (ctx_len - 1) % GROUPS) {
+      const float pj = T16<T>::to_f(T16<T>::from_f(dec_smem[ctx_len - 1] * inv));
+      const uint4 v = *reinterpret_cast<const uint4*>(s_new + 2 * HD + dv);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack2<T>(u[e]);
@@ -755,28 +837,45 @@ attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, const T* __restrict__ 
   }
 }
 
-template <typename T, int HD>
-static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
-                         int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
-                         cudaStream_t stream, const int32_t* ctx_dev, int max_ctx, bool pdl) {
+template <typename T, int HD, bool kRope>
+static int decode_launch_k(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
+                           int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
+                           cudaStream_t stream, const int32_t* ctx_dev, int max_ctx, bool pdl, const float* cos_t,
+                           const float* sin_t) {
   constexpr int GROUPS = DEC_THREADS / (HD / 8);
   const int smem_ctx = ctx_dev ? max_ctx : ctx_len;  // with a device-side length the buffer covers the whole cache
   size_t smem = sizeof(float) * static_cast<size_t>(smem_ctx > GROUPS * HD ? smem_ctx : GROUPS * HD);
-  auto kern = attn_decode_kernel<T, HD>;
+  auto kern = attn_decode_kernel<T, HD, kRope>;
   if (smem > 48 * 1024) {
     ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   dim3 grid(heads, batch);
   return check_cuda(launch_pdl(kern, grid, dim3(DEC_THREADS), smem, stream, pdl, static_cast<const T*>(q), q_bs,
-                               static_cast<const T*>(kc), static_cast<const T*>(vc), cache_bs, cache_hs,
-                               static_cast<T*>(o), o_bs, ctx_len, scale * 1.4426950408889634f, ctx_dev),
+                               static_cast<T*>(const_cast<void*>(kc)), static_cast<T*>(const_cast<void*>(vc)), cache_bs,
+                               cache_hs, static_cast<T*>(o), o_bs, ctx_len, scale * 1.4426950408889634f, ctx_dev, cos_t,
+                               sin_t, heads * HD),
                     "attn_decode launch");
 }
 
+template <typename T, int HD>
+static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
+                         int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
+                         cudaStream_t stream, const int32_t* ctx_dev, int max_ctx, bool pdl,
+                         const float* cos_t = nullptr, const float* sin_t = nullptr) {
+  if (cos_t != nullptr)
+    return decode_launch_k<T, HD, true>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale,
+                                        stream, ctx_dev, max_ctx, pdl, cos_t, sin_t);
+  return decode_launch_k<T, HD, false>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream,
+                                       ctx_dev, max_ctx, pdl, nullptr, nullptr);
+}
+
+// rope_cos / rope_sin != nullptr: fused RoPE + KV-cache write of the new token (q = packed qkv row, see the kernel)
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
-                         float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev, int max_ctx) {
+                         float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev, int max_ctx,
+                         const float* rope_cos, const float* rope_sin) {
   if (ctx_dev) ctx_len = max_ctx;
+  ULLAVA_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "attention_decode: cos and sin go together");
   ProfScope _ps(ctx, stream, ULLAVA_PROF_ATTN_DECODE, 4.0 * batch * heads * (double)ctx_len * head_dim, 4.0 * batch * heads * (double)ctx_len * head_dim);
   ULLAVA_REQUIRE(q && kc && vc && o, "attention_decode: null pointer");
   ULLAVA_REQUIRE(ctx_len > 0 && ctx_len <= 16384, "attention_decode: ctx_len %d out of range", ctx_len);
@@ -785,7 +884,7 @@ int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* 
   int st;
 #define ULLAVA_DEC(TT, HDIM) \
   st = decode_launch<TT, HDIM>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream, \
-                               ctx_dev, max_ctx, ctx->pdl != 0)
+                               ctx_dev, max_ctx, ctx->pdl != 0, rope_cos, rope_sin)
   if (dtype == DT_BF16) {
     if (head_dim == 128) ULLAVA_DEC(__nv_bfloat16, 128);
     else if (head_dim == 64) ULLAVA_DEC(__nv_bfloat16, 64);

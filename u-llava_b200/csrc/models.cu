@@ -162,12 +162,13 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
     }
     RUN(rmsnorm_run(ctx, a.hidden, H, L[0], xn, H, rows, H, a.eps, dt, s));
     RUN(gemm(ctx, s, dt, xn, H, L[1], H, qkv, 3 * H, rows, 3 * H, H));
-    RUN(rope_kvcache_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, a.batch, a.seq, a.heads, hd, a.pos0, a.rope_cos,
-                         a.rope_sin, dt, s, pos_dev));
     if (a.seq == 1) {
+      // decode step: RoPE of the new q / k and the KV-cache write are fused into the single-query attention kernel
       RUN(attention_decode_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, att, H, a.batch, a.heads, hd, a.pos0 + 1,
-                               scale, dt, s, pos_dev, a.max_seq));
+                               scale, dt, s, pos_dev, a.max_seq, a.rope_cos, a.rope_sin));
     } else {
+      RUN(rope_kvcache_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, a.batch, a.seq, a.heads, hd, a.pos0, a.rope_cos,
+                           a.rope_sin, dt, s, pos_dev));
       AttnArgs at{};
       at.q = qkv; at.q_bs = static_cast<int64_t>(a.seq) * 3 * H; at.q_rs = 3 * H; at.q_hs = hd;
       at.k = kc; at.k_bs = cache_bs; at.k_rs = hd; at.k_hs = cache_hs;

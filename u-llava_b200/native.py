@@ -102,6 +102,8 @@ _SIGNATURES = {
     "ullava_set_weight_prefetch": (_i32, [_vp, _i32]),
     "ullava_attention_decode": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32,
                                        _f32, _i32, _vp]),
+    "ullava_attention_decode_rope": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp,
+                                            _i32, _vp, _vp, _f32, _i32, _vp]),
     "ullava_rope_kvcache": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                    _i32, _vp]),
     "ullava_vit_im2col": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -358,6 +360,19 @@ class Context:
             self.handle, q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0),
             k_cache.stride(1), out.data_ptr(), out.stride(0), B, H, D, int(ctx_len),
             float(scale if scale is not None else D ** -0.5), dtype_code(q.dtype), _stream()))
+        return out
+
+    def attention_decode_rope(self, qkv, k_cache, v_cache, ctx_len, cos, sin, pos_dev=None, scale=None, out=None):
+        """Fused decode step: RoPE(q, k) of the new token, KV-cache write at row ctx_len - 1, single-query attention.
+        qkv: [B, 3 * H * D] packed; caches [B, H, max_seq, D]; cos / sin fp32 [max_seq, D / 2]."""
+        B, H, max_seq, D = k_cache.shape
+        if out is None:
+            out = torch.empty((B, H * D), dtype=qkv.dtype, device=qkv.device)
+        self._chk(self.lib.ullava_attention_decode_rope(
+            self.handle, qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0),
+            k_cache.stride(1), out.data_ptr(), out.stride(0), B, H, D, int(ctx_len), _ptr(pos_dev), max_seq,
+            cos.data_ptr(), sin.data_ptr(), float(scale if scale is not None else D ** -0.5), dtype_code(qkv.dtype),
+            _stream()))
         return out
 
     def rope_kvcache(self, qkv, k_cache, v_cache, batch, seq, pos0, cos, sin):
