@@ -33,6 +33,50 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(native.DecodeArgs) > C.sizeof(native.LlamaArgs)
 
 
+def test_header_is_plain_c_and_ctypes_mirrors_match_field_for_field(tmp_path):
+    """include/ullava_sm100.h compiles as C99 with gcc (no CUDA, no C++), and every ctypes.Structure in native.py has
+    the size AND the per-field offsets the C compiler gives the struct it mirrors."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import native
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"ullava_gemm_args": native.GemmArgs, "ullava_attn_args": native.AttnArgs,
+             "ullava_sam_decoder_args": native.SamDecoderArgs, "ullava_vit_args": native.VitArgs,
+             "ullava_sam_encoder_args": native.SamEncoderArgs, "ullava_llama_args": native.LlamaArgs,
+             "ullava_decode_args": native.DecodeArgs}
+    hdr = open(os.path.join(ROOT, "include", "ullava_sm100.h")).read()
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ullava_sm100.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                fields.append(re.findall(r"(\w+)\s*$", part.strip())[0])
+        assert fields == [f[0] for f in cls._fields_], (cname, fields, [f[0] for f in cls._fields_])
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        cls = pairs[name]
+        assert C.sizeof(cls) == int(size), (name, C.sizeof(cls), size)
+        assert [getattr(cls, f[0]).offset for f in cls._fields_] == [int(o) for o in offs], name
+
+
 def test_no_cuda_means_loud_failure():
     import native
     if torch.cuda.is_available():
