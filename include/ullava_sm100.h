@@ -181,11 +181,13 @@ ULLAVA_API int ullava_attention_decode(ullava_ctx* ctx, const void* q, int64_t q
  * single-query attention over rows 0 .. ctx_len - 1, in one kernel (what ullava_rope_kvcache followed by
  * ullava_attention_decode compute for seq == 1; ullava_llama_forward / _decode_step use this form).
  * qkv: packed [B, 3 * heads * head_dim] rows (row stride ld_qkv); rope_cos / rope_sin fp32 [max_seq, head_dim / 2];
- * pos_dev (optional): device int32, ctx_len = *pos_dev + 1 (CUDA-graph replay; max_seq then bounds the score buffer). */
+ * pos_dev (optional): device int32, ctx_len = *pos_dev + 1 (CUDA-graph replay; max_seq then bounds the score buffer);
+ * pos_offset (optional): device int32 [B], added to ctx_len per sample (see ullava_llama_args.pos_offset). */
 ULLAVA_API int ullava_attention_decode_rope(ullava_ctx* ctx, const void* qkv, int64_t ld_qkv, void* k_cache, void* v_cache,
                                  int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
                                  int32_t head_dim, int32_t ctx_len, const int32_t* pos_dev, int32_t max_seq,
-                                 const float* rope_cos, const float* rope_sin, float scale, int32_t dtype, void* stream);
+                                 const float* rope_cos, const float* rope_sin, const int32_t* pos_offset, float scale,
+                                 int32_t dtype, void* stream);
 
 /* RoPE (rotate-half, hf:models/llama/modeling_llama.py:74-168) applied to the q and k thirds of a
  * packed QKV buffer [rows, 3*heads*head_dim]; rotated k and the untouched v are scattered into the
@@ -310,6 +312,11 @@ typedef struct ullava_llama_args {
   float eps;
   const float* rope_cos; const float* rope_sin; /* fp32 [max_seq, head_dim/2] */
   int32_t dtype;
+  /* decode only (seq == 1), optional: device int32 [B]; sample b's token sits at KV / RoPE position
+   * pos + pos_offset[b] (<= 0).  Lets one batch hold right-padded prompts of different lengths: the prefill runs on
+   * the padded [B, P] block (causal attention keeps valid positions exact), then every sample continues right after
+   * ITS last valid token (the reference generates one prompt at a time, models/ullava.py:350-362). */
+  const int32_t* pos_offset;
 } ullava_llama_args;
 ULLAVA_API int ullava_llama_forward(ullava_ctx* ctx, const ullava_llama_args* args, void* stream);
 ULLAVA_API size_t ullava_llama_scratch_bytes(int32_t rows, int32_t hidden_size, int32_t ffn);

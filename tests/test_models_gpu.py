@@ -114,6 +114,37 @@ def test_generate_matches_stepping_and_collects_hidden(ctx, dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("use_criteria", [False, True])
+def test_generate_right_padded_batch_equals_per_prompt_oracle(ctx, dtype, use_criteria):
+    """Prompts of different lengths in ONE right-padded batch (the reference collator's layout, attention_mask =
+    ids != pad): every sample continues right after its own last valid token, i.e. it generates what the oracle
+    generates for that prompt alone (KV / RoPE positions = the unpadded ones).  Both loops: the graph-replayed device
+    loop and the per-step host loop used with stopping_criteria."""
+    m, sd, cfg = build_tiny_core(dtype)
+    ids, images = oracle_inputs_core(2)
+    L, new, cut = ids.shape[1], 6, 3
+    short = ids[1, : L - cut]
+    padded = ids.clone()
+    padded[1, L - cut:] = 0                                            # pad_token_id of the tiny config
+    mask = padded != 0
+    kw = dict(stopping_criteria=[lambda seqs, scores: False]) if use_criteria else {}
+    out = m.generate(input_ids=padded.cuda(), attention_mask=mask.cuda(), images=images.cuda().to(dtype),
+                     max_new_tokens=new, do_sample=False, output_hidden_states=True, return_dict_in_generate=True,
+                     eos_token_id=-1, **kw)
+    seqs, hidden = out.sequences.cpu(), out.hidden_states[-1][-1].float().cpu()
+    assert seqs.shape == (2, L + new) and torch.equal(seqs[:, :L], padded)
+    for b, prompt in ((0, ids[0]), (1, short)):
+        o_seqs, o_hid, margins = O.greedy_generate(sd, cfg, prompt[None], images[b:b + 1], new)
+        P = prompt.shape[0]
+        if bool((margins > 2 * tol(dtype)).all()):
+            assert torch.equal(seqs[b, L:], o_seqs[0, P:]), (b, seqs[b, L:], o_seqs[0, P:])
+            # state that predicted generated token t sits at column L - 1 + t here, at position P - 1 + t in the oracle
+            assert max_err(hidden[b, L - 1:], o_hid[0, P - 1:]) < tol(dtype, 3e-2)
+    # same call without padding information would attend the pad tokens: the mask must matter for the short row
+    assert bool((seqs[1, L:] >= 0).all())
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_tiny_full_inference_forward(ctx, dtype):
     """UllavaForCausalLM.forward(inference=True): logits, masks and boxes vs the real reference (golden)."""
     g, meta = load_golden("tiny_full")

@@ -629,10 +629,11 @@ __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const T* __restrict__ q, int64_t q_bs, T* __restrict__ kc, T* __restrict__ vc,
                    int64_t cache_bs, int64_t cache_hs, T* __restrict__ o, int64_t o_bs, int ctx_len,
                    float scale_log2, const int32_t* __restrict__ ctx_dev, const float* __restrict__ cos_t,
-                   const float* __restrict__ sin_t, int qkv_hd) {
+                   const float* __restrict__ sin_t, int qkv_hd, const int32_t* __restrict__ ctx_off) {
   pdl_launch_dependents();  // the o-projection GEMM may start prefetching its weights under this kernel
   pdl_wait();               // launched with programmatic serialization: resident before its predecessor ends
   if (ctx_dev) ctx_len = *ctx_dev + 1;  // CUDA-graph decode: keys 0..pos are attended, pos read from device memory
+  if (ctx_off) ctx_len += ctx_off[blockIdx.y];  // per-sample offset (<= 0): right-padded prompts of different lengths
   extern __shared__ float dec_smem[];   // [ctx_len] scores, then [groups][HD] partial outputs
   __shared__ float red[DEC_THREADS / 32];
   __shared__ float bcast[2];
@@ -841,7 +842,7 @@ template <typename T, int HD, bool kRope>
 static int decode_launch_k(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                            int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
                            cudaStream_t stream, const int32_t* ctx_dev, int max_ctx, bool pdl, const float* cos_t,
-                           const float* sin_t) {
+                           const float* sin_t, const int32_t* ctx_off) {
   constexpr int GROUPS = DEC_THREADS / (HD / 8);
   const int smem_ctx = ctx_dev ? max_ctx : ctx_len;  // with a device-side length the buffer covers the whole cache
   size_t smem = sizeof(float) * static_cast<size_t>(smem_ctx > GROUPS * HD ? smem_ctx : GROUPS * HD);
@@ -853,7 +854,7 @@ static int decode_launch_k(const void* q, int64_t q_bs, const void* kc, const vo
   return check_cuda(launch_pdl(kern, grid, dim3(DEC_THREADS), smem, stream, pdl, static_cast<const T*>(q), q_bs,
                                static_cast<T*>(const_cast<void*>(kc)), static_cast<T*>(const_cast<void*>(vc)), cache_bs,
                                cache_hs, static_cast<T*>(o), o_bs, ctx_len, scale * 1.4426950408889634f, ctx_dev, cos_t,
-                               sin_t, heads * HD),
+                               sin_t, heads * HD, ctx_off),
                     "attn_decode launch");
 }
 
@@ -861,19 +862,19 @@ template <typename T, int HD>
 static int decode_launch(const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int ctx_len, float scale,
                          cudaStream_t stream, const int32_t* ctx_dev, int max_ctx, bool pdl,
-                         const float* cos_t = nullptr, const float* sin_t = nullptr) {
+                         const float* cos_t = nullptr, const float* sin_t = nullptr, const int32_t* ctx_off = nullptr) {
   if (cos_t != nullptr)
     return decode_launch_k<T, HD, true>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale,
-                                        stream, ctx_dev, max_ctx, pdl, cos_t, sin_t);
+                                        stream, ctx_dev, max_ctx, pdl, cos_t, sin_t, ctx_off);
   return decode_launch_k<T, HD, false>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream,
-                                       ctx_dev, max_ctx, pdl, nullptr, nullptr);
+                                       ctx_dev, max_ctx, pdl, nullptr, nullptr, ctx_off);
 }
 
 // rope_cos / rope_sin != nullptr: fused RoPE + KV-cache write of the new token (q = packed qkv row, see the kernel)
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
                          float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev, int max_ctx,
-                         const float* rope_cos, const float* rope_sin) {
+                         const float* rope_cos, const float* rope_sin, const int32_t* ctx_offset) {
   if (ctx_dev) ctx_len = max_ctx;
   ULLAVA_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "attention_decode: cos and sin go together");
   ProfScope _ps(ctx, stream, ULLAVA_PROF_ATTN_DECODE, 4.0 * batch * heads * (double)ctx_len * head_dim, 4.0 * batch * heads * (double)ctx_len * head_dim);
@@ -884,7 +885,7 @@ int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* 
   int st;
 #define ULLAVA_DEC(TT, HDIM) \
   st = decode_launch<TT, HDIM>(q, q_bs, kc, vc, cache_bs, cache_hs, o, o_bs, batch, heads, ctx_len, scale, stream, \
-                               ctx_dev, max_ctx, ctx->pdl != 0, rope_cos, rope_sin)
+                               ctx_dev, max_ctx, ctx->pdl != 0, rope_cos, rope_sin, ctx_offset)
   if (dtype == DT_BF16) {
     if (head_dim == 128) ULLAVA_DEC(__nv_bfloat16, 128);
     else if (head_dim == 64) ULLAVA_DEC(__nv_bfloat16, 64);

@@ -54,13 +54,14 @@ int ullava_set_pdl(ullava_ctx* ctx, int32_t enabled) {
 int ullava_attention_decode_rope(ullava_ctx* ctx, const void* qkv, int64_t ld_qkv, void* k_cache, void* v_cache,
                                  int64_t cache_bs, int64_t cache_hs, void* o, int64_t o_bs, int32_t batch, int32_t heads,
                                  int32_t head_dim, int32_t ctx_len, const int32_t* pos_dev, int32_t max_seq,
-                                 const float* rope_cos, const float* rope_sin, float scale, int32_t dtype, void* stream) {
+                                 const float* rope_cos, const float* rope_sin, const int32_t* pos_offset, float scale,
+                                 int32_t dtype, void* stream) {
   CTX_CHECK("ullava_attention_decode_rope");
   if (!rope_cos || !rope_sin) { set_last_error("ullava_attention_decode_rope: rope tables are NULL"); return ERR_BAD_ARG; }
   if (pos_dev == nullptr && ctx_len > max_seq) { set_last_error("ullava_attention_decode_rope: ctx_len > max_seq"); return ERR_BAD_ARG; }
   return attention_decode_run(ctx, qkv, ld_qkv, k_cache, v_cache, cache_bs, cache_hs, o, o_bs, batch, heads, head_dim,
                               ctx_len, scale, dtype, static_cast<cudaStream_t>(stream), pos_dev, max_seq, rope_cos,
-                              rope_sin);
+                              rope_sin, pos_offset);
 }
 
 int ullava_gemm_next_weight(ullava_ctx* ctx, const void* next_weight, int32_t n, int32_t k, int64_t ldb) {

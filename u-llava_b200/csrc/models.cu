@@ -136,6 +136,7 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
   ULLAVA_REQUIRE(a.pos0 >= 0 && a.pos0 + a.seq <= a.max_seq, "llama_forward: positions %d..%d exceed the KV cache (%d)",
                  a.pos0, a.pos0 + a.seq, a.max_seq);
   ULLAVA_REQUIRE(a.ffn % 16 == 0, "llama_forward: ffn must be a multiple of 16");
+  ULLAVA_REQUIRE(a.pos_offset == nullptr || a.seq == 1, "llama_forward: pos_offset applies to the decode step (seq == 1)");
   const int rows = a.batch * a.seq, H = a.hidden_size, F = a.ffn, hd = a.head_dim;
   if (rows == 0) return OK;
   Arena ar(a.scratch, a.scratch_bytes);
@@ -165,7 +166,7 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
     if (a.seq == 1) {
       // decode step: RoPE of the new q / k and the KV-cache write are fused into the single-query attention kernel
       RUN(attention_decode_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, att, H, a.batch, a.heads, hd, a.pos0 + 1,
-                               scale, dt, s, pos_dev, a.max_seq, a.rope_cos, a.rope_sin));
+                               scale, dt, s, pos_dev, a.max_seq, a.rope_cos, a.rope_sin, a.pos_offset));
     } else {
       RUN(rope_kvcache_run(ctx, qkv, 3 * H, kc, vc, cache_bs, cache_hs, a.batch, a.seq, a.heads, hd, a.pos0, a.rope_cos,
                            a.rope_sin, dt, s, pos_dev));

@@ -84,7 +84,8 @@ int attention_relpos_run(Context* ctx, const AttnArgs& a, const void* rel_h, con
 int attention_decode_run(Context* ctx, const void* q, int64_t q_bs, const void* kc, const void* vc, int64_t cache_bs,
                          int64_t cache_hs, void* o, int64_t o_bs, int batch, int heads, int head_dim, int ctx_len,
                          float scale, int dtype, cudaStream_t stream, const int32_t* ctx_dev = nullptr,
-                         int max_ctx = 0, const float* rope_cos = nullptr, const float* rope_sin = nullptr);
+                         int max_ctx = 0, const float* rope_cos = nullptr, const float* rope_sin = nullptr,
+                         const int32_t* ctx_offset = nullptr);
 
 // fmha_sm100.cu -- tcgen05/TMEM flash attention (hd 64 / 80 / 128); rel_h == nullptr: no rel-pos bias
 bool fmha_supported(const AttnArgs& a, bool relpos, int S);

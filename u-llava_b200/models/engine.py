@@ -194,7 +194,8 @@ class LlamaStack:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._scratch
 
-    def run(self, ctx, hidden: torch.Tensor, cache: KVCache, batch: int, seq: int, want_all_hidden=False):
+    def run(self, ctx, hidden: torch.Tensor, cache: KVCache, batch: int, seq: int, want_all_hidden=False,
+            pos_offset=None):
         """hidden [batch*seq, H] is updated in place to the last layer's output; returns
         (final_norm_out [batch*seq, H], all_hidden [layers, batch*seq, H] or None)."""
         self.ensure()
@@ -207,7 +208,8 @@ class LlamaStack:
         if want_all_hidden:
             allh = torch.empty((self.cfg["layers"],) + tuple(hidden.shape), dtype=hidden.dtype, device=hidden.device)
         ctx.llama_forward(self.table, len(self.tensors), hidden, cache.k, cache.v, self.scratch(ctx, batch * seq),
-                          batch, seq, pos0, self.cfg, cos, sin, final_out=final, all_hidden=allh)
+                          batch, seq, pos0, self.cfg, cos, sin, final_out=final, all_hidden=allh,
+                          pos_offset=pos_offset if seq == 1 else None)
         cache.length = pos0 + seq
         return final, allh
 
@@ -231,6 +233,8 @@ class DecodeSession:
         self.logits = torch.empty((batch, V), dtype=torch.float32, device=dev)
         self.cur_ids = torch.zeros((batch,), dtype=torch.int64, device=dev)
         self.pos = torch.zeros((1,), dtype=torch.int32, device=dev)
+        # per-sample KV / RoPE position = pos + pos_offset[b] (<= 0): right-padded prompts of different lengths
+        self.pos_offset = torch.zeros((batch,), dtype=torch.int32, device=dev)
         self.finished = torch.zeros((batch,), dtype=torch.uint8, device=dev)
         self.seqs = torch.zeros((batch, max_seq), dtype=torch.int64, device=dev)
         self.hid_buf = torch.empty((batch, max_seq - 1, H), dtype=dt, device=dev) if keep_hidden else None
@@ -248,7 +252,7 @@ class DecodeSession:
         a = native.DecodeArgs()
         self.ctx.fill_llama_args(a.llama, self.stack.table, len(self.stack.tensors), self.hidden, self.cache.k,
                                  self.cache.v, self.scratch, self.batch, 1, 0, self.stack.cfg, cos, sin,
-                                 final_out=self.final)
+                                 final_out=self.final, pos_offset=self.pos_offset)
         a.pos_dev = self.pos.data_ptr()
         a.embed_table, a.vocab, a.lm_head = self.embed_table.data_ptr(), self.lm_head.shape[0], self.lm_head.data_ptr()
         a.cur_ids, a.logits = self.cur_ids.data_ptr(), self.logits.data_ptr()
@@ -261,9 +265,14 @@ class DecodeSession:
             a.temperature, a.top_p = float(self.sampling[0]), float(self.sampling[1])
         self.args = a
 
-    def begin(self, input_ids: torch.Tensor, eos_id, pad_id: int, sampling=None, generator=None):
+    def begin(self, input_ids: torch.Tensor, eos_id, pad_id: int, sampling=None, generator=None, lengths=None):
         """sampling: None (greedy) or (temperature, top_p); the uniforms of every position are drawn here, once per
-        generate() call, from `generator` (torch's default CUDA generator when None)."""
+        generate() call, from `generator` (torch's default CUDA generator when None).  lengths (optional, [B] on the
+        device): valid prompt lengths of a right-padded batch; sample b then continues at position lengths[b]."""
+        if lengths is None:
+            self.pos_offset.zero_()
+        else:
+            self.pos_offset.copy_((lengths - input_ids.shape[1]).to(torch.int32))
         eos = -1 if eos_id is None else int(eos_id)
         if sampling is not None:
             sampling = (float(sampling[0]), float(sampling[1]) if sampling[1] is not None else 1.0)

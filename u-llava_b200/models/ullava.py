@@ -192,7 +192,9 @@ class UllavaForCausalLM(PreTrainedModel):
                 "logits": output.logits}
 
     def evaluate(self, images_sam, images, input_ids, raw_size_list, resize_list, max_new_tokens=32, temperature=0.2,
-                 top_p=None, num_beams=1, no_repeat_ngram_size=None, stopping_criteria=None):
+                 top_p=None, num_beams=1, no_repeat_ngram_size=None, stopping_criteria=None, attention_mask=None):
+        """Reference signature (models/ullava.py:335-345) plus `attention_mask` (optional): a right-padded batch of
+        prompts of different lengths, as the reference collator builds it (dataset/collators/base_collator.py:28-44)."""
         with torch.inference_mode():
             self._mark("start")
             self.llm.timeline = self.timeline
@@ -200,7 +202,7 @@ class UllavaForCausalLM(PreTrainedModel):
                                         num_beams=num_beams, top_p=top_p, do_sample=True if temperature > 0 else False,
                                         temperature=temperature, output_hidden_states=True,
                                         return_dict_in_generate=True, no_repeat_ngram_size=no_repeat_ngram_size,
-                                        stopping_criteria=stopping_criteria)
+                                        stopping_criteria=stopping_criteria, attention_mask=attention_mask)
             output_ids = outputs.sequences
             last_hidden = outputs.hidden_states[-1][-1]
             self.llm.timeline = None

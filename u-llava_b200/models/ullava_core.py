@@ -319,6 +319,15 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             if pad_token_id is None:
                 pad_token_id = eos_token_id if eos_token_id is not None else 0
         self._check_mask(attention_mask, B, P)
+        # Right-padded prompts of different lengths in one batch (the reference generates one prompt at a time): the
+        # prefill runs on the padded block, every sample then continues right after ITS last valid token.  Returned
+        # sequences keep the HF layout [prompt | pads | new tokens]; hidden_states[-1][-1][:, j] is the state that
+        # predicted token j + 1 for every generated token (column P - 1 holds the state of the last valid position).
+        lengths = None
+        if attention_mask is not None and attention_mask.shape[-1] == P and not bool(attention_mask.bool().all()):
+            lengths = attention_mask.bool().sum(1).to(torch.int32)
+            if int(lengths.min()) < 1:
+                raise ValueError("every prompt needs at least one valid token")
         H = self.config.hidden_size
         T = P + max_new_tokens
         greedy = not (do_sample and temperature and temperature > 0)
@@ -326,7 +335,8 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         if stopping_criteria is None and max_new_tokens >= 1:
             return self._generate_greedy_device(ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id,
                                                 pad_token_id, output_hidden_states, return_dict_in_generate,
-                                                sampling=sampling, generator=generator)
+                                                sampling=sampling, generator=generator, lengths=lengths)
+        pos_offset = None if lengths is None else (lengths - P).to(torch.int32)
         cache = stack.new_cache(B, T)
         table = self.model.embed_tokens.weight.detach()
         w = self.lm_head.weight.detach()
@@ -344,7 +354,12 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         seqs = torch.full((B, T), pad_token_id, dtype=torch.int64, device=input_ids.device)
         seqs[:, :P] = input_ids
         logits = torch.empty((B, V), dtype=torch.float32, device=final.device)
-        last = final.view(B, P, H)[:, -1].contiguous()
+        if lengths is None:
+            last = final.view(B, P, H)[:, -1].contiguous()
+        else:
+            last = final.view(B, P, H)[torch.arange(B, device=final.device), (lengths - 1).long()].contiguous()
+            if hid_buf is not None:
+                hid_buf[:, P - 1] = last
         finished = torch.zeros((B,), dtype=torch.bool, device=final.device)
         step_hidden = torch.empty((B, H), dtype=final.dtype, device=final.device)
         n_done = T
@@ -371,7 +386,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
                 n_done = P + t + 1
                 break
             step_in = ctx.embed_gather(nxt, table, out=step_hidden)
-            final, _ = stack.run(ctx, step_in, cache, B, 1)
+            final, _ = stack.run(ctx, step_in, cache, B, 1, pos_offset=pos_offset)
             if hid_buf is not None:
                 hid_buf[:, P + t] = final
             last = final
@@ -384,7 +399,8 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=cache)
 
     def _generate_greedy_device(self, ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id, pad_token_id,
-                                output_hidden_states, return_dict_in_generate, sampling=None, generator=None):
+                                output_hidden_states, return_dict_in_generate, sampling=None, generator=None,
+                                lengths=None):
         """Greedy (or, with `sampling` = (temperature, top_p), sampling) loop with all per-step state on the device:
         prefill, then max_new_tokens-1 replays of ONE
         captured decode-step graph (the position is read from device memory).  The host only synchronises to
@@ -395,14 +411,17 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         table = self.model.embed_tokens.weight.detach()
         w = self.lm_head.weight.detach()
         sess = stack.decode_session(ctx, B, T, table, w, bool(output_hidden_states))
-        sess.begin(input_ids, eos_token_id, pad_token_id, sampling=sampling, generator=generator)
+        sess.begin(input_ids, eos_token_id, pad_token_id, sampling=sampling, generator=generator, lengths=lengths)
         _, embeds = self.embed_images_videos(input_ids, images, videos)
         self._mark("vit_projector_splice")
         final, _ = stack.run(ctx, embeds.view(B * P, H), sess.cache, B, P)
         if sess.hid_buf is not None:
             ctx.copy_rows(final, sess.hid_buf, B, P, H, P * H, H, sess.hid_buf.stride(0), H)
         self._mark("prefill")
-        last = final.view(B, P, H)[:, -1].contiguous()
+        if lengths is None:
+            last = final.view(B, P, H)[:, -1].contiguous()
+        else:   # last VALID position of every row; first_token() also stores it as the state of column P - 1
+            last = final.view(B, P, H)[torch.arange(B, device=final.device), (lengths - 1).long()].contiguous()
         sess.first_token(last, P)
         remaining = max_new_tokens - 1
         n_tokens = 1

@@ -71,7 +71,7 @@ class LlamaArgs(C.Structure):
                 ("all_hidden", _vp), ("k_cache", _vp), ("v_cache", _vp), ("scratch", _vp), ("scratch_bytes", _sz),
                 ("batch", _i32), ("seq", _i32), ("pos0", _i32), ("max_seq", _i32),
                 ("layers", _i32), ("hidden_size", _i32), ("heads", _i32), ("head_dim", _i32), ("ffn", _i32),
-                ("eps", _f32), ("rope_cos", _vp), ("rope_sin", _vp), ("dtype", _i32)]
+                ("eps", _f32), ("rope_cos", _vp), ("rope_sin", _vp), ("dtype", _i32), ("pos_offset", _vp)]
 
 
 class DecodeArgs(C.Structure):
@@ -103,7 +103,7 @@ _SIGNATURES = {
     "ullava_attention_decode": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32,
                                        _f32, _i32, _vp]),
     "ullava_attention_decode_rope": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp,
-                                            _i32, _vp, _vp, _f32, _i32, _vp]),
+                                            _i32, _vp, _vp, _vp, _f32, _i32, _vp]),
     "ullava_rope_kvcache": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                    _i32, _vp]),
     "ullava_vit_im2col": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -362,7 +362,8 @@ class Context:
             float(scale if scale is not None else D ** -0.5), dtype_code(q.dtype), _stream()))
         return out
 
-    def attention_decode_rope(self, qkv, k_cache, v_cache, ctx_len, cos, sin, pos_dev=None, scale=None, out=None):
+    def attention_decode_rope(self, qkv, k_cache, v_cache, ctx_len, cos, sin, pos_dev=None, scale=None, out=None,
+                              pos_offset=None):
         """Fused decode step: RoPE(q, k) of the new token, KV-cache write at row ctx_len - 1, single-query attention.
         qkv: [B, 3 * H * D] packed; caches [B, H, max_seq, D]; cos / sin fp32 [max_seq, D / 2]."""
         B, H, max_seq, D = k_cache.shape
@@ -371,8 +372,8 @@ class Context:
         self._chk(self.lib.ullava_attention_decode_rope(
             self.handle, qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0),
             k_cache.stride(1), out.data_ptr(), out.stride(0), B, H, D, int(ctx_len), _ptr(pos_dev), max_seq,
-            cos.data_ptr(), sin.data_ptr(), float(scale if scale is not None else D ** -0.5), dtype_code(qkv.dtype),
-            _stream()))
+            cos.data_ptr(), sin.data_ptr(), _ptr(pos_offset), float(scale if scale is not None else D ** -0.5),
+            dtype_code(qkv.dtype), _stream()))
         return out
 
     def rope_kvcache(self, qkv, k_cache, v_cache, batch, seq, pos0, cos, sin):
@@ -605,7 +606,7 @@ class Context:
         return out
 
     def fill_llama_args(self, a: "LlamaArgs", weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq,
-                        pos0, cfg: dict, rope_cos, rope_sin, final_out=None, all_hidden=None):
+                        pos0, cfg: dict, rope_cos, rope_sin, final_out=None, all_hidden=None, pos_offset=None):
         a.weights, a.n_weights = weight_table, n_weights
         a.hidden, a.final_out, a.all_hidden = hidden.data_ptr(), _ptr(final_out), _ptr(all_hidden)
         a.k_cache, a.v_cache = k_cache.data_ptr(), v_cache.data_ptr()
@@ -616,11 +617,13 @@ class Context:
         a.eps = cfg["eps"]
         a.rope_cos, a.rope_sin = rope_cos.data_ptr(), rope_sin.data_ptr()
         a.dtype = dtype_code(hidden.dtype)
+        a.pos_offset = _ptr(pos_offset)
         return a
 
     def llama_forward(self, weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq, pos0, cfg: dict,
-                      rope_cos, rope_sin, final_out=None, all_hidden=None):
+                      rope_cos, rope_sin, final_out=None, all_hidden=None, pos_offset=None):
         a = LlamaArgs()
+        a.pos_offset = _ptr(pos_offset)
         a.weights, a.n_weights = weight_table, n_weights
         a.hidden, a.final_out, a.all_hidden = hidden.data_ptr(), _ptr(final_out), _ptr(all_hidden)
         a.k_cache, a.v_cache = k_cache.data_ptr(), v_cache.data_ptr()
