@@ -488,6 +488,19 @@ def run_b200(args):
                                    "frac": a_s / peaks["hbm_gbs"], "traffic": (traffic or {}).get("gemm_stream"),
                                    "launches": gs["launches"], "avg_launch_ms": gs["ms"] / max(gs["launches"], 1),
                                    "peak_source": peaks_src}
+        if stages and "decode" in stages:
+            # the decode stage as a whole against the HBM roofline: per generated token every LLaMA weight (fused
+            # qkv, o, gate/up, down, lm_head) and the K/V rows 0..pos of every layer are read once
+            hs, ff, nl = LLM["hidden_size"], LLM["intermediate_size"], LLM["num_hidden_layers"]
+            w_bytes = 2.0 * (nl * (4 * hs * hs + 3 * hs * ff) + VOCAB * hs)
+            steps = max(args.new_tokens - 1, 0)          # the first token comes from the prefill
+            kv_bytes = sum(B * nl * 2.0 * (P_LEN + t + 1) * hs * 2.0 for t in range(steps))
+            dec_s = stages["decode"] / 1e3
+            gbs = (steps * w_bytes + kv_bytes) / dec_s / 1e9 if dec_s > 0 else 0.0
+            line["decode_stage"] = {"ms": round(stages["decode"], 3), "tokens": args.new_tokens, "gbs": round(gbs, 1),
+                                    "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 3),
+                                    "note": "in the CUDA graph (PDL overlap on): algorithmic weight + KV bytes of the "
+                                            "whole stage / its duration; includes lm_head, sampling and the first-token step"}
         if stages and "prefill" in stages and "vit_projector_splice" in stages:
             fl = B * (FLOP_VIT + FLOP_PROJ + FLOP_PREFILL_LAST)
             sec = (stages["prefill"] + stages["vit_projector_splice"]) / 1e3
