@@ -132,6 +132,11 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi spends its first second initialising NVML (driver locks that can stall kernel launches): let
+            # it deliver its first sample before the warm-up starts, so that only steady 200 ms polling overlaps the run
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

@@ -114,7 +114,16 @@ class UllavaForCausalLM(PreTrainedModel):
                          epilogue=native.EPI_RELU if i < len(lins) - 1 else native.EPI_NONE)
         return x
 
-    def _decode_heads(self, token_ids, hidden, image_embeddings, raw_size_list, resize_list, pack_bits=False):
+    def _seg_loc_counts(self, token_ids):
+        """[SEG] / [LOC] tokens per sample, on the host: the ONE synchronisation the mask / box heads need for their
+        control flow.  evaluate() takes it before it enqueues the SAM image encoder, so that the head kernels are
+        queued behind the encoder instead of after a round trip at its end."""
+        seg_mask = token_ids[:, 1:] == self.config.seg_token_idx
+        loc_mask = token_ids[:, 1:] == self.config.loc_token_idx
+        return torch.stack([seg_mask.sum(1), loc_mask.sum(1)], 0).cpu()
+
+    def _decode_heads(self, token_ids, hidden, image_embeddings, raw_size_list, resize_list, pack_bits=False,
+                      counts=None):
         """Shared tail of forward(inference=True) and evaluate (reference :168-256, :364-432).
         token_ids [B,T]; hidden [B,>=T-1,H] post-final-norm; position j is used when token j+1 is [SEG]/[LOC]."""
         ctx = native.Context.get(hidden.device)
@@ -123,7 +132,8 @@ class UllavaForCausalLM(PreTrainedModel):
         hid = hidden[:, : T - 1]
         seg_mask = token_ids[:, 1:] == self.config.seg_token_idx
         loc_mask = token_ids[:, 1:] == self.config.loc_token_idx
-        counts = torch.stack([seg_mask.sum(1), loc_mask.sum(1)], 0).cpu()  # one host sync for the control flow
+        if counts is None:
+            counts = self._seg_loc_counts(token_ids)  # one host sync for the control flow
         seg_counts, loc_counts = counts[0].tolist(), counts[1].tolist()
         sam = self.visual_model
         dt = hidden.dtype
@@ -207,10 +217,11 @@ class UllavaForCausalLM(PreTrainedModel):
             last_hidden = outputs.hidden_states[-1][-1]
             self.llm.timeline = None
             self._mark("decode")
+            counts = self._seg_loc_counts(output_ids)   # host sync here, while nothing else is queued
             image_embeddings = self.get_visual_embs(images_sam)
             self._mark("sam_encoder")
             pred_masks, pred_boxes, bits = self._decode_heads(output_ids, last_hidden, image_embeddings, raw_size_list,
-                                                              resize_list, pack_bits=self.pack_mask_bits)
+                                                              resize_list, pack_bits=self.pack_mask_bits, counts=counts)
             self.last_mask_bits = bits if self.pack_mask_bits else None
             self._mark("mask_heads")
         return output_ids, pred_masks, pred_boxes
