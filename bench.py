@@ -385,19 +385,36 @@ def run_b200(args):
         return out_ids, masks, gathered
 
     def timed(fn, warmup, steps):
+        # warm-up with the SAME liveness pattern as the timed loop (the previous step's outputs stay referenced while the
+        # next step runs): otherwise the caching allocator meets that footprint for the first time at the second timed
+        # step and grows the pool there (8-9 cudaMalloc calls, +60..300 ms on that one step)
+        r = None
         for _ in range(warmup):
-            fn()
+            r = fn()
         torch.cuda.synchronize()
         if ws > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         n0 = ctx.launch_count() + model.llm.graph_kernel_launches()
+        st0 = torch.cuda.memory_stats(dev)
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             r = fn()
+            marks[i].record()
         e1.record()
         torch.cuda.synchronize()
+        st1 = torch.cuda.memory_stats(dev)
+        prev = e0
+        step_ms = []
+        for m in marks:
+            step_ms.append(round(prev.elapsed_time(m), 1))
+            prev = m
+        timed.last_info = {"step_ms": step_ms,
+                           "cuda_mallocs": int(st1.get("num_device_alloc", 0) - st0.get("num_device_alloc", 0)),
+                           "cuda_frees": int(st1.get("num_device_free", 0) - st0.get("num_device_free", 0)),
+                           "alloc_retries": int(st1.get("num_alloc_retries", 0) - st0.get("num_alloc_retries", 0))}
         if ws > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -415,8 +432,10 @@ def run_b200(args):
     if rank == 0 and not os.environ.get("ULLAVA_BENCH_NO_CLOCKS"):
         sampler.start()
     ms_res, launches, res = timed(step_resident, args.warmup, args.steps)
+    info_res = timed.last_info
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _, res2 = timed(step_e2e, 1, args.steps)
+    ms_e2e, _, res2 = timed(step_e2e, 2, args.steps)
+    info_e2e = timed.last_info
 
     out_ids, masks, gathered = res
     assert out_ids.shape == (B, T), out_ids.shape
@@ -467,7 +486,7 @@ def run_b200(args):
             "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h_ids.numel() * 8 + h_img.numel() * 2 + h_sam.numel() * 2),
                     "d2h_bytes_per_step": int(h_out_ids.numel() * 8 + h_masks.numel() * 4 + h_gather.numel() * 4)},
-            "masks_per_step": n_masks}
+            "masks_per_step": n_masks, "timed_region": info_res, "timed_region_e2e": info_e2e}
     if stages:
         line["stages_ms"] = {k: round(v, 3) for k, v in stages.items()}
     if prof:
