@@ -17,9 +17,12 @@
 //     of tile i overlaps the MMAs of tile i+1;
 //   * STAGES-deep shared-memory ring guarded by full/empty mbarriers; tcgen05.commit releases a
 //     slot when the MMAs that read it have retired;
-//   * small-M (decode) products run "swap-AB": the weight matrix is the 128-row operand and the
-//     (padded) batch is the UMMA N (16/32), with split-K so that >=148 CTAs stream weights from
-//     HBM; partials go to an fp32 workspace and splitk_reduce_kernel applies the epilogue.
+//   * gemm_tcgen05_pair_kernel: the same pipeline on CTA pairs (cta_group::2, clusters of 2 SMs) with 256 x 256
+//     tiles -- every product with >= 148 pair tiles (all ViT / prefill / SAM-encoder GEMMs) takes it;
+//   * rasterisation group chosen per shape: when B does not fit in L2 beside the A panel a taller M group cuts the
+//     DRAM re-reads of B;
+//   * small-M (decode, M <= 32) products go to the weight-streaming kernel of gemm_stream_sm100.cu; force_splits keeps
+//     a split-K flavour of the large-M kernel (fp32 workspace + splitk_reduce_kernel) for tests and odd shapes.
 #include "common.cuh"
 #include "ullava_internal.h"
 

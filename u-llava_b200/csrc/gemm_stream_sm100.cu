@@ -18,8 +18,13 @@
 //     whole shared-memory ring with W tiles BEFORE griddepcontrol.wait and only then loads X; launched with the
 //     programmatic-serialization attribute this overlaps pipeline fill with the previous kernel's tail (the
 //     norm / rope / attention kernels of the decode step call griddepcontrol.launch_dependents at their start).
-//   * 5-deep TMA ring (80 KB of W in flight per SM, two CTAs of consecutive GEMMs can share an SM), warp-specialised like the large-M kernel: warp 0 producer,
-//     warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue; accumulator double buffered in TMEM.
+//   * next-weight L2 prefetch: once its own loads are issued, each CTA pulls the tiles its successor (the next GEMM of
+//     the decode chain, hinted by ullava_gemm_next_weight) will ask for right after its ring fill into L2
+//     (cp.async.bulk.prefetch.tensor), so HBM stays busy through this kernel's reduction tail and the launch boundary;
+//   * 8-stage TMA ring (128 KB of W in flight per SM, one CTA per SM so that the next GEMM's CTAs map 1:1 onto SMs),
+//     warp-specialised like the large-M kernel: warp 0 producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+//     warps 4-7 epilogue; accumulator double buffered in TMEM; partial tiles are stored row-interleaved
+//     ([BN/4][128] float4) so that a warp's store / load is one contiguous 512-byte run.
 #include "common.cuh"
 #include "ullava_internal.h"
 
