@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ULLAVA_ABI_VERSION 1
+#define ULLAVA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ULLAVA_API __attribute__((visibility("default")))

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = native.load_library()  # dlopen; raises if the .so is missing (no fallback)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ullava_abi_version() == 1
+    assert lib.ullava_abi_version() == native.ABI_VERSION == int(re.search(r"#define ULLAVA_ABI_VERSION (\d+)", hdr).group(1))
 
 
 def test_struct_layouts_match_header_sizes():

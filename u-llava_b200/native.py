@@ -20,6 +20,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libullava_sm100.so")
 
+ABI_VERSION = 2   # ULLAVA_ABI_VERSION of include/ullava_sm100.h (struct layouts and signatures mirrored below)
 BF16, F16, F32 = 0, 1, 2
 EPI_NONE, EPI_RELU, EPI_GELU, EPI_QUICK_GELU, EPI_SILU_MUL = 0, 1, 2, 3, 4
 SAM_N_WEIGHTS = 121
@@ -166,7 +167,7 @@ def load_library():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.ullava_abi_version() != 1:
+        if lib.ullava_abi_version() != ABI_VERSION:
             raise RuntimeError("libullava_sm100.so ABI version mismatch")
         _lib = lib
         return lib
