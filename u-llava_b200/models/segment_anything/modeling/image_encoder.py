@@ -4,8 +4,9 @@ SURVEY.md section 8 row a12 / f1: the encoder is on the u-LLaVA path (models/ull
 ImageEncoderViT.forward runs ullava_sam_encoder_forward (csrc/sam_encoder.cu): tcgen05 GEMMs for the patch
 embedding, qkv / proj / MLP and the neck convolutions, flash attention with the decomposed relative-position
 bias for the windowed and global blocks.  The nn.Modules below keep the reference's parameters and
-state_dict keys, so SAM checkpoints load unchanged; their own forward() methods (plain torch ops) are NOT
-on the product path -- forward_torch() exists for tests that cross-check the kernels on a GPU.
+state_dict keys, so SAM checkpoints load unchanged; they are parameter containers: their own forward() methods
+raise (the blocks run fused inside ImageEncoderViT.forward), and there is no torch implementation of the encoder in
+this package -- the tests cross-check the kernels against oracle/ullava_oracle.py:sam_image_encoder.
 Images are processed as one batch (the reference loops image by image with empty_cache() calls)."""
 from typing import Optional, Tuple, Type
 
@@ -24,23 +25,8 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride, padding=padding)
 
     def forward(self, x):
-        return self.proj(x).permute(0, 2, 3, 1)  # B C H W -> B H W C
-
-
-def _rel_table(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tensor:
-    """[q_size, k_size, hd] lookup of the relative-position embedding (linear resize when the stored table has a
-    different length, as the reference does)."""
-    max_rel = 2 * max(q_size, k_size) - 1
-    if rel_pos.shape[0] != max_rel:
-        rp = F.interpolate(rel_pos.reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1).float(), size=max_rel,
-                           mode="linear").reshape(-1, max_rel).permute(1, 0).to(rel_pos.dtype)
-    else:
-        rp = rel_pos
-    dev = rel_pos.device
-    qc = torch.arange(q_size, device=dev)[:, None] * max(k_size / q_size, 1.0)
-    kc = torch.arange(k_size, device=dev)[None, :] * max(q_size / k_size, 1.0)
-    idx = (qc - kc) + (k_size - 1) * max(q_size / k_size, 1.0)
-    return rp[idx.long()]
+        raise RuntimeError("PatchEmbed runs fused inside ImageEncoderViT.forward (ullava_sam_encoder_forward: im2col + "
+                           "tcgen05 GEMM); this module only holds the parameters")
 
 
 class Attention(nn.Module):
@@ -59,19 +45,8 @@ class Attention(nn.Module):
             self.rel_pos_w = nn.Parameter(torch.zeros(2 * input_size[1] - 1, self.head_dim))
 
     def forward(self, x):
-        B, H, W, _ = x.shape
-        nh, hd = self.num_heads, self.head_dim
-        qkv = self.qkv(x).reshape(B, H * W, 3, nh, hd).permute(2, 0, 3, 1, 4)  # 3 B nh HW hd
-        q, k, v = qkv[0], qkv[1], qkv[2]
-        bias = None
-        if self.use_rel_pos:
-            rq = q.reshape(B, nh, H, W, hd)
-            rel_h = torch.einsum("bnhwc,hkc->bnhwk", rq, _rel_table(H, H, self.rel_pos_h))
-            rel_w = torch.einsum("bnhwc,wkc->bnhwk", rq, _rel_table(W, W, self.rel_pos_w))
-            bias = (rel_h[..., :, None] + rel_w[..., None, :]).reshape(B, nh, H * W, H * W)
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=self.scale)
-        o = o.permute(0, 2, 1, 3).reshape(B, H, W, nh * hd)
-        return self.proj(o)
+        raise RuntimeError("Attention runs fused inside ImageEncoderViT.forward (tcgen05 flash attention with the "
+                           "decomposed relative-position bias); this module only holds the parameters")
 
 
 class Block(nn.Module):
@@ -87,23 +62,8 @@ class Block(nn.Module):
         self.window_size = window_size
 
     def forward(self, x):
-        shortcut = x
-        x = self.norm1(x)
-        ws = self.window_size
-        if ws > 0:
-            B, H, W, C = x.shape
-            ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
-            if ph or pw:
-                x = F.pad(x, (0, 0, 0, pw, 0, ph))
-            Hp, Wp = H + ph, W + pw
-            x = x.view(B, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws, ws, C)
-        x = self.attn(x)
-        if ws > 0:
-            x = x.view(B, Hp // ws, Wp // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)
-            if ph or pw:
-                x = x[:, :H, :W].contiguous()
-        x = shortcut + x
-        return x + self.mlp(self.norm2(x))
+        raise RuntimeError("Block runs fused inside ImageEncoderViT.forward (ullava_sam_encoder_forward); this module "
+                           "only holds the parameters")
 
 
 class ImageEncoderViT(nn.Module):
@@ -221,12 +181,3 @@ class ImageEncoderViT(nn.Module):
             if x.shape[0] <= n:
                 return self._forward_native(x)
             return torch.cat([self._forward_native(x[i:i + n]) for i in range(0, x.shape[0], n)], 0)
-
-    # ---- plain torch ops, for GPU cross-checks in tests only ---------------------------------------------
-    def forward_torch(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.patch_embed(x)
-        if self.pos_embed is not None:
-            x = x + self.pos_embed
-        for blk in self.blocks:
-            x = blk(x)
-        return self.neck(x.permute(0, 3, 1, 2))
