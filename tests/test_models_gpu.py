@@ -321,7 +321,7 @@ def test_sam_image_encoder_tiny_vs_reference_golden(ctx, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16])
-def test_sam_image_encoder_vith_width_vs_torch_fp32(ctx, dtype):
+def test_sam_image_encoder_vith_width_vs_oracle_fp32(ctx, dtype):
     """ViT-H geometry (embed 1280, 16 heads of 80, window 14 with padding 64->70, one global 4096-token block):
     native kernels vs the oracle restatement (oracle/ullava_oracle.py:sam_image_encoder) evaluated in fp32 on the GPU
     (a 4096 x 4096 global block takes the host minutes)."""
