@@ -380,6 +380,17 @@ ULLAVA_API int ullava_seg_meter_update(ullava_ctx* ctx, const int32_t* counts, c
 ULLAVA_API int ullava_box_iou_diag(ullava_ctx* ctx, const void* pred, const void* gt, int32_t n, int32_t dtype, float* iou,
                         double* meter, void* stream);
 
+/* Shifted token cross-entropy of UllavaCoreForCausalLM.forward(labels=...) (models/ullava_core.py:327-338):
+ * mean over t < T - 1, labels[b, t + 1] != ignore_index, of logsumexp(logits[b, t, :]) - logits[b, t, labels[b, t+1]].
+ * logits: [batch, T, cols] fp32 (logits_f32 = 1) or 16-bit `dtype`, row stride ld_row, batch stride ld_batch
+ * (elements); labels int64 [batch, >= T] with row stride labels_ld.  out: device float[2] = {loss, valid tokens}
+ * (loss is NaN when every label is ignored, like torch).  scratch: ullava_cross_entropy_scratch_bytes. */
+ULLAVA_API size_t ullava_cross_entropy_scratch_bytes(int32_t batch, int32_t seq);
+ULLAVA_API int ullava_cross_entropy(ullava_ctx* ctx, const void* logits, int32_t logits_f32, int32_t dtype, int64_t ld_row,
+                         int64_t ld_batch, const int64_t* labels, int64_t labels_ld, int32_t batch, int32_t seq,
+                         int32_t cols, int32_t ignore_index, float* out, void* scratch, size_t scratch_bytes,
+                         void* stream);
+
 /* ---- image preprocessing on the device (dataset/processors/clip_processor.py, dataset/tools/mask_toolbox.py) ---
  * ullava_resize_u8: PIL.Image.resize of an RGB uint8 HWC image, bit-exact with Pillow's 8-bit resampler (separable,
  * antialiased, 22-bit fixed-point taps); filter 0 = BILINEAR (ResizeLongestSide.apply_image,

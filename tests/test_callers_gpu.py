@@ -133,6 +133,33 @@ def test_validate_batched_right_padded_equals_per_image(ctx):
     assert one[0] == ref["ciou"] and one[1] == ref["giou"] and one[2] == ref["prec05"], (one, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_cross_entropy_kernel_matches_torch(ctx, dtype):
+    """Shifted token cross-entropy (models/ullava_core.py:327-338) against torch.nn.functional.cross_entropy on the
+    same logits: ignore_index rows, a strided logits view, and the all-ignored NaN case."""
+    g = torch.Generator().manual_seed(12)
+    B, T, V = 3, 37, 32011
+    logits = (torch.randn((B, T, V), generator=g) * 3).to(dtype).cuda()
+    labels = torch.randint(0, V, (B, T), generator=g)
+    labels[0, :9] = -100
+    labels[2, 5::3] = -100
+    labels = labels.cuda()
+    ref = torch.nn.functional.cross_entropy(logits[:, :-1].float().reshape(-1, V), labels[:, 1:].reshape(-1))
+    got = ctx.cross_entropy(logits, labels)
+    assert abs(got.item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+    view = logits[:, :20]                                              # batch stride != T * V
+    ref_v = torch.nn.functional.cross_entropy(view[:, :-1].float().reshape(-1, V), labels[:, 1:20].reshape(-1))
+    assert abs(ctx.cross_entropy(view, labels).item() - ref_v.item()) < 2e-5 * max(1.0, abs(ref_v.item()))
+    assert torch.isnan(ctx.cross_entropy(logits, torch.full_like(labels, -100)))
+    # through the module API: forward(labels=...) returns the loss of its own logits
+    model, sd, cfg = build_tiny_core(torch.bfloat16)
+    ids, images = oracle_inputs_core(2)
+    out = model(input_ids=ids.cuda(), images=images.cuda().to(torch.bfloat16), labels=ids.cuda(), return_dict=True)
+    ref_m = torch.nn.functional.cross_entropy(out.logits[:, :-1].float().reshape(-1, out.logits.shape[-1]),
+                                              ids.cuda()[:, 1:].reshape(-1))
+    assert abs(out.loss.item() - ref_m.item()) < 1e-4 * max(1.0, abs(ref_m.item()))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # f3: preprocessing
 # ---------------------------------------------------------------------------------------------------------------

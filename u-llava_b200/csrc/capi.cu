@@ -233,6 +233,20 @@ int ullava_box_iou_diag(ullava_ctx* ctx, const void* pred, const void* gt, int32
   return box_iou_diag_run(ctx, pred, gt, n, dtype, iou, meter, static_cast<cudaStream_t>(stream));
 }
 
+size_t ullava_cross_entropy_scratch_bytes(int32_t batch, int32_t seq) {
+  if (batch <= 0 || seq <= 1) return 256;
+  return cross_entropy_scratch(batch, seq);
+}
+
+int ullava_cross_entropy(ullava_ctx* ctx, const void* logits, int32_t logits_f32, int32_t dtype, int64_t ld_row,
+                         int64_t ld_batch, const int64_t* labels, int64_t labels_ld, int32_t batch, int32_t seq,
+                         int32_t cols, int32_t ignore_index, float* out, void* scratch, size_t scratch_bytes,
+                         void* stream) {
+  CTX_CHECK("ullava_cross_entropy");
+  return cross_entropy_run(ctx, logits, logits_f32, dtype, ld_row, ld_batch, labels, labels_ld, batch, seq, cols,
+                           ignore_index, out, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t ullava_resize_u8_scratch_bytes(int32_t h, int32_t w, int32_t out_h, int32_t out_w) {
   if (h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0) return 0;
   return resize_u8_scratch(h, w, out_h, out_w);

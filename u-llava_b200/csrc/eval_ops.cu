@@ -236,4 +236,101 @@ int box_iou_diag_run(Context* ctx, const void* pred, const void* gt, int n, int 
   return check_cuda(cudaGetLastError(), "box_iou_diag launch");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Token cross-entropy of UllavaCoreForCausalLM.forward when labels are given (models/ullava_core.py:327-338:
+// CrossEntropyLoss() over logits[..., :-1, :] vs labels[..., 1:], mean over the labels != ignore_index).  The
+// inference callers discard it, but the reference computes it whenever labels are passed (validate() passes them),
+// so the drop-in does too -- on the device, without materialising log-softmax.
+//   ce_rows_kernel   : row r = (b, t), t < T - 1: loss = logsumexp(logits[b, t, :]) - logits[b, t, labels[b, t + 1]]
+//   ce_reduce_kernel : fixed-order sum of the row losses / number of valid rows (NaN if none, like torch)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct CeT { static __device__ __forceinline__ float ld(const T* p) { return T16<T>::to_f(*p); } };
+template <> struct CeT<float> { static __device__ __forceinline__ float ld(const float* p) { return *p; } };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const T* __restrict__ logits, int64_t ld_row, int64_t ld_batch, const int64_t* __restrict__ labels,
+               int64_t labels_ld, int T_len, int cols, int ignore_index, float* __restrict__ row_loss,
+               float* __restrict__ row_valid) {
+  const int r = blockIdx.x;
+  const int b = r / (T_len - 1), t = r - b * (T_len - 1);
+  const int64_t label = labels[b * labels_ld + t + 1];
+  if (label == ignore_index || label < 0 || label >= cols) {
+    if (threadIdx.x == 0) { row_loss[r] = 0.f; row_valid[r] = 0.f; }
+    return;
+  }
+  const T* row = logits + b * ld_batch + t * ld_row;
+  float m = -INFINITY, s = 0.f;   // online logsumexp
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = CeT<T>::ld(row + c);
+    if (v > m) { s = s * __expf(m - v) + 1.f; m = v; }
+    else s += __expf(v - m);
+  }
+  __shared__ float sm[8], ss[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - nm)) + (om == -INFINITY ? 0.f : os * __expf(om - nm));
+    m = nm;
+  }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = sm[0], S = ss[0];
+    for (int w = 1; w < 8; ++w) {
+      const float nm = fmaxf(M, sm[w]);
+      S = (M == -INFINITY ? 0.f : S * __expf(M - nm)) + (sm[w] == -INFINITY ? 0.f : ss[w] * __expf(sm[w] - nm));
+      M = nm;
+    }
+    row_loss[r] = M + __logf(S) - CeT<T>::ld(row + label);
+    row_valid[r] = 1.f;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+ce_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_valid, int rows,
+                 float* __restrict__ out) {
+  __shared__ double sl[32], sv[32];
+  double l = 0.0, v = 0.0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) { l += row_loss[r]; v += row_valid[r]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
+  if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = l; sv[threadIdx.x >> 5] = v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double L = 0.0, V = 0.0;
+    for (int w = 0; w < 32; ++w) { L += sl[w]; V += sv[w]; }
+    out[0] = static_cast<float>(L / V);   // 0 / 0 -> NaN when every label is ignored, as torch does
+    out[1] = static_cast<float>(V);
+  }
+}
+
+size_t cross_entropy_scratch(int batch, int T_len) { return static_cast<size_t>(batch) * (T_len > 1 ? T_len - 1 : 0) * 8 + 256; }
+
+int cross_entropy_run(Context* ctx, const void* logits, int logits_f32, int dtype, int64_t ld_row, int64_t ld_batch,
+                      const int64_t* labels, int64_t labels_ld, int batch, int T_len, int cols, int ignore_index,
+                      float* out, void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  ProfScope _ps(ctx, s, ULLAVA_PROF_GLUE, 0.0, static_cast<double>(batch) * T_len * cols * (logits_f32 ? 4.0 : 2.0));
+  ULLAVA_REQUIRE(logits && labels && out && scratch, "cross_entropy: null pointer");
+  ULLAVA_REQUIRE(batch > 0 && T_len > 1 && cols > 0, "cross_entropy: needs at least two positions");
+  ULLAVA_REQUIRE(scratch_bytes >= cross_entropy_scratch(batch, T_len), "cross_entropy: scratch too small");
+  const int rows = batch * (T_len - 1);
+  float* row_loss = static_cast<float*>(scratch);
+  float* row_valid = row_loss + rows;
+  if (logits_f32)
+    ce_rows_kernel<float><<<rows, 256, 0, s>>>(static_cast<const float*>(logits), ld_row, ld_batch, labels, labels_ld,
+                                               T_len, cols, ignore_index, row_loss, row_valid);
+  else if (dtype == DT_BF16)
+    ce_rows_kernel<__nv_bfloat16><<<rows, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), ld_row, ld_batch,
+                                                       labels, labels_ld, T_len, cols, ignore_index, row_loss, row_valid);
+  else if (dtype == DT_F16)
+    ce_rows_kernel<__half><<<rows, 256, 0, s>>>(static_cast<const __half*>(logits), ld_row, ld_batch, labels, labels_ld,
+                                                T_len, cols, ignore_index, row_loss, row_valid);
+  else { set_last_error("cross_entropy: unsupported dtype"); return ERR_UNSUPPORTED; }
+  ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, row_valid, rows, out);
+  ctx->launches += 2;
+  return check_cuda(cudaGetLastError(), "cross_entropy launch");
+}
+
 }  // namespace ullava

@@ -131,6 +131,11 @@ int seg_meter_update_run(Context* ctx, const int32_t* counts, const int32_t* off
 int box_iou_diag_run(Context* ctx, const void* pred, const void* gt, int n, int dtype, float* iou, double* meter,
                      cudaStream_t s);
 
+size_t cross_entropy_scratch(int batch, int T_len);
+int cross_entropy_run(Context* ctx, const void* logits, int logits_f32, int dtype, int64_t ld_row, int64_t ld_batch,
+                      const int64_t* labels, int64_t labels_ld, int batch, int T_len, int cols, int ignore_index,
+                      float* out, void* scratch, size_t scratch_bytes, cudaStream_t s);
+
 // preprocess.cu -- Pillow-exact uint8 resize, CLIP / SAM normalisation
 size_t resize_u8_scratch(int h, int w, int oh, int ow);
 int resize_u8_run(Context* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int filter,

@@ -277,10 +277,11 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
 
         loss = None
         if labels is not None:
-            # reference :327-338; off the accelerated path (inference callers ignore it)
-            shift_logits = logits[..., :-1, :].float().reshape(-1, logits.shape[-1])
-            shift_labels = labels[..., 1:].reshape(-1).to(shift_logits.device)
-            loss = nn.functional.cross_entropy(shift_logits, shift_labels)
+            # reference :327-338 (CrossEntropyLoss over the shifted logits; inference callers ignore it)
+            if logits.shape[1] == labels.shape[1] and logits.shape[1] > 1:
+                loss = ctx.cross_entropy(logits, labels.to(logits.device))
+            else:
+                raise ValueError("labels must cover the positions the logits were computed for")
 
         pkv = cache if use_cache else None
         if not return_dict:

@@ -132,6 +132,9 @@ _SIGNATURES = {
     "ullava_mask_iou_counts": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "ullava_seg_meter_update": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "ullava_box_iou_diag": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "ullava_cross_entropy_scratch_bytes": (_sz, [_i32, _i32]),
+    "ullava_cross_entropy": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz,
+                                    _vp]),
     "ullava_resize_u8_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ullava_resize_u8": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "ullava_clip_preprocess": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32),
@@ -575,6 +578,22 @@ class Context:
         self._chk(self.lib.ullava_box_iou_diag(self.handle, pred.data_ptr(), gt.data_ptr(), n, dt, iou.data_ptr(),
                                                _ptr(meter), _stream()))
         return iou
+
+    def cross_entropy(self, logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+        """Shifted token cross-entropy (CrossEntropyLoss over logits[:, :-1] vs labels[:, 1:], mean over valid labels).
+        logits [B, T, V] fp32 / bf16 / fp16 with unit stride on V; labels int64 [B, T].  Returns a 0-dim fp32 tensor."""
+        B, T, V = logits.shape
+        assert logits.stride(2) == 1 and labels.dtype == torch.int64 and labels.shape[0] == B and labels.shape[1] >= T
+        labels = labels if labels.stride(1) == 1 else labels.contiguous()
+        out = torch.empty((2,), dtype=torch.float32, device=logits.device)
+        nbytes = int(self.lib.ullava_cross_entropy_scratch_bytes(B, T))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+        f32 = logits.dtype == torch.float32
+        self._chk(self.lib.ullava_cross_entropy(self.handle, logits.data_ptr(), int(f32), 0 if f32 else dtype_code(logits.dtype),
+                                                logits.stride(1), logits.stride(0), labels.data_ptr(), labels.stride(0),
+                                                B, T, V, int(ignore_index), out.data_ptr(), scratch.data_ptr(), nbytes,
+                                                _stream()))
+        return out[0]
 
     # ---- image preprocessing (dataset/processors/clip_processor.py, dataset/tools/mask_toolbox.py) -----------
     def resize_u8(self, img: torch.Tensor, out_h: int, out_w: int, bicubic: bool) -> torch.Tensor:
