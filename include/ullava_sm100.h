@@ -395,6 +395,12 @@ ULLAVA_API int ullava_cross_entropy(ullava_ctx* ctx, const void* logits, int32_t
  * ullava_resize_u8: PIL.Image.resize of an RGB uint8 HWC image, bit-exact with Pillow's 8-bit resampler (separable,
  * antialiased, 22-bit fixed-point taps); filter 0 = BILINEAR (ResizeLongestSide.apply_image,
  * models/segment_anything/utils/transforms.py:29-37), 1 = BICUBIC (CLIPImageProcessor.resize). */
+/* Host-only (no GPU work, no context): the fixed-point tap table of one resampling pass, exactly Pillow's
+ * precompute_coeffs + normalize_coeffs_8bpc.  Returns ksize (taps per output sample) or -1 on bad arguments; when
+ * bounds ([out_size][2] = first input index, tap count) and taps ([out_size][ksize]) are given and `capacity` (int32
+ * entries available in taps) suffices they are filled in. */
+ULLAVA_API int ullava_resample_coeffs(int32_t in_size, int32_t out_size, int32_t filter, int32_t* bounds, int32_t* taps,
+                           size_t capacity);
 ULLAVA_API size_t ullava_resize_u8_scratch_bytes(int32_t h, int32_t w, int32_t out_h, int32_t out_w);
 ULLAVA_API int ullava_resize_u8(ullava_ctx* ctx, const uint8_t* src, int32_t h, int32_t w, uint8_t* dst, int32_t out_h, int32_t out_w,
                      int32_t filter, void* scratch, size_t scratch_bytes, void* stream);

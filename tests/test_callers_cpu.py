@@ -66,6 +66,19 @@ def test_pil_resize_restatement_is_bit_exact(h, w, oh, ow, bicubic):
     assert np.array_equal(O.pil_resize(img, oh, ow, bicubic), ref)
 
 
+@pytest.mark.parametrize("bicubic", [False, True])
+def test_library_tap_tables_equal_the_pillow_restatement(bicubic):
+    """The host half of ullava_resize_u8 (C++ restatement of precompute_coeffs / normalize_coeffs_8bpc inside the
+    library, no GPU involved) gives the oracle's tap tables bit for bit, for up- and down-scaling, odd sizes, 1 pixel."""
+    import native
+    for in_size, out_size in [(640, 1024), (480, 768), (333, 682), (1920, 597), (53, 200), (97, 31), (1, 5), (7, 3),
+                              (300, 300), (336, 336), (1024, 64), (2, 1)]:
+        bounds, taps = native.resample_coeffs(in_size, out_size, bicubic)
+        ob, ok = O.pil_coeffs(in_size, out_size, bicubic)
+        assert taps.shape == ok.shape, (in_size, out_size)
+        assert np.array_equal(bounds, ob) and np.array_equal(taps, ok), (in_size, out_size)
+
+
 def test_sam_preprocess_matches_reference_segtoolbox():
     z, meta = _load("callers_preprocess")
     for i, case in enumerate(meta["cases"]):

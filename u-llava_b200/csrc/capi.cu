@@ -247,6 +247,11 @@ int ullava_cross_entropy(ullava_ctx* ctx, const void* logits, int32_t logits_f32
                            ignore_index, out, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int ullava_resample_coeffs(int32_t in_size, int32_t out_size, int32_t filter, int32_t* bounds, int32_t* taps,
+                           size_t capacity) {
+  return resample_coeffs_host(in_size, out_size, filter, bounds, taps, capacity);
+}
+
 size_t ullava_resize_u8_scratch_bytes(int32_t h, int32_t w, int32_t out_h, int32_t out_w) {
   if (h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0) return 0;
   return resize_u8_scratch(h, w, out_h, out_w);

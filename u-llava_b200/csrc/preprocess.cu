@@ -13,6 +13,7 @@
 //                    evaluation/tools.py:55-67 casts to the model dtype).
 //   sam_preprocess   (x - mean) / std in fp32, zero pad to S x S, 16-bit CHW (mask_toolbox.py:15-25).
 // HBM-bound byte work: one thread per output pixel, channels together, coalesced along x.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -113,6 +114,20 @@ resample_v_kernel(const uint8_t* __restrict__ src, int row_bytes, uint8_t* __res
   int s = 1 << (kPrecisionBits - 1);
   for (int y = 0; y < taps; ++y) s += p[static_cast<int64_t>(y) * row_bytes] * k[y];
   dst[static_cast<int64_t>(yy) * row_bytes + i] = pil_clip8(s);
+}
+
+// Host-only entry: the tap table the device passes consume (for callers that cache it, and for CPU tests of the
+// Pillow restatement).  Returns ksize; bounds [out][2], kk [out][ksize] are written when the pointers are given and
+// `capacity` (entries of kk) is large enough, otherwise only ksize is returned.
+int resample_coeffs_host(int in_size, int out_size, int filter, int32_t* bounds_out, int32_t* kk_out, size_t capacity) {
+  if (in_size <= 0 || out_size <= 0 || (filter != 0 && filter != 1)) return -1;
+  std::vector<int32_t> bounds, kk;
+  const int ksize = pil_coeffs(in_size, out_size, filter, bounds, kk);
+  if (bounds_out && kk_out && capacity >= kk.size()) {
+    std::copy(bounds.begin(), bounds.end(), bounds_out);
+    std::copy(kk.begin(), kk.end(), kk_out);
+  }
+  return ksize;
 }
 
 static inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }

@@ -138,6 +138,7 @@ int cross_entropy_run(Context* ctx, const void* logits, int logits_f32, int dtyp
 
 // preprocess.cu -- Pillow-exact uint8 resize, CLIP / SAM normalisation
 size_t resize_u8_scratch(int h, int w, int oh, int ow);
+int resample_coeffs_host(int in_size, int out_size, int filter, int32_t* bounds_out, int32_t* kk_out, size_t capacity);
 int resize_u8_run(Context* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int filter,
                   void* scratch, size_t scratch_bytes, cudaStream_t s);
 int clip_preprocess_run(Context* ctx, const uint8_t* src, int h, int w, int top, int left, int size,

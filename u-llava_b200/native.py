@@ -135,6 +135,7 @@ _SIGNATURES = {
     "ullava_cross_entropy_scratch_bytes": (_sz, [_i32, _i32]),
     "ullava_cross_entropy": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz,
                                     _vp]),
+    "ullava_resample_coeffs": (_i32, [_i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), _sz]),
     "ullava_resize_u8_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ullava_resize_u8": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _sz, _vp]),
     "ullava_clip_preprocess": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32),
@@ -178,6 +179,20 @@ def load_library():
 
 def exported_symbols() -> Sequence[str]:
     return tuple(_SIGNATURES.keys())
+
+
+def resample_coeffs(in_size: int, out_size: int, bicubic: bool):
+    """Host-only: (bounds [out, 2], taps [out, ksize]) of one Pillow resampling pass as the device kernels use them."""
+    import numpy as np
+    lib = load_library()
+    ksize = lib.ullava_resample_coeffs(in_size, out_size, int(bicubic), None, None, 0)
+    if ksize <= 0:
+        raise ValueError("bad resampling geometry")
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    taps = np.zeros((out_size, ksize), dtype=np.int32)
+    lib.ullava_resample_coeffs(in_size, out_size, int(bicubic), bounds.ctypes.data_as(C.POINTER(_i32)),
+                               taps.ctypes.data_as(C.POINTER(_i32)), taps.size)
+    return bounds, taps
 
 
 def dtype_code(dt: torch.dtype) -> int:
