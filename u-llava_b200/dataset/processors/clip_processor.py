@@ -14,6 +14,17 @@ OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
+def _register(cls):
+    """registry.register_processor('clip_image') (reference clip_processor.py:23) when the reference's utils package
+    is importable, so that tasks/base_task.py:49 builds THIS processor from the eval / train configs."""
+    try:
+        from utils.registry import registry
+        return registry.register_processor('clip_image')(cls)
+    except Exception:
+        return cls
+
+
+@_register
 class CLIPProcessor:
     def __init__(self, checkpoint_path=None, aspect_ratio=None, size: int = 336, image_mean=OPENAI_CLIP_MEAN,
                  image_std=OPENAI_CLIP_STD, rescale_factor: float = 1 / 255, dtype=torch.bfloat16, device=None):

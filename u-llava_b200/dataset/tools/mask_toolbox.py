@@ -1,4 +1,4 @@
-"""SegToolBox of /root/reference/dataset/tools/mask_toolbox.py:8-28 (+ ResizeLongestSide.apply_image,
+"""SegToolBox and DetToolBox of /root/reference/dataset/tools/mask_toolbox.py:8-28,31-90 (+ ResizeLongestSide.apply_image,
 models/segment_anything/utils/transforms.py:29-37,61-70) on the device.
 
 apply_image: Pillow BILINEAR resize of the longest side to 1024 (uint8 HWC in, uint8 HWC out, on the GPU);
@@ -48,3 +48,40 @@ class SegToolBox:
         """image -> (images_sam [3, 1024, 1024], resize (h, w)): the two values inference_ullava.py:82-85 needs."""
         r = self.apply_image(image)
         return self.preprocess(r), (int(r.shape[0]), int(r.shape[1]))
+
+
+class DetToolBox:
+    """Box bookkeeping of the reference (mask_toolbox.py:31-90): boxes are normalised on the image padded to a square
+    (the CLIP 'pad' aspect ratio).  Host-side scalar arithmetic on four numbers; nothing here touches the device."""
+
+    @staticmethod
+    def get_pad_length(width, height):
+        if width > height:
+            return 0, (width - height) / 2.0
+        return (height - width) / 2.0, 0
+
+    @staticmethod
+    def xywh2xyxy(xywh):
+        x, y, w, h = xywh
+        return [x, y, x + w, y + h]
+
+    def pad_normalize_xyxy(self, xyxy, width, height):
+        side = max(width, height)
+        pad_x, pad_y = self.get_pad_length(width, height)
+        x0, y0, x1, y1 = xyxy
+        return [(x0 + pad_x) / side, (y0 + pad_y) / side, (x1 + pad_x) / side, (y1 + pad_y) / side]
+
+    def denormalize_padded_xyxy(self, normalized_xyxy, width, height):
+        side = max(width, height)
+        pad_x, pad_y = self.get_pad_length(width, height)
+        x0, y0, x1, y1 = normalized_xyxy
+        return [x0 * side - pad_x, y0 * side - pad_y, x1 * side - pad_x, y1 * side - pad_y]
+
+    @staticmethod
+    def mask2bbox(binary_mask):
+        """[x0, y0, x1, y1] (inclusive) of the non-zero pixels, what pycocotools' encode + toBbox give the reference."""
+        m = np.asarray(binary_mask) != 0
+        if not m.any():
+            return [0.0, 0.0, -1.0, -1.0]
+        ys, xs = np.nonzero(m)
+        return [float(xs.min()), float(ys.min()), float(xs.max()), float(ys.max())]
