@@ -105,6 +105,39 @@ def test_dataset_and_evaluation_merge_with_the_reference_tree():
         assert where[n].startswith(ref), (n, where[n])
 
 
+def test_resize_longest_side_helpers_match_reference():
+    """models.segment_anything.utils.transforms.ResizeLongestSide: shapes, coords and boxes equal the reference's
+    (loaded from its file when the tree is present, otherwise the formulas are checked directly)."""
+    import importlib.util
+    import numpy as np
+    from models.segment_anything.utils.transforms import ResizeLongestSide
+    t = ResizeLongestSide(1024)
+    ref_t = None
+    ref_file = "/root/reference/models/segment_anything/utils/transforms.py"
+    if os.path.exists(ref_file):
+        try:
+            spec = importlib.util.spec_from_file_location("ref_transforms", ref_file)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            ref_t = mod.ResizeLongestSide(1024)
+        except Exception:
+            ref_t = None
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        h, w = int(rng.integers(20, 2000)), int(rng.integers(20, 2000))
+        s = 1024.0 / max(h, w)
+        assert t.get_preprocess_shape(h, w, 1024) == (int(h * s + 0.5), int(w * s + 0.5))
+        boxes = rng.uniform(0, min(h, w), (5, 4))
+        got = t.apply_boxes(boxes, (h, w))
+        if ref_t is not None:
+            assert ref_t.get_preprocess_shape(h, w, 1024) == t.get_preprocess_shape(h, w, 1024)
+            assert np.array_equal(got, ref_t.apply_boxes(boxes, (h, w)))
+            assert torch.equal(t.apply_boxes_torch(torch.from_numpy(boxes), (h, w)),
+                               ref_t.apply_boxes_torch(torch.from_numpy(boxes), (h, w)))
+        nh, nw = t.get_preprocess_shape(h, w, 1024)
+        assert np.allclose(got[:, 0], boxes[:, 0] * (nw / w)) and np.allclose(got[:, 1], boxes[:, 1] * (nh / h))
+
+
 def test_det_toolbox_matches_reference_arithmetic():
     """DetToolBox (dataset/tools/mask_toolbox.py:31-90): pad / normalise / denormalise round trip and the reference's
     formulas on random boxes; mask2bbox on a hand-made mask."""
