@@ -105,6 +105,43 @@ def test_dataset_and_evaluation_merge_with_the_reference_tree():
         assert where[n].startswith(ref), (n, where[n])
 
 
+def test_reference_inference_script_imports_resolve_to_this_build():
+    """The import block of the reference's inference_ullava.py:12-20, executed with u-llava_b200/ in front of the
+    reference tree: model / processor / toolbox names come from this build, utils.* from the reference, and the
+    reference's registry hands out this build's classes ('ullava', 'clip_image').  peft is not installed in this
+    image and is stubbed.  Skipped where /root/reference does not exist."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    ours = os.path.join(ROOT, "u-llava_b200")
+    code = f"""
+import sys, types
+sys.path[:0] = [{ours!r}, {ref!r}]
+sys.modules['peft'] = types.ModuleType('peft'); sys.modules['peft'].PeftModel = object
+from utils.tools import load_image
+from transformers import LlamaTokenizer
+from dataset.processors.clip_processor import CLIPProcessor
+from dataset.tools.mask_toolbox import SegToolBox, DetToolBox
+from utils.conversation import default_conversation, SeparatorStyle
+from models import UllavaForCausalLM, KeywordsStoppingCriteria, \\
+    DEFAULT_IMG_END_TOKEN, DEFAULT_IMG_START_TOKEN, DEFAULT_IMG_TOKEN, DEFAULT_IMG_PATCH_TOKEN
+from models.ullava import UllavaForCausalLM as U2
+from evaluation.tools import intersectionAndUnionGPU, AverageMeter, Summary, dict_to_cuda, bbox_iou
+from utils.registry import registry
+import models, utils.tools
+assert U2 is UllavaForCausalLM
+print(models.__file__); print(utils.tools.__file__)
+print(registry.get_processor_class('clip_image').__module__, CLIPProcessor.__module__)
+print(registry.get_model_class('ullava') is UllavaForCausalLM)
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert lines[0].startswith(ours) and lines[1].startswith(ref), lines
+    assert lines[2].split() == ["dataset.processors.clip_processor"] * 2 and lines[3] == "True", lines
+
+
 def test_resize_longest_side_helpers_match_reference():
     """models.segment_anything.utils.transforms.ResizeLongestSide: shapes, coords and boxes equal the reference's
     (loaded from its file when the tree is present, otherwise the formulas are checked directly)."""
