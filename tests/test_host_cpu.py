@@ -306,3 +306,22 @@ def test_all_gather_results_gloo_world2():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gather_worker, args=(ws, port, ret), nprocs=ws, join=True)
     assert ret[0] and ret[1]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: oracle port on the host cores, bounded sample) runs without a GPU and
+    prints ONE JSON line with the driver's keys."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "images/s" and j["higher_is_better"] is True
+    assert j["metric"].startswith("images/sec") and j["value"] > 0 and j["n_gpus"] == 1 and j["steps"] == 1
+    assert j["e2e"] == {"value": j["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and len(cb["sample"]) > 20
+    assert j["config"]["workload"].startswith("c5 shard") and j["vs_baseline"] is None
