@@ -79,6 +79,29 @@ def test_library_tap_tables_equal_the_pillow_restatement(bicubic):
         assert np.array_equal(bounds, ob) and np.array_equal(taps, ok), (in_size, out_size)
 
 
+def test_pil_resize_restatement_random_geometries():
+    """Property test: for random small geometries (up / down / mixed scaling, degenerate 1-pixel sides) the restatement
+    and the library's tap tables agree with Pillow bit for bit."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    Image = pytest.importorskip("PIL.Image")
+    import native
+
+    @hyp.settings(max_examples=60, deadline=None, derandomize=True)
+    @hyp.given(st.integers(1, 48), st.integers(1, 48), st.integers(1, 80), st.integers(1, 80), st.booleans(),
+               st.integers(0, 2 ** 31 - 1))
+    def check(h, w, oh, ow, bicubic, seed):
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.array(Image.fromarray(img).resize((ow, oh), Image.BICUBIC if bicubic else Image.BILINEAR))
+        assert np.array_equal(O.pil_resize(img, oh, ow, bicubic), ref)
+        for a, b in ((w, ow), (h, oh)):
+            lb, lk = native.resample_coeffs(a, b, bicubic)
+            ob, ok = O.pil_coeffs(a, b, bicubic)
+            assert np.array_equal(lb, ob) and np.array_equal(lk, ok)
+
+    check()
+
+
 def test_sam_preprocess_matches_reference_segtoolbox():
     z, meta = _load("callers_preprocess")
     for i, case in enumerate(meta["cases"]):
