@@ -9,7 +9,7 @@ batch of images into the running fp64 meters, and the only device->host copy is 
 Everything goes through the C ABI (native.py); there is no torch fallback.
 """
 from enum import Enum
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
