@@ -9,7 +9,7 @@ All values are rounded to bf16-representable numbers, hence exactly loadable int
 from __future__ import annotations
 
 import zlib
-from typing import Dict, Iterable, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import torch
 
