@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ULLAVA_ABI_VERSION 2
+#define ULLAVA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ULLAVA_API __attribute__((visibility("default")))
@@ -342,6 +342,7 @@ typedef struct ullava_decode_args {
    * instead of the argmax; uniforms[pos * uniforms_ld + b] in [0, 1) is the draw of row b at position pos */
   const float* uniforms; int64_t uniforms_ld;
   float temperature, top_p;
+  int32_t top_k;                /* 0 = off; HF's GenerationConfig default (50) is applied by the Python caller */
 } ullava_decode_args;
 ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, void* stream);
 /* The bookkeeping tail of a step on its own (used once after the prefill, with *pos_dev = P - 1):
@@ -350,14 +351,15 @@ ULLAVA_API int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t 
                        int64_t* seqs, int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
                        uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, void* stream);
 
-/* Sampling flavour of the same tail (temperature > 0; top_p in (0, 1) filters like TopPLogitsWarper, 0 or 1 = off):
- * scores = logits / temperature, nucleus filter, then ONE draw per row by inverse CDF in vocabulary order with the
+/* Sampling flavour of the same tail (temperature > 0; top_k > 0 keeps the k largest scores like TopKLogitsWarper,
+ * 0 = off; top_p in [0, 1) then filters the survivors like TopPLogitsWarper, 1 = off, 0 = top-1 only):
+ * scores = logits / temperature, top-k filter, nucleus filter, then ONE draw per row by inverse CDF in vocabulary order with the
  * caller's uniform number uniforms[pos * uniforms_ld + b] (pos = *pos_dev, 0 if pos_dev is NULL).  torch.multinomial's
  * random stream is not reproducible outside torch: parity is on the filtered distribution (probs_out, optional
  * [rows, cols] fp32, receives it) and on the inverse-CDF draw.  Replaces the sampling branch of
  * GenerationMixin.generate as called by models/ullava.py:350-362. */
 ULLAVA_API int ullava_sample_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, float temperature,
-                       float top_p, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
+                       float top_p, int32_t top_k, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
                        int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
                        uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, float* probs_out,
                        void* stream);

@@ -91,14 +91,18 @@ def box_iou_diag(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------------------------
 # Sampling step (GenerationMixin.generate with do_sample=True as called by models/ullava.py:350-362):
-# TemperatureLogitsWarper, TopPLogitsWarper (transformers generation/logits_process.py), then one categorical draw.
+# TemperatureLogitsWarper, TopKLogitsWarper (GenerationConfig default top_k = 50 in the pinned transformers 4.29.1; the
+# reference never overrides it), TopPLogitsWarper (transformers generation/logits_process.py), then one categorical draw.
 # ------------------------------------------------------------------------------------------------------------------
-def filtered_distribution(logits: np.ndarray, temperature: float, top_p=None) -> np.ndarray:
+def filtered_distribution(logits: np.ndarray, temperature: float, top_p=None, top_k=None) -> np.ndarray:
     """probabilities [V] (fp64) of the warped distribution; dropped tokens get 0."""
     s = logits.astype(np.float64) / temperature
+    if top_k is not None and 0 < top_k < s.shape[0]:
+        kth = np.sort(s)[-top_k]                       # scores < k-th largest are removed (ties stay)
+        s = np.where(s < kth, -np.inf, s)
     e = np.exp(s - s.max())
     p = e / e.sum()
-    if top_p is not None and 0.0 < top_p < 1.0:
+    if top_p is not None and 0.0 <= top_p < 1.0:
         order = np.argsort(p, kind="stable")           # ascending, like torch.sort(descending=False)
         cum = np.cumsum(p[order])
         remove = cum <= (1.0 - top_p)
@@ -109,9 +113,9 @@ def filtered_distribution(logits: np.ndarray, temperature: float, top_p=None) ->
     return p
 
 
-def sample_inverse_cdf(logits: np.ndarray, temperature: float, top_p, u: float) -> int:
+def sample_inverse_cdf(logits: np.ndarray, temperature: float, top_p, u: float, top_k=None) -> int:
     """smallest index i with cdf(i) > u over the filtered distribution taken in vocabulary order."""
-    p = filtered_distribution(logits, temperature, top_p)
+    p = filtered_distribution(logits, temperature, top_p, top_k)
     cdf = np.cumsum(p)
     idx = int(np.searchsorted(cdf, u * cdf[-1], side="right"))
     kept = np.nonzero(p > 0)[0]

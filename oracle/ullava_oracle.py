@@ -155,7 +155,7 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
 def rope_tables(positions: torch.Tensor, hd: int, theta: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """LlamaRotaryEmbedding default rope (hf:...modeling_llama.py:74-135): returns cos, sin [S, hd/2]."""
     inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
-    fr = positions.float()[:, None] * inv[None, :]
+    fr = positions.float()[:, None] * inv.to(positions.device)[None, :]
     return fr.cos(), fr.sin()
 
 
@@ -180,10 +180,11 @@ def llama_layers(sd: SD, x: torch.Tensor, cfg: dict, prefix: str = "", past: Opt
     L = cfg["num_hidden_layers"] if n_layers is None else n_layers
     B, S, _ = x.shape
     pos0 = 0 if past is None else past[0][0].shape[2]
-    cos, sin = rope_tables(torch.arange(pos0, pos0 + S), hd, cfg.get("rope_theta", 10000.0))
-    qi = torch.arange(S)[:, None] + pos0
-    kj = torch.arange(pos0 + S)[None, :]
-    mask = torch.zeros(S, pos0 + S).masked_fill(kj > qi, float("-inf"))
+    dev = x.device  # the oracle also runs in fp32 on the GPU for the full-size checks (tests/test_fullsize_gpu.py)
+    cos, sin = rope_tables(torch.arange(pos0, pos0 + S, device=dev), hd, cfg.get("rope_theta", 10000.0))
+    qi = torch.arange(S, device=dev)[:, None] + pos0
+    kj = torch.arange(pos0 + S, device=dev)[None, :]
+    mask = torch.zeros(S, pos0 + S, device=dev).masked_fill(kj > qi, float("-inf"))
     new_past = []
     hiddens = [x] if collect_hidden else None
     for l in range(L):
@@ -265,7 +266,7 @@ def sam_dense_pe(sd: SD, prefix: str, size: int = 64) -> torch.Tensor:
     """PromptEncoder.get_dense_pe -> PositionEmbeddingRandom.forward
     (segment_anything/modeling/prompt_encoder.py:67-76,203-229): [1, 256, size, size]."""
     g = sd[prefix + "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"]
-    grid = torch.ones((size, size), dtype=g.dtype)
+    grid = torch.ones((size, size), dtype=g.dtype, device=g.device)
     y = (grid.cumsum(0) - 0.5) / size
     x = (grid.cumsum(1) - 0.5) / size
     c = torch.stack([x, y], -1)
@@ -392,10 +393,10 @@ def masks_from_hidden(sd: SD, cfg: dict, token_ids: torch.Tensor, hidden: torch.
             m, _ = sam_mask_decoder(sd, "visual_model.", image_embeddings[i:i + 1], e)
             m = m[:, 0:1]
         else:
-            m = torch.zeros((0, 1, 256, 256))
+            m = torch.zeros((0, 1, 256, 256), device=hidden.device)
         low_res.append(m)
         pm = postprocess_masks(m, resize_list[i], raw_size_list[i]) if e.shape[0] > 0 else \
-            torch.zeros((0, 1) + tuple(raw_size_list[i]))
+            torch.zeros((0, 1) + tuple(raw_size_list[i]), device=hidden.device)
         pred_masks.append(pm[:, 0])
         le = seg_project(sd, "det_projector.", hid[i][loc_mask[i]])
         pred_boxes.append(det_decode(sd, le))

@@ -35,6 +35,13 @@ from models.segment_anything.build_sam import _build_sam as ref_build_sam  # noq
 torch.set_grad_enabled(False)
 torch.manual_seed(0)
 
+# Weight seeds of the two tiny end-to-end fixtures.  They were picked (tests/golden/find_seed.py, a search over the
+# oracle) so that EVERY greedy decision the tests compare has a top-2 margin above 0.16 = twice the bf16 logit
+# tolerance: the exact-id / hidden-state / mask assertions of the generate() and evaluate() tests then always run
+# (a near-tie could legitimately flip under a different reduction order and used to gate them off).
+SEED_TINY_CORE = 14400   # min margin 0.163 over 2 x 8 golden tokens + the right-padded prompt variant (6 tokens)
+SEED_TINY_FULL = 332     # min margin 0.252 over 2 x 8 tokens of the [SEG]/[LOC] prompt
+
 
 def load_synth(module, seed=0):
     shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
@@ -55,7 +62,7 @@ def tiny_core():
     cfg._attn_implementation = "eager"
     cfg.vision_config._attn_implementation = "eager"
     m = ref_models.UllavaCoreForCausalLM(cfg).eval().float()
-    shapes, _ = load_synth(m)
+    shapes, _ = load_synth(m, SEED_TINY_CORE)
     B = 2
     ids = C.tiny_prompt(B)
     images = synth_normal("images", (B, 3, 28, 28))
@@ -83,7 +90,8 @@ def tiny_core():
                            last_hidden=first.hidden_states[-1].numpy(), hidden1=first.hidden_states[1].numpy(),
                            greedy=seqs.numpy(), greedy_hidden=torch.cat(hid, 1).numpy(),
                            margins=np.stack(margins, 1)),
-         dict(shapes={k: list(v) for k, v in shapes.items()}, seed=0, config="TINY_LLM",
+         dict(shapes={k: list(v) for k, v in shapes.items()}, seed=SEED_TINY_CORE, config="TINY_LLM",
+              min_margin=float(np.stack(margins, 1).min()),
               note="reference UllavaCoreForCausalLM, transformers 5.5.0 eager, fp32 CPU"))
 
 
@@ -97,7 +105,7 @@ def tiny_full():
     ref_ullava.build_sam_vit_h = lambda checkpoint=None: ref_build_sam(e["embed_dim"], e["depth"], e["num_heads"],
                                                                         e["global_attn_indexes"])
     m = ref_models.UllavaForCausalLM(cfg).eval().float()
-    shapes, _ = load_synth(m)
+    shapes, _ = load_synth(m, SEED_TINY_FULL)
     B = 2
     ids = C.tiny_prompt(B, seg_loc=True)
     images = synth_normal("images", (B, 3, 28, 28))
@@ -113,7 +121,7 @@ def tiny_full():
         arrays[f"pred_mask_{i}"] = out["pred_masks"][i].numpy()
         arrays[f"pred_box_{i}"] = out["pred_boxes"][i].numpy()
     save("tiny_full", arrays,
-         dict(shapes={k: list(v) for k, v in shapes.items()}, seed=0, sizes=sizes, resizes=resizes,
+         dict(shapes={k: list(v) for k, v in shapes.items()}, seed=SEED_TINY_FULL, sizes=sizes, resizes=resizes,
               note="reference UllavaForCausalLM.forward(inference=True); SAM image encoder reduced to 2 blocks, "
                    "prompt encoder / mask decoder at build_sam geometry; .cuda() shim"))
 

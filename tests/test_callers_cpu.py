@@ -127,22 +127,27 @@ def test_clip_preprocess_matches_hf_pil_processor(h, w):
     assert np.array_equal(O.clip_preprocess(img, 336), ref)
 
 
-@pytest.mark.parametrize("temperature,top_p", [(0.2, None), (0.2, 0.7), (1.0, 0.9), (0.7, 0.3)])
-def test_filtered_distribution_matches_hf_warpers(temperature, top_p):
+@pytest.mark.parametrize("temperature,top_p,top_k", [(0.2, None, None), (0.2, 0.7, None), (1.0, 0.9, None),
+                                                      (0.7, 0.3, None), (0.2, None, 50), (1.0, 0.9, 50), (1.3, 0.5, 7),
+                                                      (1.0, None, 1), (1.0, 0.0, None), (1.0, 0.0, 50)])
+def test_filtered_distribution_matches_hf_warpers(temperature, top_p, top_k):
+    """The warper chain of HF generate(do_sample=True): temperature, top-k (GenerationConfig default 50), top-p."""
     lp = pytest.importorskip("transformers.generation.logits_process")
     g = torch.Generator().manual_seed(11)
     logits = torch.randn((4, 997), generator=g) * 3
     scores = lp.TemperatureLogitsWarper(temperature)(None, logits.clone())
+    if top_k is not None:
+        scores = lp.TopKLogitsWarper(top_k)(None, scores)
     if top_p is not None:
         scores = lp.TopPLogitsWarper(top_p)(None, scores)
     ref = scores.double().softmax(-1).numpy()
     for b in range(4):
-        p = O.filtered_distribution(logits[b].numpy(), temperature, top_p)
+        p = O.filtered_distribution(logits[b].numpy(), temperature, top_p, top_k)
         assert np.array_equal(p > 0, ref[b] > 0)
         assert np.abs(p - ref[b]).max() < 1e-6
         # inverse CDF: the drawn index is a kept token and its CDF interval contains u
         for u in (0.0, 0.25, 0.5, 0.999999):
-            i = O.sample_inverse_cdf(logits[b].numpy(), temperature, top_p, u)
+            i = O.sample_inverse_cdf(logits[b].numpy(), temperature, top_p, u, top_k)
             cdf = np.cumsum(p)
             assert p[i] > 0 and cdf[i] > u * cdf[-1] - 1e-12 and (cdf[i] - p[i]) <= u * cdf[-1] + 1e-12
 

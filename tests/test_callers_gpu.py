@@ -244,8 +244,10 @@ def test_video_and_image_rows_match_reference_golden(ctx, dtype):
 # sampling
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("V", [32011, 997, 64])
-@pytest.mark.parametrize("temperature,top_p", [(0.2, None), (0.2, 0.7), (1.0, 0.9), (0.7, 0.3), (1.5, 1.0)])
-def test_sample_step_distribution_and_draw(ctx, V, temperature, top_p):
+@pytest.mark.parametrize("temperature,top_p,top_k", [(0.2, None, 0), (0.2, 0.7, 0), (1.0, 0.9, 0), (0.7, 0.3, 0),
+                                                      (1.5, 1.0, 0), (0.2, None, 50), (1.0, 0.9, 50), (1.3, 0.5, 7),
+                                                      (1.0, None, 1), (1.0, 0.0, 0), (1.0, 0.0, 50)])
+def test_sample_step_distribution_and_draw(ctx, V, temperature, top_p, top_k):
     B = 6
     g = torch.Generator().manual_seed(V + int(temperature * 10))
     logits = torch.randn((B, V), generator=g) * 3
@@ -253,15 +255,17 @@ def test_sample_step_distribution_and_draw(ctx, V, temperature, top_p):
     u[0, 0], u[0, 1] = 0.0, 0.9999999
     probs = torch.empty((B, V), dtype=torch.float32, device="cuda")
     ids = torch.empty((B,), dtype=torch.int64, device="cuda")
-    ctx.sample_step(logits.cuda(), temperature, top_p, u.cuda(), ids, probs_out=probs)
+    ctx.sample_step(logits.cuda(), temperature, top_p, u.cuda(), ids, probs_out=probs, top_k=top_k)
     probs, ids = probs.cpu().double().numpy(), ids.cpu().numpy()
     for b in range(B):
-        ref = O.filtered_distribution(logits[b].numpy(), temperature, top_p)
+        ref = O.filtered_distribution(logits[b].numpy(), temperature, top_p, top_k)
+        if top_k:
+            assert int((probs[b] > 0).sum()) <= top_k
         # kept set: identical except for tokens whose ascending cumulative mass sits within rounding of the cut
         diff = np.nonzero((probs[b] > 0) != (ref > 0))[0]
         diff = np.array([t for t in diff if ref[t] > 1e-30], dtype=np.int64)   # fp32 exp underflows to 0, fp64 does not
         if len(diff):
-            full = O.filtered_distribution(logits[b].numpy(), temperature, None)
+            full = O.filtered_distribution(logits[b].numpy(), temperature, None, top_k)
             order = np.argsort(full, kind="stable")
             cum = np.cumsum(full[order])
             pos = {int(t): k for k, t in enumerate(order)}
@@ -274,7 +278,7 @@ def test_sample_step_distribution_and_draw(ctx, V, temperature, top_p):
         i, t = int(ids[b]), float(u[0, b]) * cdf[-1]
         assert probs[b][i] > 0 and cdf[i] - probs[b][i] <= t + 1e-5 and t <= cdf[i] + 1e-5, (i, t, cdf[i], probs[b][i])
         if not len(diff):
-            j = O.sample_inverse_cdf(logits[b].numpy(), temperature, top_p, float(u[0, b]))
+            j = O.sample_inverse_cdf(logits[b].numpy(), temperature, top_p, float(u[0, b]), top_k)
             if j != i:   # only when u * Z falls within fp32 rounding of a CDF step
                 assert abs(i - j) <= max(2, V // 1000) or min(abs(t - cdf[i]), abs(t - (cdf[i] - probs[b][i]))) < 1e-5
 
@@ -310,8 +314,9 @@ def test_sample_step_statistics_and_bookkeeping(ctx):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16])
 def test_generate_sampling_on_device(ctx, dtype):
-    """do_sample generate: reproducible under a seeded generator, equal to greedy when the temperature is tiny, and
-    the graph-replayed session agrees with the per-step host loop (stopping_criteria path) given the same uniforms."""
+    """do_sample generate (HF warper chain: temperature, top-k = 50 by default, top-p): reproducible under a seeded
+    generator, equal to greedy when the temperature is tiny or top_k = 1 / top_p = 0, and the graph-replayed loop agrees
+    with the eagerly launched one and with the stopping_criteria variant given the same uniforms."""
     model, sd, cfg = build_tiny_core(dtype)
     ids, images = oracle_inputs_core(2)
     ids, images = ids.cuda(), images.cuda().to(dtype)
@@ -328,6 +333,17 @@ def test_generate_sampling_on_device(ctx, dtype):
     assert torch.equal(a, b) and a.shape == (2, ids.shape[1] + 8)
     assert torch.equal(a[:, :ids.shape[1]], ids) and int(a.max()) < model.config.vocab_size
     assert not torch.equal(a, c)
+    for kw in (dict(top_k=1), dict(top_p=0.0)):          # only the most likely token survives the filter
+        one = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1.0,
+                             generator=torch.Generator("cuda").manual_seed(3), **kw)
+        assert torch.equal(one, greedy), kw
+    model.use_cuda_graph = False
+    d = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1.0, top_p=0.9,
+                       generator=torch.Generator("cuda").manual_seed(7))
+    model.use_cuda_graph = True
+    e = model.generate(input_ids=ids, images=images, max_new_tokens=8, do_sample=True, temperature=1.0, top_p=0.9,
+                       generator=torch.Generator("cuda").manual_seed(7), stopping_criteria=[lambda s, sc: False])
+    assert torch.equal(a, d) and torch.equal(a, e)
     # evaluate()'s default (temperature = 0.2) also runs on the device path
     out = model.generate(input_ids=ids, images=images, max_new_tokens=4, do_sample=True, temperature=0.2,
                          output_hidden_states=True, return_dict_in_generate=True)

@@ -109,3 +109,121 @@ def test_c4_full_pipeline_b8_determinism_and_batch_invariance(full):
         band = 4 * (x - y).abs().mean().item() + 1e-6
         clear = y.abs() > 8 * band
         assert bool(((x > 0) == (y > 0))[clear].all()) and float(clear.float().mean()) > 0.5
+
+
+def _oracle_cfg():
+    cfg = dict(bench.LLM)
+    cfg["rope_theta"] = 10000.0
+    return cfg
+
+
+SAM_VITH = dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=[7, 15, 23, 31], window_size=14,
+                patch_size=16)
+
+
+@pytest.fixture(scope="module")
+def oracle_run(full):
+    """The oracle restatement of the WHOLE path at full size (LLaMA-7B, ViT-L/14-336, SAM ViT-H), evaluated in fp32 ON
+    THE GPU on the very weights the product model holds (the CPU would need tens of minutes): B = 2 bench prompts,
+    prefill logits, 8 greedy tokens with their margins, SAM embeddings, low-res and final mask logits."""
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False      # plain fp32 arithmetic: the oracle is the checker
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd32 = {k: v.detach().float() for k, v in full.state_dict().items()}
+        ids, img, sam = _inputs(2)
+        cfg = _oracle_cfg()
+        new = 8
+        pre = O.core_forward(sd32, cfg, ids, img.float(), prefix="llm.")
+        o_seqs, o_hid, margins = O.greedy_generate(sd32, cfg, ids, img.float(), new, prefix="llm.")
+        emb = O.sam_image_encoder(sd32, "visual_model.", sam.float(), SAM_VITH)
+        sizes, resizes = [(bench.IMG, bench.IMG)] * 2, [(bench.SAM_IMG, bench.SAM_IMG)] * 2
+        scfg = dict(seg_token_idx=bench.SEG_ID, loc_token_idx=bench.LOC_ID)
+        pm, pb, low = O.masks_from_hidden(sd32, scfg, o_seqs, o_hid, emb, sizes, resizes)
+        out = dict(ids=ids, img=img, sam=sam, new=new, last_logits=pre["logits"][:, -1].clone(),
+                   last_hidden=pre["last_hidden"].clone(), seqs=o_seqs, hid=o_hid, margins=margins, emb=emb, pm=pm,
+                   low=low, sizes=sizes, resizes=resizes)
+        del sd32, pre
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _iou(a, b):
+    a, b = a > 0, b > 0
+    u = (a | b).sum().item()
+    return 1.0 if u == 0 else (a & b).sum().item() / u
+
+
+def test_c4_full_size_bf16_vs_fp32_oracle(full, oracle_run):
+    """The benchmarked configuration itself (full u-LLaVA-7B, bf16, evaluate() through the graph-replayed decode loop)
+    against the fp32 oracle: greedy ids (exact wherever the oracle's top-2 margin exceeds twice the logit tolerance),
+    last-position prefill logits, hidden states, SAM embeddings, low-res mask logits, thresholded masks."""
+    r = oracle_run
+    ids, img, sam, new = r["ids"], r["img"], r["sam"], r["new"]
+    seqs, masks, _ = full.evaluate(sam, img, ids, r["sizes"], r["resizes"], max_new_tokens=new, temperature=0)
+    assert full.llm.graph_kernel_launches() > 0
+    tol = 8e-2                                        # bf16 logit bar (8 x the 1e-2 fp16 bar: 8 vs 11 mantissa bits)
+    out = full.llm(input_ids=ids, images=img, return_dict=True, logits_to_keep=1, logits_fp32=True,
+                   _return_last_hidden=True)
+    err = (out.logits[:, 0].float() - r["last_logits"]).abs().max().item()
+    herr = (out.hidden_states[-1].float() - r["last_hidden"]).abs().max().item()
+    print(f"c4 bf16 vs fp32 oracle: last-position logits max-abs {err:.4f}, post-norm hidden max-abs {herr:.4f}, "
+          f"oracle margins {[round(float(x), 3) for x in r['margins'].flatten()]}")
+    assert err < tol, err
+    checked = 0
+    for b in range(2):
+        from tests.util_models import greedy_walk
+        exact, prefix = greedy_walk(seqs[b].cpu(), r["seqs"][b].cpu(), r["margins"][b].cpu(), bench.P_LEN, 2 * tol)
+        checked += exact
+        print(f"  sample {b}: {exact} ids asserted exactly (margin > {2 * tol}), common prefix {prefix} of {new}")
+    assert checked >= 1, "no generated token had a clear margin: nothing was compared"
+    # SAM ViT-H embeddings (32 blocks) and the heads, teacher-forced with the ORACLE's ids / hidden states so that the
+    # comparison does not depend on the greedy ids above
+    emb = full.get_visual_embs(sam)
+    e_rel = ((emb.float() - r["emb"]).norm() / r["emb"].norm()).item()
+    assert e_rel < 3e-2, f"SAM ViT-H embeddings: relative error {e_rel:.4f}"
+    tm, _, _ = full._decode_heads(r["seqs"], r["hid"].to(DT), emb, r["sizes"], r["resizes"])
+    ious = []
+    for i in range(2):
+        got, ref = tm[i].float(), r["pm"][i]
+        assert got.shape == ref.shape and got.shape[0] >= 1
+        rel = ((got - ref).norm() / ref.norm()).item()
+        assert rel < 6e-2, f"mask logits vs fp32 oracle: relative error {rel:.4f}"
+        band = ref.abs() > 0.1 * ref.abs().max()
+        agree = ((got > 0) == (ref > 0))[band].float().mean().item()
+        assert agree == 1.0, f"mask pixels outside the rounding band disagree ({agree:.6f})"
+        ious.append(_iou(got, ref))
+    print(f"  SAM embeddings rel err {e_rel:.4f}; mask IoU vs oracle (noise-like random-weight masks) {ious}")
+    assert min(ious) > 0.9
+
+
+def test_c4_full_size_fp16_logits_within_1e_2(full, oracle_run):
+    """north_star's logit bar is stated for fp16: the same weights cast to fp16, last-position prefill logits and the
+    teacher-forced decode-step logits within 1e-2 max-abs of the fp32 oracle; greedy ids as above."""
+    import copy
+    r = oracle_run
+    ids, img, new = r["ids"], r["img"], r["new"]
+    tower, stack = full.llm._tower, full.llm._stack          # packed copies / captured graphs are not deep-copyable
+    full.llm._tower = full.llm._stack = None
+    try:
+        llm16 = copy.deepcopy(full.llm).to(torch.float16)
+    finally:
+        full.llm._tower, full.llm._stack = tower, stack
+    try:
+        out = llm16(input_ids=ids, images=img.to(torch.float16), return_dict=True, logits_to_keep=1, logits_fp32=True)
+        err = (out.logits[:, 0].float() - r["last_logits"]).abs().max().item()
+        print(f"c4 fp16 vs fp32 oracle: last-position logits max-abs {err:.5f}")
+        assert err < 1e-2, err
+        seqs = llm16.generate(input_ids=ids, images=img.to(torch.float16), max_new_tokens=new, do_sample=False)
+        from tests.util_models import greedy_walk
+        checked = 0
+        for b in range(2):
+            exact, prefix = greedy_walk(seqs[b].cpu(), r["seqs"][b].cpu(), r["margins"][b].cpu(), bench.P_LEN, 2e-2)
+            checked += exact
+            print(f"  sample {b}: {exact} ids asserted exactly (margin > 0.02), common prefix {prefix} of {new}")
+        assert checked >= 4
+    finally:
+        del llm16
+        torch.cuda.empty_cache()

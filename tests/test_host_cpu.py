@@ -325,3 +325,65 @@ def test_bench_reference_arm_prints_the_contract_line():
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and len(cb["sample"]) > 20
     assert j["config"]["workload"].startswith("c5 shard") and j["vs_baseline"] is None
+
+
+def test_lora_adapters_are_folded_into_packed_weights():
+    """`model.llm = PeftModel.from_pretrained(model.llm, ...)` (inference_ullava.py:42-43): the injected LoRA layers keep
+    the BASE weight in `.weight`; LlamaStack must pack W + scaling * B @ A, re-pack when the adapter state changes, and
+    refuse adapter kinds it does not fold (never drop them silently)."""
+    import torch
+    from transformers import LlamaConfig, LlamaModel
+    from models.engine import LlamaStack, effective_weight
+    from tests.util_models import LoraLinearStub, inject_lora
+    torch.manual_seed(0)
+    lc = LlamaConfig(vocab_size=64, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
+                     num_key_value_heads=2)
+    m = LlamaModel(lc).eval().to(torch.bfloat16)
+    head = torch.nn.Linear(64, 64, bias=False).to(torch.bfloat16)
+    stack = LlamaStack(m, head)
+    stack.ensure()
+    base_qkv = [stack.tensors[6 * l + 1].clone() for l in range(2)]
+    deltas = inject_lora(m)
+    m.to(torch.bfloat16)
+    stack.ensure()                                         # module identity changed -> re-pack
+    for l in range(2):
+        a = m.layers[l].self_attn
+        want = torch.cat([(a.q_proj.weight.float() + deltas[f"model.layers.{l}.self_attn.q_proj.weight"]).to(torch.bfloat16),
+                          a.k_proj.weight, (a.v_proj.weight.float() +
+                                            deltas[f"model.layers.{l}.self_attn.v_proj.weight"]).to(torch.bfloat16)], 0)
+        assert torch.equal(stack.tensors[6 * l + 1], want)
+        assert not torch.equal(stack.tensors[6 * l + 1], base_qkv[l])
+    # disable_adapter(): the base model runs
+    for l in range(2):
+        m.layers[l].self_attn.q_proj.disable_adapters = m.layers[l].self_attn.v_proj.disable_adapters = True
+    stack.ensure()
+    assert all(torch.equal(stack.tensors[6 * l + 1], base_qkv[l]) for l in range(2))
+    # merged flag: the delta is already in W
+    q = m.layers[0].self_attn.q_proj
+    q.disable_adapters = False
+    q.weight.data += q.delta().to(torch.bfloat16)
+    q.merged = True
+    assert torch.equal(effective_weight(q), q.weight)
+    # peft >= 0.6 layout: the wrapper holds the nn.Linear as .base_layer
+    class NewStyle(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.base_layer = torch.nn.Linear(inner.in_features, inner.out_features, bias=False).to(torch.bfloat16)
+            self.lora_A, self.lora_B, self.scaling, self.r = inner.lora_A, inner.lora_B, inner.scaling, inner.r
+            self.active_adapters, self.merged, self.disable_adapters = ["default"], False, False
+    v = m.layers[1].self_attn.v_proj
+    ns = NewStyle(v)
+    assert torch.equal(effective_weight(ns), (ns.base_layer.weight.float() + v.delta()).to(torch.bfloat16))
+    # DoRA / embedding adapters are refused
+    ns.lora_magnitude_vector = {"default": torch.ones(4)}
+    with pytest.raises(NotImplementedError):
+        effective_weight(ns)
+    # in-place .data edits leave no trace in the signature: invalidate() is the documented hook
+    k = m.layers[1].self_attn.k_proj
+    stack.ensure()
+    k.weight.data.mul_(2)
+    stack.ensure()
+    stale = stack.tensors[6 + 1][64:128].clone()
+    stack.invalidate()
+    stack.ensure()
+    assert not torch.equal(stack.tensors[6 + 1][64:128], stale)

@@ -73,3 +73,80 @@ def iou(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a > 0, b > 0
     u = (a | b).sum().item()
     return 1.0 if u == 0 else (a & b).sum().item() / u
+
+
+class LoraLinearStub(torch.nn.Linear):
+    """Attribute layout of peft 0.4's `lora.Linear` (the reference's pin; peft is not installed here): an nn.Linear
+    whose `.weight` is the frozen base weight plus per-adapter lora_A / lora_B modules, `scaling`, `r`, `merged`."""
+
+    def __init__(self, base: torch.nn.Linear, r: int, alpha: float, key: str, adapter="default"):
+        super().__init__(base.in_features, base.out_features, bias=base.bias is not None)
+        self.weight, self.bias = base.weight, base.bias
+        self.lora_A = torch.nn.ModuleDict({adapter: torch.nn.Linear(base.in_features, r, bias=False)})
+        self.lora_B = torch.nn.ModuleDict({adapter: torch.nn.Linear(r, base.out_features, bias=False)})
+        self.lora_embedding_A, self.lora_embedding_B = torch.nn.ParameterDict(), torch.nn.ParameterDict()
+        self.r, self.scaling = {adapter: r}, {adapter: alpha / r}
+        self.active_adapter, self.merged, self.disable_adapters, self.fan_in_fan_out = adapter, False, False, False
+        with torch.no_grad():
+            self.lora_A[adapter].weight.copy_(synth_normal(key + ".A", (r, base.in_features), scale=0.3))
+            self.lora_B[adapter].weight.copy_(synth_normal(key + ".B", (base.out_features, r), scale=0.3))
+
+    def delta(self) -> torch.Tensor:
+        a = self.active_adapter
+        return (self.lora_B[a].weight.float() @ self.lora_A[a].weight.float()) * self.scaling[a]
+
+
+class PeftModelStub(torch.nn.Module):
+    """What `PeftModel.from_pretrained(model.llm, ...)` leaves in `model.llm` (inference_ullava.py:43): a wrapper whose
+    forward / generate / attribute lookups end up at the wrapped module (base_model.model)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.base_model = torch.nn.Module()
+        self.base_model.model = model
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(self.base_model.model, name)
+
+    def forward(self, *a, **k):
+        return self.base_model.model(*a, **k)
+
+    def generate(self, **k):
+        return self.base_model.model.generate(**k)
+
+
+def inject_lora(llama_model, targets=("q_proj", "v_proj"), r=4, alpha=8.0):
+    """Wraps the target projections of every decoder layer in LoraLinearStub (train_ullava.py:42 default targets);
+    returns {state_dict key of the base weight: delta} for the oracle."""
+    deltas = {}
+    for i, lay in enumerate(llama_model.layers):
+        for t in targets:
+            parent = lay.self_attn if hasattr(lay.self_attn, t) else lay.mlp
+            stub = LoraLinearStub(getattr(parent, t), r, alpha, f"lora.{i}.{t}")
+            setattr(parent, t, stub)
+            sub = "self_attn" if parent is lay.self_attn else "mlp"
+            deltas[f"model.layers.{i}.{sub}.{t}.weight"] = stub.delta()
+    return deltas
+
+
+def greedy_walk(got: torch.Tensor, ref: torch.Tensor, margins: torch.Tensor, prompt_len: int, min_margin: float,
+                got_prompt_len: int = None):
+    """Per-token comparison of greedy ids with the reference's.  got [T_got], ref [T_ref] (one sample), margins [n] =
+    the reference's top-2 logit margin of every generated token.  A token decided by a margin above `min_margin` (twice
+    the logit tolerance) must be identical; at a narrower margin a flip is legitimate under a different reduction
+    order, and everything after it is conditioned differently, so the walk stops there.
+    Returns (n_checked_exact, n_compared_prefix): tokens asserted under a wide margin / length of the common prefix."""
+    gp = prompt_len if got_prompt_len is None else got_prompt_len
+    n = margins.shape[0]
+    exact = 0
+    for t in range(n):
+        a, b = int(got[gp + t]), int(ref[prompt_len + t])
+        if float(margins[t]) > min_margin:
+            assert a == b, f"token {t}: got {a}, reference {b} at margin {float(margins[t]):.4f} > {min_margin}"
+            exact += 1
+        elif a != b:
+            return exact, t
+    return exact, n

@@ -268,11 +268,8 @@ template <typename T, int HD>
 static int flash_launch(const FlashParams& p, int batch, int heads, cudaStream_t stream) {
   constexpr int smem = 5 * FA_BN * HD * 2;
   auto kern = flash_fwd_kernel<T, HD>;
-  static bool configured = false;
-  if (!configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemOptIn opt_in;   // per device (common.cuh)
+  { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
   dim3 grid((p.seq_q + FA_BM - 1) / FA_BM, heads, batch);
   kern<<<grid, FA_THREADS, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "flash_fwd launch");
@@ -557,11 +554,8 @@ template <typename T, int HD>
 static int relpos_launch(const FlashParams& p, const RelPosParams& rp, int batch, int heads, cudaStream_t stream) {
   const int smem = 5 * FA_BN * fa_row_bytes<HD>() + FA_BM * (2 * (2 * rp.S - 1) + 1) * 4;
   auto kern = flash_relpos_kernel<T, HD>;
-  static int configured = 0;
-  if (smem > configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static SmemOptIn opt_in;   // per device (common.cuh)
+  { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
   dim3 grid((p.seq_q + FA_BM - 1) / FA_BM, heads, batch);
   kern<<<grid, FA_THREADS, smem, stream>>>(p, rp);
   return check_cuda(cudaGetLastError(), "flash_relpos launch");

@@ -204,12 +204,12 @@ int ullava_video_pool(ullava_ctx* ctx, const void* feats, void* out, int32_t bat
 }
 
 int ullava_sample_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, float temperature,
-                       float top_p, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
+                       float top_p, int32_t top_k, const float* uniforms, int64_t uniforms_ld, int64_t* cur_ids, int64_t* seqs,
                        int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
                        uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, float* probs_out,
                        void* stream) {
   CTX_CHECK("ullava_sample_step");
-  return sample_step_run(ctx, logits, ld, rows, cols, temperature, top_p, uniforms, uniforms_ld, cur_ids, seqs, seqs_ld,
+  return sample_step_run(ctx, logits, ld, rows, cols, temperature, top_p, top_k, uniforms, uniforms_ld, cur_ids, seqs, seqs_ld,
                          final_h, hid_buf, hid_bs, hdim, finished, eos_id, pad_id, pos_dev, probs_out,
                          static_cast<cudaStream_t>(stream));
 }

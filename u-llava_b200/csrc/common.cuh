@@ -440,6 +440,23 @@ int encode_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], c
 
 int device_sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what was configured per device (a
+// process may drive several GPUs through several contexts), keyed by the device current at launch time.
+struct SmemOptIn {
+  int bytes[64] = {0};
+};
+template <typename Kern>
+inline int ensure_dynamic_smem(Kern kern, int bytes, SmemOptIn& state) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev >= 0 && bytes <= state.bytes[dev]) return OK;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  if (dev >= 0) state.bytes[dev] = bytes;
+  return OK;
+}
+
+
 #ifdef __CUDACC__
 // Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the
 // stream is still running, once every CTA of the predecessor has executed griddepcontrol.launch_dependents (or

@@ -565,11 +565,8 @@ static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int
   using C = FmhaCfg<HD>;
   const int smem = C::smem_bytes(RP ? FM_BM * (2 * p.S + 1) : 0);
   auto kern = fmha_tcgen05_kernel<T, HD, RP>;
-  static int configured = 0;
-  if (smem > configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static SmemOptIn opt_in;   // per device (common.cuh)
+  { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
   dim3 grid((p.seq_q + FM_BM - 1) / FM_BM, heads, batch);
   kern<<<grid, FM_THREADS, smem, stream>>>(maps, p);
   return check_cuda(cudaGetLastError(), "fmha_tcgen05 launch");

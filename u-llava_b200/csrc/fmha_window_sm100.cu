@@ -308,20 +308,14 @@ int fmha_window_run(Context* ctx, const AttnArgs& a, const void* rel_h, const in
   int st;
   if (a.dtype == DT_BF16) {
     auto kern = fmha_window_kernel<__nv_bfloat16>;
-    static bool configured = false;
-    if (!configured) {
-      ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
-      configured = true;
-    }
+    static SmemOptIn opt_in;   // per device (common.cuh)
+    { const int _st = ensure_dynamic_smem(kern, FW_SMEM, opt_in); if (_st != OK) return _st; }
     kern<<<grid, FW_THREADS, FW_SMEM, stream>>>(maps, p);
     st = check_cuda(cudaGetLastError(), "fmha_window launch");
   } else {
     auto kern = fmha_window_kernel<__half>;
-    static bool configured = false;
-    if (!configured) {
-      ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
-      configured = true;
-    }
+    static SmemOptIn opt_in;   // per device (common.cuh)
+    { const int _st = ensure_dynamic_smem(kern, FW_SMEM, opt_in); if (_st != OK) return _st; }
     kern<<<grid, FW_THREADS, FW_SMEM, stream>>>(maps, p);
     st = check_cuda(cudaGetLastError(), "fmha_window launch");
   }

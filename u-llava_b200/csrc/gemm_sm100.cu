@@ -648,11 +648,8 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
                           cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES>;
   auto kern = gemm_tcgen05_kernel<T, BN, STAGES, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
-  }
+  static SmemOptIn opt_in;   // per device (common.cuh)
+  { const int _st = ensure_dynamic_smem(kern, S::kTotal, opt_in); if (_st != OK) return _st; }
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ta, tb, p);
   return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
@@ -674,11 +671,8 @@ template <typename T, int EPI>
 static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
                        cudaStream_t stream) {
   auto kern = gemm_tcgen05_pair_kernel<T, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
-    configured = true;
-  }
+  static SmemOptIn opt_in;   // per device (common.cuh)
+  { const int _st = ensure_dynamic_smem(kern, PairSmem::kTotal, opt_in); if (_st != OK) return _st; }
   kern<<<grid, kGemmThreads, PairSmem::kTotal, stream>>>(ta, tb, p);   // __cluster_dims__(2, 1, 1): grid is even
   return check_cuda(cudaGetLastError(), "gemm_tcgen05_pair_kernel launch");
 }

@@ -381,11 +381,8 @@ static int stream_launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUt
                          int grid, bool pdl, cudaStream_t stream) {
   using S = StreamSmem<BN>;
   auto kern = gemm_stream_kernel<T, BN, EK>;
-  static bool configured = false;
-  if (!configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
-  }
+  static SmemOptIn opt_in;   // per device (common.cuh)
+  { const int _st = ensure_dynamic_smem(kern, S::kTotal, opt_in); if (_st != OK) return _st; }
   return check_cuda(launch_pdl(kern, dim3(grid), dim3(GS_THREADS), S::kTotal, stream, pdl, tw, tx, tp, p),
                     "gemm_stream_kernel launch");
 }

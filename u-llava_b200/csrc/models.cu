@@ -216,7 +216,7 @@ int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_
   g.M = L.batch; g.N = a.vocab; g.K = L.hidden_size; g.dtype = L.dtype; g.out_f32 = 1; g.epilogue = EPI_NONE;
   RUN(gemm_run(ctx, g, s));
   if (a.uniforms) {
-    RUN(sample_step_run(ctx, a.logits, a.vocab, L.batch, a.vocab, a.temperature, a.top_p, a.uniforms, a.uniforms_ld,
+    RUN(sample_step_run(ctx, a.logits, a.vocab, L.batch, a.vocab, a.temperature, a.top_p, a.top_k, a.uniforms, a.uniforms_ld,
                         a.cur_ids, a.seqs, a.seqs_ld, L.final_out, a.hid_buf, a.hid_bs, L.hidden_size, a.finished,
                         a.eos_id, a.pad_id, a.pos_dev, nullptr, s));
   } else {

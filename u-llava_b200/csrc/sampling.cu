@@ -1,8 +1,9 @@
-// Device-side temperature / top-p sampling step of the generate loop.
+// Device-side temperature / top-k / top-p sampling step of the generate loop.
 //
 // Reference: UllavaForCausalLM.evaluate passes do_sample = temperature > 0 (default 0.2), top_p to
-// GenerationMixin.generate (models/ullava.py:343-362), i.e. per step
+// GenerationMixin.generate (models/ullava.py:343-362); GenerationConfig's default top_k = 50 applies as well, i.e. per step
 //   scores = logits / temperature                                  (TemperatureLogitsWarper)
+//   drop scores < the k-th largest score (ties kept)               (TopKLogitsWarper, top_k = 50 unless the caller says otherwise)
 //   sort ascending, cum = cumsum(softmax(sorted)); drop cum <= 1 - top_p, always keep the last   (TopPLogitsWarper)
 //   next ~ Categorical(softmax(filtered scores))                   (torch.multinomial)
 // torch.multinomial's random stream cannot be reproduced by another kernel, so parity here is distributional: this
@@ -12,9 +13,11 @@
 //
 // One CTA per row, the row's exp() values live in shared memory (V = 32 011 -> 125 KB): logits are read once.
 //   1. m = max(logits); e_i = exp((l_i - m) / T); Z = sum e_i
-//   2. top-p: the kept set is {i : S(e_i) > (1 - top_p) * Z}, S(x) = sum of all e_j <= x  (what the ascending cumsum
-//      tests, up to ties).  It is an upper set in e, found by bisection on the float bit pattern of the threshold
-//      (non-negative floats order like their bits): 31 block-wide masked sums.
+//   2. top-k: the k-th largest e is the largest float t with #{e_i >= t} >= k: bisection on the float bit pattern of t
+//      (non-negative floats order like their bits), 31 block-wide counts; Z_k = sum of the survivors.
+//      top-p over the survivors: the kept set is {i : S(e_i) > (1 - top_p) * Z_k}, S(x) = sum of all surviving
+//      e_j <= x (what the ascending cumsum tests, up to ties).  It is an upper set in e, found by the same kind of
+//      bisection with masked sums.  top_p = 0 keeps the maximum only (min_tokens_to_keep = 1).
 //   3. target = u * Z_kept; block-wide exclusive scan of per-thread chunk sums (contiguous chunks: index order), the
 //      owning thread walks its chunk.
 // Bookkeeping (finished / eos / pad, sequence buffer, hidden-state copy, position) is that of greedy_step_kernel.
@@ -52,7 +55,7 @@ __device__ __forceinline__ float block_max_f(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(SMP_THREADS)
-sample_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, float inv_temp, float top_p,
+sample_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, float inv_temp, float top_p, int top_k,
                    const float* __restrict__ uniforms, int64_t uni_ld, int64_t* __restrict__ cur_ids,
                    int64_t* __restrict__ seqs, int64_t seqs_ld, const uint16_t* __restrict__ final_h,
                    uint16_t* __restrict__ hid_buf, int64_t hid_bs, int hdim, uint8_t* __restrict__ finished,
@@ -88,16 +91,35 @@ sample_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, float
   }
   z = block_sum_f(z, red);
 
-  // ---- top-p threshold: smallest float thr with S(thr) = sum{e <= thr} > (1 - top_p) * z ----
+  // ---- top-k threshold: largest float tk with #{e >= tk} >= k (the k-th largest value; ties survive like HF's
+  //      `scores < kth` test) ----
   uint32_t thr_bits = 0u;  // keep everything
-  if (top_p > 0.f && top_p < 1.f) {
+  if (top_k > 0 && top_k < cols) {
+    uint32_t lo = 0u, hi = __float_as_uint(1.0f);  // count(e >= 0) = cols >= k, count(e >= 1.0) >= 1 (the maximum)
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+      const float t = __uint_as_float(mid);
+      float n = 0.f;
+      for (int c = tid; c < cols; c += SMP_THREADS) n += ev[c] >= t ? 1.f : 0.f;
+      n = block_sum_f(n, red);  // exact: counts stay below 2^24
+      if (n >= static_cast<float>(top_k)) lo = mid; else hi = mid - 1;
+    }
+    thr_bits = lo;
+    const float tk = __uint_as_float(lo);
+    float zk = 0.f;
+    for (int c = tid; c < cols; c += SMP_THREADS) zk += ev[c] >= tk ? ev[c] : 0.f;
+    z = block_sum_f(zk, red);
+  }
+  // ---- top-p threshold over the survivors: smallest float thr with S(thr) = sum{tk <= e <= thr} > (1 - top_p) * z ----
+  if (top_p >= 0.f && top_p < 1.f) {
+    const float tk = __uint_as_float(thr_bits);
     const float cut = (1.f - top_p) * z;
-    uint32_t lo = 0u, hi = __float_as_uint(1.0f);  // e in [0, 1]; S(1.0) = z > cut
+    uint32_t lo = thr_bits, hi = __float_as_uint(1.0f);  // e in [0, 1]; S(1.0) = z > cut unless top_p = 0 (-> thr = 1.0)
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       const float t = __uint_as_float(mid);
       float s = 0.f;
-      for (int c = tid; c < cols; c += SMP_THREADS) s += ev[c] <= t ? ev[c] : 0.f;
+      for (int c = tid; c < cols; c += SMP_THREADS) s += (ev[c] <= t && ev[c] >= tk) ? ev[c] : 0.f;
       s = block_sum_f(s, red);
       if (s > cut) hi = mid; else lo = mid + 1;
     }
@@ -165,23 +187,21 @@ sample_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, float
 __global__ void sample_advance_pos_kernel(int32_t* pos) { *pos += 1; }
 
 int sample_step_run(Context* ctx, const float* logits, int64_t ld, int rows, int cols, float temperature, float top_p,
-                    const float* uniforms, int64_t uni_ld, int64_t* cur_ids, int64_t* seqs, int64_t seqs_ld,
+                    int top_k, const float* uniforms, int64_t uni_ld, int64_t* cur_ids, int64_t* seqs, int64_t seqs_ld,
                     const void* final_h, void* hid_buf, int64_t hid_bs, int hdim, uint8_t* finished, int eos_id,
                     int pad_id, int32_t* pos_dev, float* probs_out, cudaStream_t stream) {
   ProfScope _ps(ctx, stream, ULLAVA_PROF_GLUE, 0.0, 4.0 * rows * cols);
   ULLAVA_REQUIRE(logits && cur_ids && cols > 0 && hdim % 8 == 0, "sample_step: bad arguments");
   ULLAVA_REQUIRE(temperature > 0.f, "sample_step: temperature must be > 0 (greedy decoding is ullava_greedy_step)");
-  ULLAVA_REQUIRE(top_p >= 0.f && top_p <= 1.f, "sample_step: top_p must be in [0, 1] (0 or 1 = no filtering)");
+  ULLAVA_REQUIRE(top_p >= 0.f && top_p <= 1.f, "sample_step: top_p must be in [0, 1] (1 = no filtering, 0 = top-1 only)");
+  ULLAVA_REQUIRE(top_k >= 0, "sample_step: top_k must be >= 0 (0 = no filtering)");
   const size_t smem = static_cast<size_t>(cols) * sizeof(float);
   ULLAVA_REQUIRE(smem <= 200 * 1024, "sample_step: vocabulary of %d does not fit the shared-memory row buffer", cols);
   if (rows == 0) return OK;
-  static bool configured = false;
-  if (!configured) {
-    ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(sample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  // per device attribute, cheap: set on every call (a process may drive several devices)
+  ULLAVA_CHECK_CUDA(cudaFuncSetAttribute(sample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   sample_step_kernel<<<rows, SMP_THREADS, smem, stream>>>(
-      logits, ld, cols, 1.f / temperature, top_p, uniforms, uni_ld, cur_ids, seqs, seqs_ld,
+      logits, ld, cols, 1.f / temperature, top_p, top_k, uniforms, uni_ld, cur_ids, seqs, seqs_ld,
       static_cast<const uint16_t*>(final_h), static_cast<uint16_t*>(hid_buf), hid_bs, hdim, finished, eos_id, pad_id,
       pos_dev, probs_out);
   ctx->launches++;

@@ -119,7 +119,7 @@ int argmax_run(Context* ctx, const float* logits, int64_t ld, int64_t* out, int 
 
 // sampling.cu -- temperature / top-p step (inverse CDF over the filtered distribution, one uniform per row)
 int sample_step_run(Context* ctx, const float* logits, int64_t ld, int rows, int cols, float temperature, float top_p,
-                    const float* uniforms, int64_t uni_ld, int64_t* cur_ids, int64_t* seqs, int64_t seqs_ld,
+                    int top_k, const float* uniforms, int64_t uni_ld, int64_t* cur_ids, int64_t* seqs, int64_t seqs_ld,
                     const void* final_h, void* hid_buf, int64_t hid_bs, int hdim, uint8_t* finished, int eos_id,
                     int pad_id, int32_t* pos_dev, float* probs_out, cudaStream_t stream);
 

@@ -20,8 +20,59 @@ except ImportError:  # pragma: no cover
     from .. import native  # type: ignore
 
 
-def _sig(params) -> Tuple:
-    return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params)
+def _sig(params, modules=()) -> Tuple:
+    """Identity of everything a packed copy was made from: parameter storage / in-place version / dtype / device, plus
+    -- for the linear layers whose weights are fused into packed copies -- the module objects and their LoRA state
+    (merge_and_unload() swaps the modules, merge_adapter() / set_adapter() / disable_adapter() flip flags without
+    touching a version counter)."""
+    return (tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in params),
+            tuple((id(m),) + _lora_state(m) for m in modules))
+
+
+def _lora_state(lin) -> Tuple:
+    if not hasattr(lin, "lora_A"):
+        return ()
+    active = getattr(lin, "active_adapters", None)
+    if active is None or callable(active):
+        active = getattr(lin, "active_adapter", None)
+    if isinstance(active, str):
+        active = (active,)
+    return (bool(getattr(lin, "merged", False)), bool(getattr(lin, "disable_adapters", False)), tuple(active or ()))
+
+
+def effective_weight(lin) -> torch.Tensor:
+    """The [out, in] matrix a (possibly LoRA-wrapped) nn.Linear applies at inference time.
+
+    The reference wraps `model.llm` in `PeftModel` when lora_r > 0 (inference_ullava.py:42-43, eval_ullava.py:137-138;
+    targets q_proj / v_proj by default, train_ullava.py:42,88-113): the injected peft layers keep the base weight in
+    `.weight` (peft 0.4, the reference's pin) or `.base_layer.weight` (peft >= 0.6) and add
+    scaling * lora_B(lora_A(x)) in their forward.  The kernels read packed weight copies, so the adapters are folded
+    in at pack time:  W_eff = W + sum_active scaling * B @ A  (exactly what peft's own merge() computes).  Anything this
+    does not understand (DoRA, embedding adapters, adapters with a bias) raises instead of being dropped silently."""
+    base = getattr(lin, "base_layer", lin)
+    w = base.weight.detach()
+    if not hasattr(lin, "lora_A"):
+        return w
+    merged, disabled, active = _lora_state(lin)
+    if merged or disabled:
+        return w            # merged: the delta already lives in W; disabled: the base model is what runs
+    if len(getattr(lin, "lora_embedding_A", {}) or {}) or len(getattr(lin, "lora_magnitude_vector", {}) or {}):
+        raise NotImplementedError("only plain LoRA adapters on nn.Linear are folded into the packed weights")
+    wf = None
+    for name in active:
+        if name not in lin.lora_A:
+            continue
+        A, Bm = lin.lora_A[name], lin.lora_B[name]
+        if getattr(A, "bias", None) is not None or getattr(Bm, "bias", None) is not None:
+            raise NotImplementedError("LoRA adapters with a bias are not supported on the B200 path")
+        r = lin.r[name] if isinstance(getattr(lin, "r", None), dict) else A.weight.shape[0]
+        if r <= 0:
+            continue
+        delta = (Bm.weight.detach().float() @ A.weight.detach().float()) * float(lin.scaling[name])
+        if getattr(lin, "fan_in_fan_out", False):
+            delta = delta.t()
+        wf = (w.float() if wf is None else wf) + delta.to(w.device)
+    return w if wf is None else wf.to(w.dtype)
 
 
 def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
@@ -103,8 +154,14 @@ class VisionTower:
     def ensure(self):
         sig = _sig(self.module.parameters())
         if sig != self._sig:
+            if any(hasattr(m, "lora_A") for m in self.module.modules()):
+                raise NotImplementedError("LoRA adapters on the CLIP tower are outside the u-LLaVA path "
+                                          "(train_ullava.py:88-113 excludes vision_encoder)")
             self._pack()
             self._sig = sig
+
+    def invalidate(self):
+        self._sig = None
 
     def __call__(self, ctx: "native.Context", pixels: torch.Tensor) -> torch.Tensor:
         self.ensure()
@@ -145,16 +202,22 @@ class LlamaStack:
         if getattr(cfg, "attention_bias", False) or getattr(cfg, "mlp_bias", False):
             raise NotImplementedError("LLaMA with biases is outside the u-LLaVA path")
         tensors = []
+        ew = effective_weight   # LoRA adapters (PeftModel-wrapped llm) are folded into the packed copies
         for lay in self.model.layers:
             a, m = lay.self_attn, lay.mlp
             tensors += [lay.input_layernorm.weight.detach(),
-                        torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).detach().contiguous(),
-                        a.o_proj.weight.detach().contiguous(),
+                        torch.cat([ew(a.q_proj), ew(a.k_proj), ew(a.v_proj)], 0).contiguous(),
+                        ew(a.o_proj).contiguous(),
                         lay.post_attention_layernorm.weight.detach(),
-                        interleave_gate_up(m.gate_proj.weight.detach(), m.up_proj.weight.detach()),
-                        m.down_proj.weight.detach().contiguous()]
+                        interleave_gate_up(ew(m.gate_proj), ew(m.up_proj)),
+                        ew(m.down_proj).contiguous()]
         tensors.append(self.model.norm.weight.detach())
         self.tensors = tensors
+        self.head_w = ew(self.lm_head).contiguous()          # == lm_head.weight itself when there is no adapter
+        emb = self.model.embed_tokens
+        if hasattr(emb, "lora_embedding_A") and len(emb.lora_embedding_A):
+            raise NotImplementedError("LoRA adapters on embed_tokens are not supported on the B200 path")
+        self.embed_w = getattr(emb, "base_layer", emb).weight.detach()
         self.table = native.Context.pointer_table(tensors)
         H = cfg.hidden_size
         self.cfg = dict(layers=len(self.model.layers), hidden=H, heads=heads, head_dim=H // heads,
@@ -167,11 +230,23 @@ class LlamaStack:
         self.device = tensors[1].device
         self._rope = None
 
+    def _linears(self):
+        out = [self.lm_head]
+        for lay in self.model.layers:
+            a, m = lay.self_attn, lay.mlp
+            out += [a.q_proj, a.k_proj, a.v_proj, a.o_proj, m.gate_proj, m.up_proj, m.down_proj]
+        return out
+
     def ensure(self):
-        sig = _sig(list(self.model.parameters()) + list(self.lm_head.parameters()))
+        sig = _sig(list(self.model.parameters()) + list(self.lm_head.parameters()), self._linears())
         if sig != self._sig:
             self._pack()
             self._sig = sig
+            self._session = None  # decode session (KV cache, captured graph) belongs to the old packed copies
+
+    def invalidate(self):
+        """Force a re-pack at the next call (for edits the signature cannot see, e.g. `p.data.copy_()` of a weight)."""
+        self._sig = None
 
     def rope_tables(self, max_pos: int):
         if self._rope is None or self._rope[0].shape[0] < max_pos:
@@ -243,7 +318,7 @@ class DecodeSession:
         self.graph = None
         self.graph_nodes = 0
         self.eos_id, self.pad_id = -1, 0
-        self.sampling = None      # None = greedy, else (temperature, top_p)
+        self.sampling = None      # None = greedy, else (temperature, top_p, top_k)
         self.uniforms = None      # [max_seq, batch] fp32: the draw of row b at position pos (ullava_sample_step)
         self.args = None
 
@@ -262,11 +337,11 @@ class DecodeSession:
         a.finished, a.eos_id, a.pad_id = self.finished.data_ptr(), self.eos_id, self.pad_id
         if self.sampling is not None:
             a.uniforms, a.uniforms_ld = self.uniforms.data_ptr(), self.uniforms.stride(0)
-            a.temperature, a.top_p = float(self.sampling[0]), float(self.sampling[1])
+            a.temperature, a.top_p, a.top_k = float(self.sampling[0]), float(self.sampling[1]), int(self.sampling[2])
         self.args = a
 
     def begin(self, input_ids: torch.Tensor, eos_id, pad_id: int, sampling=None, generator=None, lengths=None):
-        """sampling: None (greedy) or (temperature, top_p); the uniforms of every position are drawn here, once per
+        """sampling: None (greedy) or (temperature, top_p, top_k); the uniforms of every position are drawn here, once per
         generate() call, from `generator` (torch's default CUDA generator when None).  lengths (optional, [B] on the
         device): valid prompt lengths of a right-padded batch; sample b then continues at position lengths[b]."""
         if lengths is None:
@@ -275,7 +350,8 @@ class DecodeSession:
             self.pos_offset.copy_((lengths - input_ids.shape[1]).to(torch.int32))
         eos = -1 if eos_id is None else int(eos_id)
         if sampling is not None:
-            sampling = (float(sampling[0]), float(sampling[1]) if sampling[1] is not None else 1.0)
+            sampling = (float(sampling[0]), float(sampling[1]) if sampling[1] is not None else 1.0,
+                        int(sampling[2]) if len(sampling) > 2 and sampling[2] else 0)
             if self.uniforms is None:
                 self.uniforms = torch.empty((self.max_seq, self.batch), dtype=torch.float32, device=self.stack.device)
             self.uniforms.uniform_(0.0, 1.0, generator=generator)
@@ -295,7 +371,8 @@ class DecodeSession:
         self.pos.fill_(prompt_len - 1)
         if self.sampling is not None:
             self.ctx.sample_step(self.logits, self.sampling[0], self.sampling[1], self.uniforms, self.cur_ids, self.seqs,
-                                 last_final, self.hid_buf, self.finished, self.eos_id, self.pad_id, self.pos)
+                                 last_final, self.hid_buf, self.finished, self.eos_id, self.pad_id, self.pos,
+                                 top_k=self.sampling[2])
         else:
             self.ctx.greedy_step(self.logits, self.cur_ids, self.seqs, last_final, self.hid_buf, self.finished,
                                  self.eos_id, self.pad_id, self.pos)

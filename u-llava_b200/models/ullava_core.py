@@ -127,7 +127,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
 
     # ---- native plumbing -------------------------------------------------------------------
     def _ctx(self) -> "native.Context":
-        dev = self.lm_head.weight.device
+        dev = getattr(self.lm_head, "base_layer", self.lm_head).weight.device
         if dev.type != "cuda":
             raise RuntimeError("UllavaCoreForCausalLM (B200 build) runs on a CUDA sm_100 device only; "
                                "call .cuda() first -- there is no CPU fallback")
@@ -140,6 +140,15 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         if self._stack is None or self._stack.model is not self.model or self._stack.lm_head is not self.lm_head:
             self._stack = LlamaStack(self.model, self.lm_head)
         return self._tower, self._stack
+
+    def invalidate_packed(self):
+        """Drop the packed weight copies (fused QKV, interleaved gate/up, LoRA-merged matrices, decode session).  They
+        are re-made automatically when a parameter is replaced, updated through autograd-visible in-place ops, or
+        when LoRA adapters are merged / switched; call this after edits that leave no trace (`p.data.copy_(...)`)."""
+        if self._tower is not None:
+            self._tower.invalidate()
+        if self._stack is not None:
+            self._stack.invalidate()
 
     def _project(self, ctx, feats2d: torch.Tensor) -> torch.Tensor:
         vp = self.vision_projector
@@ -169,7 +178,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         _, stack = self._engine()
         stack.ensure()
         B, L = input_ids.shape
-        table = self.model.embed_tokens.weight.detach()
+        table = stack.embed_w
         H = table.shape[1]
         embeds = ctx.embed_gather(input_ids, table).view(B, L, H)
         ids = self.mm_token_ids
@@ -248,8 +257,8 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             if inputs_embeds is None:
                 input_ids, inputs_embeds = self.embed_images_videos(input_ids, images, videos)
                 if inputs_embeds is None:  # decode step: [B,1] token ids
-                    table = self.model.embed_tokens.weight.detach()
-                    inputs_embeds = ctx.embed_gather(input_ids, table).view(input_ids.shape[0], 1, -1)
+                    stack.ensure()
+                    inputs_embeds = ctx.embed_gather(input_ids, stack.embed_w).view(input_ids.shape[0], 1, -1)
             B, L, H = inputs_embeds.shape
             self._check_mask(attention_mask, B, L)
             if past_key_values is not None and not isinstance(past_key_values, KVCache):
@@ -263,7 +272,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             if caller_embeds:
                 hidden = hidden.to(stack.dtype).clone()  # the stack updates its input in place
             final, allh = stack.run(ctx, hidden, cache, B, L, want_all_hidden=bool(output_hidden_states))
-            w = self.lm_head.weight.detach()
+            w = stack.head_w   # lm_head.weight with any LoRA adapter folded in (engine.effective_weight)
             if logits_to_keep:
                 last = final.view(B, L, H)[:, -logits_to_keep:].reshape(-1, H)
                 logits = ctx.gemm(last, w, out_f32=logits_fp32).view(B, logits_to_keep, -1)
@@ -296,13 +305,24 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
     def generate(self, input_ids=None, images=None, videos=None, max_new_tokens=32, num_beams=1, top_p=None,
                  do_sample=False, temperature=1.0, output_hidden_states=False, return_dict_in_generate=False,
                  no_repeat_ngram_size=None, stopping_criteria=None, eos_token_id=None, pad_token_id=None,
-                 attention_mask=None, use_cache=True, generator=None, **kwargs):
+                 attention_mask=None, use_cache=True, generator=None, top_k=None, **kwargs):
         """Greedy / sampling generation with a KV cache (replaces HF GenerationMixin.generate for the
         path used by UllavaForCausalLM.evaluate, models/ullava.py:349-365, and inference_ullava_core.py:73-80).
 
         With output_hidden_states=True and return_dict_in_generate=True, `hidden_states[-1][-1]` is the
         post-final-norm hidden state of every processed position, [B, T-1, H] -- exactly what the
-        reference reads when its checkpoints run with use_cache=False."""
+        reference reads when its checkpoints run with use_cache=False.
+
+        Sampling (do_sample and temperature > 0) applies HF's warper chain: temperature, top-k, top-p.  top_k=None
+        takes generation_config.top_k, i.e. the GenerationConfig default of 50 that the reference's
+        `generate(do_sample=True, temperature=0.2, top_p=None)` call runs with; top_k=0 switches it off.
+        top_p=None or 1 switches the nucleus filter off, top_p=0 keeps the most likely token only (HF:
+        min_tokens_to_keep=1).
+
+        stopping_criteria (HF StoppingCriteria callables, e.g. models.tools.KeywordsStoppingCriteria as passed by
+        inference_ullava.py:88-102) are evaluated WITHOUT leaving the graph-replayed device loop: the loop runs in
+        chunks of 8 tokens and the criteria are then called on every new prefix in order, exactly as HF would have
+        called them token by token; the result is trimmed to the first hit."""
         if num_beams != 1:
             raise NotImplementedError("beam search is outside the u-LLaVA path (num_beams=1 everywhere)")
         if no_repeat_ngram_size:
@@ -329,88 +349,41 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             lengths = attention_mask.bool().sum(1).to(torch.int32)
             if int(lengths.min()) < 1:
                 raise ValueError("every prompt needs at least one valid token")
-        H = self.config.hidden_size
-        T = P + max_new_tokens
-        greedy = not (do_sample and temperature and temperature > 0)
-        sampling = None if greedy else (float(temperature), top_p)
-        if stopping_criteria is None and max_new_tokens >= 1:
-            return self._generate_greedy_device(ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id,
-                                                pad_token_id, output_hidden_states, return_dict_in_generate,
-                                                sampling=sampling, generator=generator, lengths=lengths)
-        pos_offset = None if lengths is None else (lengths - P).to(torch.int32)
-        cache = stack.new_cache(B, T)
-        table = self.model.embed_tokens.weight.detach()
-        w = self.lm_head.weight.detach()
-        V = w.shape[0]
+        sampling = None
+        if do_sample and temperature and temperature > 0:
+            if top_p is not None and not (0.0 <= float(top_p) <= 1.0):
+                raise ValueError(f"`top_p` has to be a float in [0, 1], but is {top_p}")   # TopPLogitsWarper
+            if top_k is None:
+                gk = getattr(getattr(self, "generation_config", None), "top_k", None)
+                top_k = 50 if gk is None else int(gk)
+            if int(top_k) < 0:
+                raise ValueError(f"`top_k` has to be a non-negative integer, but is {top_k}")
+            sampling = (float(temperature), top_p, int(top_k))
+        if max_new_tokens < 1:
+            seqs = input_ids.clone()
+            return GenerateOutput(sequences=seqs, hidden_states=None, past_key_values=None) \
+                if return_dict_in_generate else seqs
+        crit = []
+        if stopping_criteria is not None:
+            crit = list(stopping_criteria) if isinstance(stopping_criteria, (list, tuple)) or \
+                hasattr(stopping_criteria, "__iter__") else [stopping_criteria]
+        return self._generate_device(ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id,
+                                     pad_token_id, output_hidden_states, return_dict_in_generate,
+                                     sampling=sampling, generator=generator, lengths=lengths, criteria=crit)
 
-        _, embeds = self.embed_images_videos(input_ids, images, videos)
-        self._mark("vit_projector_splice")
-        hidden = embeds.view(B * P, H)
-        final, _ = stack.run(ctx, hidden, cache, B, P)
-        self._mark("prefill")
-        hid_buf = None
-        if output_hidden_states:
-            hid_buf = torch.empty((B, T - 1, H), dtype=final.dtype, device=final.device)
-            hid_buf[:, :P] = final.view(B, P, H)
-        seqs = torch.full((B, T), pad_token_id, dtype=torch.int64, device=input_ids.device)
-        seqs[:, :P] = input_ids
-        logits = torch.empty((B, V), dtype=torch.float32, device=final.device)
-        if lengths is None:
-            last = final.view(B, P, H)[:, -1].contiguous()
-        else:
-            last = final.view(B, P, H)[torch.arange(B, device=final.device), (lengths - 1).long()].contiguous()
-            if hid_buf is not None:
-                hid_buf[:, P - 1] = last
-        finished = torch.zeros((B,), dtype=torch.bool, device=final.device)
-        step_hidden = torch.empty((B, H), dtype=final.dtype, device=final.device)
-        n_done = T
-        for t in range(max_new_tokens):
-            ctx.gemm(last, w, out=logits)
-            if sampling is not None:
-                # one uniform number per row, inverse-CDF draw on the device (ullava_sample_step)
-                u = torch.rand((1, B), dtype=torch.float32, device=logits.device, generator=generator)
-                nxt = torch.empty((B,), dtype=torch.int64, device=logits.device)
-                ctx.sample_step(logits, sampling[0], sampling[1], u, nxt)
-            else:
-                nxt = ctx.argmax(logits)
-            if eos_token_id is not None:
-                nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
-                finished = finished | (nxt == eos_token_id)
-            seqs[:, P + t] = nxt
-            stop = False
-            if stopping_criteria is not None:
-                crit = stopping_criteria if isinstance(stopping_criteria, (list, tuple)) else list(stopping_criteria)
-                stop = any(bool(c(seqs[:, :P + t + 1], logits)) for c in crit)
-            if eos_token_id is not None and (t % 8 == 7 or stop) and bool(finished.all()):
-                stop = True
-            if stop or t == max_new_tokens - 1:
-                n_done = P + t + 1
-                break
-            step_in = ctx.embed_gather(nxt, table, out=step_hidden)
-            final, _ = stack.run(ctx, step_in, cache, B, 1, pos_offset=pos_offset)
-            if hid_buf is not None:
-                hid_buf[:, P + t] = final
-            last = final
-        seqs = seqs[:, :n_done]
-        if not return_dict_in_generate:
-            return seqs
-        hs = None
-        if output_hidden_states:
-            hs = ((hid_buf[:, : n_done - 1],),)
-        return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=cache)
+    CRITERIA_CHUNK = 8   # decode steps between two host checks (EOS of every row / stopping criteria)
 
-    def _generate_greedy_device(self, ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id, pad_token_id,
-                                output_hidden_states, return_dict_in_generate, sampling=None, generator=None,
-                                lengths=None):
-        """Greedy (or, with `sampling` = (temperature, top_p), sampling) loop with all per-step state on the device:
-        prefill, then max_new_tokens-1 replays of ONE
-        captured decode-step graph (the position is read from device memory).  The host only synchronises to
-        test for EOS (every 8 steps, and only when an eos id is set)."""
+    def _generate_device(self, ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id, pad_token_id,
+                         output_hidden_states, return_dict_in_generate, sampling=None, generator=None,
+                         lengths=None, criteria=()):
+        """Greedy (or, with `sampling` = (temperature, top_p, top_k), sampling) loop with all per-step state on the
+        device: prefill, then max_new_tokens-1 replays of ONE captured decode-step graph (the position is read from
+        device memory).  The host only synchronises every CRITERIA_CHUNK steps, and only when an eos id or stopping
+        criteria are set."""
         B, P = input_ids.shape
         H = self.config.hidden_size
         T = P + max_new_tokens
-        table = self.model.embed_tokens.weight.detach()
-        w = self.lm_head.weight.detach()
+        table, w = stack.embed_w, stack.head_w
         sess = stack.decode_session(ctx, B, T, table, w, bool(output_hidden_states))
         sess.begin(input_ids, eos_token_id, pad_token_id, sampling=sampling, generator=generator, lengths=lengths)
         _, embeds = self.embed_images_videos(input_ids, images, videos)
@@ -424,19 +397,33 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         else:   # last VALID position of every row; first_token() also stores it as the state of column P - 1
             last = final.view(B, P, H)[torch.arange(B, device=final.device), (lengths - 1).long()].contiguous()
         sess.first_token(last, P)
+
+        def first_hit(n_from, n_to):
+            """Calls the criteria on the prefixes holding n_from+1 .. n_to generated tokens, in order, the way HF calls
+            them after every token (scores are not materialised per step: None); returns the first count that stops."""
+            for n in range(n_from + 1, n_to + 1):
+                view = sess.seqs[:, :P + n]
+                for c in criteria:
+                    r = c(view, None)
+                    if bool(r.all()) if isinstance(r, torch.Tensor) else bool(r):
+                        return n
+            return None
+
         remaining = max_new_tokens - 1
         n_tokens = 1
-        if eos_token_id is None:
-            stack.graph_launches += self._count_graph(ctx, sess, remaining)
-            n_tokens += remaining
-        else:
-            while remaining > 0:
-                if bool(sess.finished.all()):
-                    break
-                n = min(8, remaining)
-                stack.graph_launches += self._count_graph(ctx, sess, n)
-                remaining -= n
-                n_tokens += n
+        stop = first_hit(0, 1) if criteria else None
+        chunk = self.CRITERIA_CHUNK if (eos_token_id is not None or criteria) else max(remaining, 1)
+        while remaining > 0 and stop is None:
+            if eos_token_id is not None and bool(sess.finished.all()):
+                break
+            n = min(chunk, remaining)
+            stack.graph_launches += self._count_graph(ctx, sess, n)
+            if criteria:
+                stop = first_hit(n_tokens, n_tokens + n)
+            remaining -= n
+            n_tokens += n
+        if stop is not None:
+            n_tokens = stop
         seqs = sess.seqs[:, :P + n_tokens]
         if eos_token_id is not None:
             # HF stops as soon as every sequence has emitted eos: trim the pad-only columns of the last chunk
@@ -445,6 +432,7 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             if bool(is_eos.any(1).all()):
                 first = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full_like(gen[:, 0], gen.shape[1]))
                 seqs = seqs[:, :P + int(first.max()) + 1]
+        sess.cache.length = seqs.shape[1] - 1   # rows written by discarded steps of the last chunk are ignored
         seqs = seqs.clone()
         if not return_dict_in_generate:
             return seqs

@@ -20,7 +20,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libullava_sm100.so")
 
-ABI_VERSION = 2   # ULLAVA_ABI_VERSION of include/ullava_sm100.h (struct layouts and signatures mirrored below)
+ABI_VERSION = 3   # ULLAVA_ABI_VERSION of include/ullava_sm100.h (struct layouts and signatures mirrored below)
 BF16, F16, F32 = 0, 1, 2
 EPI_NONE, EPI_RELU, EPI_GELU, EPI_QUICK_GELU, EPI_SILU_MUL = 0, 1, 2, 3, 4
 SAM_N_WEIGHTS = 121
@@ -79,7 +79,7 @@ class DecodeArgs(C.Structure):
     _fields_ = [("llama", LlamaArgs), ("pos_dev", _vp), ("embed_table", _vp), ("vocab", _i32), ("lm_head", _vp),
                 ("cur_ids", _vp), ("logits", _vp), ("seqs", _vp), ("seqs_ld", _i64), ("hid_buf", _vp),
                 ("hid_bs", _i64), ("finished", _vp), ("eos_id", _i32), ("pad_id", _i32),
-                ("uniforms", _vp), ("uniforms_ld", _i64), ("temperature", _f32), ("top_p", _f32)]
+                ("uniforms", _vp), ("uniforms_ld", _i64), ("temperature", _f32), ("top_p", _f32), ("top_k", _i32)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/ullava_sm100.h
@@ -127,7 +127,7 @@ _SIGNATURES = {
     "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
     "ullava_greedy_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
                                   _vp, _vp]),
-    "ullava_sample_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64,
+    "ullava_sample_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64,
                                   _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ullava_mask_iou_counts": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "ullava_seg_meter_update": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
@@ -547,14 +547,16 @@ class Context:
         return out
 
     def sample_step(self, logits, temperature, top_p, uniforms, cur_ids, seqs=None, final_h=None, hid_buf=None,
-                    finished=None, eos_id=-1, pad_id=0, pos_dev=None, probs_out=None):
-        """Temperature / top-p draw per row by inverse CDF with the caller's uniforms[pos, b]; bookkeeping as
-        greedy_step.  probs_out (optional [rows, cols] fp32) receives the filtered, renormalised distribution."""
+                    finished=None, eos_id=-1, pad_id=0, pos_dev=None, probs_out=None, top_k=0):
+        """Temperature / top-k / top-p draw per row by inverse CDF with the caller's uniforms[pos, b]; bookkeeping as
+        greedy_step.  probs_out (optional [rows, cols] fp32) receives the filtered, renormalised distribution.
+        top_k = 0 / top_p = None switch the filters off (HF's default top_k = 50 is applied by generate())."""
         rows, cols = logits.shape
         assert uniforms.dtype == torch.float32 and uniforms.dim() == 2 and uniforms.stride(1) == 1
         self._chk(self.lib.ullava_sample_step(
             self.handle, logits.data_ptr(), logits.stride(0), rows, cols, float(temperature),
-            float(top_p if top_p is not None else 1.0), uniforms.data_ptr(), uniforms.stride(0), cur_ids.data_ptr(),
+            float(top_p if top_p is not None else 1.0), int(top_k or 0), uniforms.data_ptr(), uniforms.stride(0),
+            cur_ids.data_ptr(),
             _ptr(seqs), seqs.stride(0) if seqs is not None else 0, _ptr(final_h), _ptr(hid_buf),
             hid_buf.stride(0) if hid_buf is not None else 0, final_h.shape[-1] if final_h is not None else 8,
             _ptr(finished), int(eos_id), int(pad_id), _ptr(pos_dev), _ptr(probs_out), _stream()))
