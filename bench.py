@@ -58,6 +58,10 @@ def parse_args():
     ap.add_argument("--new-tokens", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="run the SAM image encoder after the decode steps instead of beside them (SM partition off)")
+    ap.add_argument("--overlap-sms", type=int, default=0,
+                    help="SMs of the decode lane of the SM partition (default: the model's, ULLAVA_OVERLAP_SMS)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="one resident step only, no e2e / stages / cpu baseline (for runs under ncu)")
     return ap.parse_args()
@@ -349,6 +353,10 @@ def run_b200(args):
     ctx = native.Context.get(local)
     model = build_model(dev, dtype)
     model.pack_mask_bits = True
+    if args.no_overlap:
+        model.overlap_sam = False
+    if args.overlap_sms:
+        model.overlap_sms_decode = args.overlap_sms
     h_ids, h_img, h_sam = make_inputs(lo, hi, dtype)
     sizes = [(IMG, IMG)] * B
     resizes = [(SAM_IMG, SAM_IMG)] * B
@@ -397,7 +405,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        n0 = ctx.launch_count() + model.llm.graph_kernel_launches()
+        n0 = native.Context.total_launches(local) + model.llm.graph_kernel_launches()
         st0 = torch.cuda.memory_stats(dev)
         e0.record()
         for i in range(steps):
@@ -420,12 +428,12 @@ def run_b200(args):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if ws > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), ctx.launch_count() + model.llm.graph_kernel_launches() - n0, r
+        return float(ms.item()), native.Context.total_launches(local) + model.llm.graph_kernel_launches() - n0, r
 
     if args.profile_mode:
         step_resident()
         torch.cuda.synchronize()
-        print(json.dumps({"profile_mode": True, "launches": ctx.launch_count() + model.llm.graph_kernel_launches()}))
+        print(json.dumps({"profile_mode": True, "launches": native.Context.total_launches(local) + model.llm.graph_kernel_launches()}))
         return
 
     sampler = ClockSampler(physical_gpu_index(local))
@@ -452,12 +460,14 @@ def run_b200(args):
         tl = model.timeline
         model.timeline = None
         stages = {tl[i][0]: tl[i - 1][1].elapsed_time(tl[i][1]) for i in range(1, len(tl))}
-        model.llm.use_cuda_graph = False
+        # per-kernel-class events: one context, one stream, eager launches (no graph, no SM partition)
+        overlap = model.overlap_sam
+        model.llm.use_cuda_graph, model.overlap_sam = False, False
         ctx.profile_begin()
         step_resident()
         torch.cuda.synchronize()
         prof = ctx.profile_end()
-        model.llm.use_cuda_graph = True
+        model.llm.use_cuda_graph, model.overlap_sam = True, overlap
 
     if ws > 1:
         dist.barrier()
@@ -487,6 +497,12 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(h_ids.numel() * 8 + h_img.numel() * 2 + h_sam.numel() * 2),
                     "d2h_bytes_per_step": int(h_out_ids.numel() * 8 + h_masks.numel() * 4 + h_gather.numel() * 4)},
             "masks_per_step": n_masks, "timed_region": info_res, "timed_region_e2e": info_e2e}
+    parts = list(native.Partition._by_key.values())
+    if model.overlap_sam and parts:
+        line["overlap"] = {"sam_encoder_beside_decode": True, "sms_decode_lane": parts[0].sms[0],
+                           "sms_sam_lane": parts[0].sms[1], "how": "CUDA green contexts (ullava_partition)"}
+    else:
+        line["overlap"] = {"sam_encoder_beside_decode": False}
     if stages:
         line["stages_ms"] = {k: round(v, 3) for k, v in stages.items()}
     if prof:

@@ -64,13 +64,31 @@ enum ullava_epilogue {
 /* ---- life cycle ---------------------------------------------------------------------- */
 ULLAVA_API int ullava_abi_version(void);
 ULLAVA_API const char* ullava_last_error(void);
-/* Creates a per-device context (device must be compute capability 10.x). */
+/* Creates a context on `device` (compute capability 10.x).  A context carries per-launch-sequence state (scratch
+ * workspace with the stream-K arrival counters, the next-weight prefetch hint, launch counters): it serves ONE stream
+ * at a time.  Stages that run concurrently on two streams (see ullava_partition below) use one context each. */
 ULLAVA_API int ullava_create(int device, ullava_ctx** out);
 ULLAVA_API int ullava_destroy(ullava_ctx* ctx);
 /* Registers caller-owned scratch memory (split-K partials, attention scratch). 256 B aligned. */
 ULLAVA_API int ullava_set_workspace(ullava_ctx* ctx, void* ptr, size_t bytes);
 /* Number of kernels this context has enqueued so far (bench.py's gpu_launches). */
 ULLAVA_API int64_t ullava_launch_count(ullava_ctx* ctx);
+
+/* ---- SM partition (csrc/partition.cu) ------------------------------------------------------------------------
+ * Two streams whose kernels run on disjoint SM sets of one device (CUDA green contexts): lane A gets `sms_a` SMs
+ * (rounded up to the architecture's granularity, 8 on sm_100), lane B the rest.  priority_*: CUDA stream priorities
+ * (0 = default, negative = higher).  UllavaForCausalLM.evaluate (reference models/ullava.py:335-434, which runs
+ * generate and get_visual_embs back to back) uses it to run the HBM-bound decode steps on lane A while the
+ * tensor-bound SAM ViT-H encoder runs on lane B.  ullava_set_sm_limit sizes a context's persistent grids and
+ * stream-K splits for `sms` SMs (0 = the whole device) -- set it to the lane's SM count on the lane's context. */
+typedef struct ullava_partition ullava_partition;
+ULLAVA_API int ullava_partition_create(int device, int32_t sms_a, int32_t priority_a, int32_t priority_b,
+                                       ullava_partition** out);
+ULLAVA_API int ullava_partition_info(const ullava_partition* p, int32_t* sms_a, int32_t* sms_b, void** stream_a,
+                                     void** stream_b);
+ULLAVA_API int ullava_partition_destroy(ullava_partition* p);
+ULLAVA_API int ullava_set_sm_limit(ullava_ctx* ctx, int32_t sms);
+ULLAVA_API int ullava_sm_count(ullava_ctx* ctx);
 
 /* CUDA-event profiler by kernel class (bench.py's live roofline measurement).  Between begin and end every
  * kernel-launching entry point brackets its launches with events on the caller's stream; end synchronises

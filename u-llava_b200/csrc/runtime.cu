@@ -146,7 +146,7 @@ int ullava_create(int device, ullava_ctx** out) {
   }
   ullava_ctx* c = new ullava_ctx();
   c->device = device;
-  c->sm_count = prop.multiProcessorCount;
+  c->sm_count = c->device_sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("ULLAVA_PREFETCH_UNITS")) {
     const int v = atoi(e);
     if (v >= 0 && v <= 256) c->prefetch_units = v;

@@ -15,7 +15,9 @@ struct ullava_prof_rec {
 
 struct ullava_ctx {
   int device = 0;
-  int sm_count = 148;
+  int device_sm_count = 148;  // SMs of the device
+  int sm_count = 148;         // SMs this context sizes persistent grids / stream-K splits for: the device's, or the SM
+                              // partition's when the context serves one lane of an ullava_partition (ullava_set_sm_limit)
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int64_t launches = 0;

@@ -315,7 +315,7 @@ class DecodeSession:
         self.hid_buf = torch.empty((batch, max_seq - 1, H), dtype=dt, device=dev) if keep_hidden else None
         self.scratch = torch.empty(ctx.llama_scratch_bytes(batch, H, stack.cfg["ffn"]), dtype=torch.uint8, device=dev)
         self.embed_table, self.lm_head = embed_table, lm_head
-        self.graph = None
+        self.graphs = {}          # id(step context) -> (CUDAGraph, kernel nodes): persistent grids are sized per context
         self.graph_nodes = 0
         self.eos_id, self.pad_id = -1, 0
         self.sampling = None      # None = greedy, else (temperature, top_p, top_k)
@@ -358,7 +358,7 @@ class DecodeSession:
         if self.args is None or eos != self.eos_id or int(pad_id) != self.pad_id or sampling != self.sampling:
             self.eos_id, self.pad_id, self.sampling = eos, int(pad_id), sampling
             self._build_args()
-            self.graph = None  # eos / pad ids and the sampling parameters are baked into the captured kernel arguments
+            self.graphs = {}   # eos / pad ids and the sampling parameters are baked into the captured kernel arguments
         P = input_ids.shape[1]
         self.cache.length = 0
         self.finished.zero_()
@@ -377,29 +377,38 @@ class DecodeSession:
             self.ctx.greedy_step(self.logits, self.cur_ids, self.seqs, last_final, self.hid_buf, self.finished,
                                  self.eos_id, self.pad_id, self.pos)
 
-    def steps(self, n: int, use_graph: bool = True) -> int:
-        """Runs n decode steps; returns the number of native kernels launched through graph REPLAYS (eager
-        launches are counted by ullava_launch_count; the phantom increments made while capturing are cancelled)."""
+    def steps(self, n: int, use_graph: bool = True, ctx=None) -> int:
+        """Runs n decode steps on the current stream; returns the number of native kernels launched through graph
+        REPLAYS (eager launches are counted by ullava_launch_count; the phantom increments made while capturing are
+        cancelled).  ctx: the context the steps are launched through (default: the session's) -- a partition lane's
+        context when the decode loop runs on an SM partition (native.Partition); one graph is kept per context."""
         if n <= 0:
             return 0
+        ctx = ctx or self.ctx
         replayed = 0
         done = 0
-        if use_graph and self.graph is None:
-            self.ctx.llama_decode_step(self.args)  # eager warm-up step (also a real step)
+        entry = self.graphs.get(id(ctx))
+        if use_graph and entry is None:
+            ctx.llama_decode_step(self.args)  # eager warm-up step (also a real step)
             done = 1
             if n > 1:
-                c0 = self.ctx.launch_count()
+                c0 = ctx.launch_count()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.ctx.llama_decode_step(self.args)
-                self.graph_nodes = self.ctx.launch_count() - c0
-                replayed -= self.graph_nodes  # capture bumped the native counter without launching anything
-                self.graph = g
+                cur = torch.cuda.current_stream()
+                # on a partition lane the capture has to happen on the lane's own (green-context) stream, so that the
+                # kernel nodes stay confined to the lane's SMs; the legacy default stream cannot capture at all
+                on_lane = cur != torch.cuda.default_stream(cur.device)
+                with torch.cuda.graph(g, **(dict(stream=cur) if on_lane else {})):
+                    ctx.llama_decode_step(self.args)
+                nodes = ctx.launch_count() - c0
+                replayed -= nodes  # capture bumped the native counter without launching anything
+                entry = self.graphs[id(ctx)] = (g, nodes)
+                self.graph_nodes = nodes
         for _ in range(n - done):
-            if use_graph and self.graph is not None:
-                self.graph.replay()
-                replayed += self.graph_nodes
+            if use_graph and entry is not None:
+                entry[0].replay()
+                replayed += entry[1]
             else:
-                self.ctx.llama_decode_step(self.args)
+                ctx.llama_decode_step(self.args)
         self.cache.length += n
         return replayed

@@ -169,7 +169,8 @@ class ImageEncoderViT(nn.Module):
         if self._packed is None or self._packed[0] != sig:
             self._packed = (sig,) + self._pack()
         _, tensors, table, cfg = self._packed
-        ctx = native.Context.get(x.device)
+        # native_ctx: the context of the SM-partition lane this call is enqueued on (UllavaForCausalLM.evaluate)
+        ctx = getattr(self, "native_ctx", None) or native.Context.get(x.device)
         win, unwin = self._row_maps(x.shape[0], x.device)
         out, self._scratch = ctx.sam_encoder_forward(table, len(tensors), x.to(tensors[0].dtype).contiguous(), cfg, win,
                                                      unwin, self._scratch)

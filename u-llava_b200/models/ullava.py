@@ -13,6 +13,8 @@ Training (inference=False) is outside the hot path and raises."""
 from __future__ import annotations
 
 import copy
+import os
+import warnings
 from typing import List
 
 import torch
@@ -69,6 +71,12 @@ class UllavaForCausalLM(PreTrainedModel):
         self.pack_mask_bits = False
         self.last_mask_bits = None
         self.timeline = None  # list of (stage name, torch.cuda.Event) when stage timing is requested
+        # evaluate(): run the SAM ViT-H image encoder (tensor-bound, depends on images_sam only) CONCURRENTLY with the
+        # decode steps (HBM-bound) on a spatial split of the SMs (native.Partition, CUDA green contexts): the decode
+        # lane gets `overlap_sms_decode` SMs and the higher stream priority, the encoder the rest.
+        self.overlap_sam = os.environ.get("ULLAVA_OVERLAP", "1") != "0"
+        self.overlap_sms_decode = int(os.environ.get("ULLAVA_OVERLAP_SMS", "72"))
+        self.overlap_min_batch = 4   # below this the encoder is too short for the split to pay
 
     def _mark(self, name: str):
         if self.timeline is not None:
@@ -201,24 +209,65 @@ class UllavaForCausalLM(PreTrainedModel):
         return {"pred_masks": pred_masks, "pred_boxes": pred_boxes, "gt_masks": mask_list, "gt_boxes": bbox_list,
                 "logits": output.logits}
 
+    def _partition(self, device, batch: int):
+        """The SM partition evaluate() overlaps on, or None (switched off, batch too small, driver without green
+        contexts -- the stages then simply run back to back on the caller's stream)."""
+        if not self.overlap_sam or batch < self.overlap_min_batch or max(1, int(self.overlap_sms_decode)) < 8:
+            return None
+        try:
+            return native.Partition.get(device, int(self.overlap_sms_decode))
+        except native.NativeError as e:
+            warnings.warn(f"SM partition unavailable ({e}); evaluate() runs its stages back to back")
+            self.overlap_sam = False
+            return None
+
     def evaluate(self, images_sam, images, input_ids, raw_size_list, resize_list, max_new_tokens=32, temperature=0.2,
                  top_p=None, num_beams=1, no_repeat_ngram_size=None, stopping_criteria=None, attention_mask=None):
         """Reference signature (models/ullava.py:335-345) plus `attention_mask` (optional): a right-padded batch of
-        prompts of different lengths, as the reference collator builds it (dataset/collators/base_collator.py:28-44)."""
+        prompts of different lengths, as the reference collator builds it (dataset/collators/base_collator.py:28-44).
+
+        Same results as the reference's order (generate, then get_visual_embs, :349-399); the image encoder does not
+        depend on the generated tokens, so with overlap_sam it is enqueued on the second lane of an SM partition as soon
+        as the prefill is queued and runs under the decode steps."""
         with torch.inference_mode():
             self._mark("start")
             self.llm.timeline = self.timeline
+            part = self._partition(input_ids.device, input_ids.shape[0])
+            side = {}
+            kw = {}
+            if part is not None:
+                main = torch.cuda.current_stream()
+                enc = self.visual_model.image_encoder
+
+                def after_prefill():
+                    lane_ctx, lane_stream = part.ctx[1], part.streams[1]
+                    lane_stream.wait_stream(main)           # inputs (and the prefill before them) are ordered first
+                    with torch.cuda.stream(lane_stream):
+                        enc.native_ctx = lane_ctx
+                        try:
+                            side["emb"] = self.get_visual_embs(images_sam)
+                        finally:
+                            enc.native_ctx = None
+                        side["done"] = torch.cuda.Event()
+                        side["done"].record(lane_stream)
+
+                kw = dict(_after_prefill=after_prefill, _decode_lane=(part.ctx[0], part.streams[0]))
             outputs = self.llm.generate(input_ids=input_ids, images=images, max_new_tokens=max_new_tokens,
                                         num_beams=num_beams, top_p=top_p, do_sample=True if temperature > 0 else False,
                                         temperature=temperature, output_hidden_states=True,
                                         return_dict_in_generate=True, no_repeat_ngram_size=no_repeat_ngram_size,
-                                        stopping_criteria=stopping_criteria, attention_mask=attention_mask)
+                                        stopping_criteria=stopping_criteria, attention_mask=attention_mask, **kw)
             output_ids = outputs.sequences
             last_hidden = outputs.hidden_states[-1][-1]
             self.llm.timeline = None
             self._mark("decode")
             counts = self._seg_loc_counts(output_ids)   # host sync here, while nothing else is queued
-            image_embeddings = self.get_visual_embs(images_sam)
+            if "emb" in side:
+                torch.cuda.current_stream().wait_event(side["done"])
+                image_embeddings = side["emb"]
+                image_embeddings.record_stream(torch.cuda.current_stream())
+            else:
+                image_embeddings = self.get_visual_embs(images_sam)
             self._mark("sam_encoder")
             pred_masks, pred_boxes, bits = self._decode_heads(output_ids, last_hidden, image_embeddings, raw_size_list,
                                                               resize_list, pack_bits=self.pack_mask_bits, counts=counts)

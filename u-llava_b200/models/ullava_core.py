@@ -363,23 +363,31 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             seqs = input_ids.clone()
             return GenerateOutput(sequences=seqs, hidden_states=None, past_key_values=None) \
                 if return_dict_in_generate else seqs
+        after_prefill = kwargs.pop("_after_prefill", None)   # callable run once the prefill has been enqueued
+        decode_lane = kwargs.pop("_decode_lane", None)       # (native.Context, torch stream) of an SM partition lane
         crit = []
         if stopping_criteria is not None:
             crit = list(stopping_criteria) if isinstance(stopping_criteria, (list, tuple)) or \
                 hasattr(stopping_criteria, "__iter__") else [stopping_criteria]
         return self._generate_device(ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id,
                                      pad_token_id, output_hidden_states, return_dict_in_generate,
-                                     sampling=sampling, generator=generator, lengths=lengths, criteria=crit)
+                                     sampling=sampling, generator=generator, lengths=lengths, criteria=crit,
+                                     after_prefill=after_prefill, decode_lane=decode_lane)
 
     CRITERIA_CHUNK = 8   # decode steps between two host checks (EOS of every row / stopping criteria)
 
     def _generate_device(self, ctx, stack, input_ids, images, videos, max_new_tokens, eos_token_id, pad_token_id,
                          output_hidden_states, return_dict_in_generate, sampling=None, generator=None,
-                         lengths=None, criteria=()):
+                         lengths=None, criteria=(), after_prefill=None, decode_lane=None):
         """Greedy (or, with `sampling` = (temperature, top_p, top_k), sampling) loop with all per-step state on the
         device: prefill, then max_new_tokens-1 replays of ONE captured decode-step graph (the position is read from
         device memory).  The host only synchronises every CRITERIA_CHUNK steps, and only when an eos id or stopping
-        criteria are set."""
+        criteria are set.
+
+        decode_lane = (context, stream) of one lane of an SM partition (native.Partition): the decode steps are then
+        launched through that context into that stream (the prefill stays on the caller's stream and the whole
+        machine); after_prefill() is called once the prefill is enqueued -- UllavaForCausalLM.evaluate uses the pair to
+        run the SAM image encoder on the other lane while the HBM-bound decode steps run on this one."""
         B, P = input_ids.shape
         H = self.config.hidden_size
         T = P + max_new_tokens
@@ -392,11 +400,28 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         if sess.hid_buf is not None:
             ctx.copy_rows(final, sess.hid_buf, B, P, H, P * H, H, sess.hid_buf.stride(0), H)
         self._mark("prefill")
+        if after_prefill is not None:
+            after_prefill()
         if lengths is None:
             last = final.view(B, P, H)[:, -1].contiguous()
         else:   # last VALID position of every row; first_token() also stores it as the state of column P - 1
             last = final.view(B, P, H)[torch.arange(B, device=final.device), (lengths - 1).long()].contiguous()
         sess.first_token(last, P)
+        step_ctx = None
+        caller_stream = torch.cuda.current_stream()
+        if decode_lane is not None:
+            step_ctx, lane_stream = decode_lane
+            lane_stream.wait_stream(caller_stream)
+            torch.cuda.set_stream(lane_stream)
+        try:
+            n_tokens = self._decode_loop(sess, P, max_new_tokens, eos_token_id, criteria, step_ctx, stack)
+        finally:
+            if decode_lane is not None:
+                torch.cuda.set_stream(caller_stream)
+                caller_stream.wait_stream(decode_lane[1])
+        return self._finish_generate(sess, P, n_tokens, eos_token_id, output_hidden_states, return_dict_in_generate)
+
+    def _decode_loop(self, sess, P, max_new_tokens, eos_token_id, criteria, step_ctx, stack) -> int:
 
         def first_hit(n_from, n_to):
             """Calls the criteria on the prefixes holding n_from+1 .. n_to generated tokens, in order, the way HF calls
@@ -417,13 +442,14 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
             if eos_token_id is not None and bool(sess.finished.all()):
                 break
             n = min(chunk, remaining)
-            stack.graph_launches += self._count_graph(ctx, sess, n)
+            stack.graph_launches += sess.steps(n, use_graph=self.use_cuda_graph, ctx=step_ctx)
             if criteria:
                 stop = first_hit(n_tokens, n_tokens + n)
             remaining -= n
             n_tokens += n
-        if stop is not None:
-            n_tokens = stop
+        return n_tokens if stop is None else stop
+
+    def _finish_generate(self, sess, P, n_tokens, eos_token_id, output_hidden_states, return_dict_in_generate):
         seqs = sess.seqs[:, :P + n_tokens]
         if eos_token_id is not None:
             # HF stops as soon as every sequence has emitted eos: trim the pad-only columns of the last chunk
@@ -440,9 +466,6 @@ class UllavaCoreForCausalLM(LlamaForCausalLM):
         if output_hidden_states:
             hs = ((sess.hid_buf[:, : seqs.shape[1] - 1].clone(),),)
         return GenerateOutput(sequences=seqs, hidden_states=hs, past_key_values=sess.cache)
-
-    def _count_graph(self, ctx, sess, n):
-        return sess.steps(n, use_graph=self.use_cuda_graph)
 
     def prepare_inputs_for_generation(self, input_ids=None, inputs_embeds=None, attention_mask=None, images=None,
                                       videos=None, labels=None, past_key_values=None, **kwargs):

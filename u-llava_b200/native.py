@@ -90,6 +90,11 @@ _SIGNATURES = {
     "ullava_destroy": (_i32, [_vp]),
     "ullava_set_workspace": (_i32, [_vp, _vp, _sz]),
     "ullava_launch_count": (_i64, [_vp]),
+    "ullava_partition_create": (_i32, [_i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "ullava_partition_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp)]),
+    "ullava_partition_destroy": (_i32, [_vp]),
+    "ullava_set_sm_limit": (_i32, [_vp, _i32]),
+    "ullava_sm_count": (_i32, [_vp]),
     "ullava_profile_begin": (_i32, [_vp]),
     "ullava_profile_end": (_i32, [_vp, C.POINTER(C.c_double)]),
     "ullava_gemm": (_i32, [_vp, C.POINTER(GemmArgs), _vp]),
@@ -216,7 +221,9 @@ class NativeError(RuntimeError):
 
 
 class Context:
-    """Per-device handle (ullava_create).  Owns a torch-allocated scratch workspace."""
+    """Handle of ullava_create: one per (device, lane).  Owns a torch-allocated scratch workspace.  A context serves
+    one stream at a time (workspace, stream-K counters and the prefetch hint are per context); lane 0 is the default,
+    Partition (below) creates one more context per concurrent lane."""
 
     _by_device = {}
 
@@ -234,20 +241,35 @@ class Context:
         self._chk(self.lib.ullava_set_workspace(self.handle, self.workspace.data_ptr(), workspace_bytes))
 
     @classmethod
-    def get(cls, device=None) -> "Context":
+    def get(cls, device=None, lane: int = 0) -> "Context":
         if device is None:
             device = torch.cuda.current_device()
         if isinstance(device, torch.device):
             device = device.index if device.index is not None else torch.cuda.current_device()
-        ctx = cls._by_device.get(device)
+        ctx = cls._by_device.get((device, lane))
         if ctx is None:
             ctx = cls(device)
-            cls._by_device[device] = ctx
+            cls._by_device[(device, lane)] = ctx
         return ctx
+
+    def set_sm_limit(self, sms: int):
+        """Size persistent grids / stream-K splits for `sms` SMs (0 = the whole device): the SM count of the partition
+        lane this context launches into."""
+        self._chk(self.lib.ullava_set_sm_limit(self.handle, int(sms)))
+
+    def sm_count(self) -> int:
+        return int(self.lib.ullava_sm_count(self.handle))
 
     def _chk(self, st: int):
         if st != 0:
             raise NativeError(f"libullava_sm100 error {st}: {self.lib.ullava_last_error().decode()}")
+
+    @classmethod
+    def total_launches(cls, device=None) -> int:
+        """Kernels enqueued by every lane's context of `device`."""
+        if isinstance(device, torch.device):
+            device = device.index
+        return sum(c.launch_count() for (d, _), c in cls._by_device.items() if device is None or d == device)
 
     def launch_count(self) -> int:
         return int(self.lib.ullava_launch_count(self.handle))
@@ -675,3 +697,40 @@ class Context:
 
     def llama_scratch_bytes(self, rows, hidden, ffn) -> int:
         return int(self.lib.ullava_llama_scratch_bytes(rows, hidden, ffn))
+
+
+class Partition:
+    """ullava_partition: two torch streams on disjoint SM sets of one device plus one Context per lane, sized to the
+    lane (lane A: `sms_a` SMs, high priority -- the latency-sensitive decode steps; lane B: the rest)."""
+
+    _by_key = {}
+
+    def __init__(self, device: int, sms_a: int):
+        lib = load_library()
+        h = _vp()
+        st = lib.ullava_partition_create(int(device), int(sms_a), -1, 0, C.byref(h))
+        if st != 0:
+            raise NativeError(f"ullava_partition_create failed ({st}): {lib.ullava_last_error().decode()}")
+        self.lib, self.handle, self.device = lib, h, device
+        a, b, sa, sb = _i32(), _i32(), _vp(), _vp()
+        lib.ullava_partition_info(h, C.byref(a), C.byref(b), C.byref(sa), C.byref(sb))
+        self.sms = (a.value, b.value)
+        dev = torch.device("cuda", device)
+        self.streams = (torch.cuda.ExternalStream(sa.value, device=dev), torch.cuda.ExternalStream(sb.value, device=dev))
+        self.ctx = (Context.get(device, lane=1), Context.get(device, lane=2))
+        self.ctx[0].set_sm_limit(self.sms[0])
+        self.ctx[1].set_sm_limit(self.sms[1])
+
+    @classmethod
+    def get(cls, device, sms_a: int) -> "Partition":
+        if isinstance(device, torch.device):
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        key = (device, sms_a)
+        p = cls._by_key.get(key)
+        if p is None:
+            for (d, _), q in cls._by_key.items():
+                if d == device:
+                    raise NativeError("one SM partition per device (its lanes own contexts 1 and 2)")
+            p = cls(device, sms_a)
+            cls._by_key[key] = p
+        return p
