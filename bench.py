@@ -62,6 +62,8 @@ def parse_args():
                     help="run the SAM image encoder after the decode steps instead of beside them (SM partition off)")
     ap.add_argument("--overlap-sms", type=int, default=0,
                     help="SMs of the decode lane of the SM partition (default: the model's, ULLAVA_OVERLAP_SMS)")
+    ap.add_argument("--overlap-blocks", type=int, default=0,
+                    help="SAM encoder blocks run on the second lane beside the decode steps (default: the model's)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="one resident step only, no e2e / stages / cpu baseline (for runs under ncu)")
     return ap.parse_args()
@@ -357,6 +359,8 @@ def run_b200(args):
         model.overlap_sam = False
     if args.overlap_sms:
         model.overlap_sms_decode = args.overlap_sms
+    if args.overlap_blocks:
+        model.overlap_sam_blocks = args.overlap_blocks
     h_ids, h_img, h_sam = make_inputs(lo, hi, dtype)
     sizes = [(IMG, IMG)] * B
     resizes = [(SAM_IMG, SAM_IMG)] * B
@@ -500,7 +504,8 @@ def run_b200(args):
     parts = list(native.Partition._by_key.values())
     if model.overlap_sam and parts:
         line["overlap"] = {"sam_encoder_beside_decode": True, "sms_decode_lane": parts[0].sms[0],
-                           "sms_sam_lane": parts[0].sms[1], "how": "CUDA green contexts (ullava_partition)"}
+                           "sms_sam_lane": parts[0].sms[1], "sam_blocks_on_lane": model.overlap_sam_blocks,
+                           "how": "CUDA green contexts (ullava_partition)"}
     else:
         line["overlap"] = {"sam_encoder_beside_decode": False}
     if stages:

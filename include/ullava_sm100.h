@@ -307,6 +307,11 @@ typedef struct ullava_sam_encoder_args {
   uint64_t global_mask;     /* bit l set: block l uses global attention */
   float eps;                /* LayerNorm eps of the blocks (1e-6) */
   int32_t dtype;
+  /* Block range [block_begin, block_end) of this call (block_end <= 0: depth).  The patch embedding runs when
+   * block_begin == 0, the neck + NCHW store when the range ends at `depth`; the token state lives in `scratch`
+   * between two calls (same scratch, same batch), so the encoder can be cut into a part that runs on an SM-partition
+   * lane beside the decode steps and a remainder that runs on the whole machine afterwards. */
+  int32_t block_begin, block_end;
 } ullava_sam_encoder_args;
 ULLAVA_API int ullava_sam_encoder_forward(ullava_ctx* ctx, const ullava_sam_encoder_args* args, void* stream);
 ULLAVA_API size_t ullava_sam_encoder_scratch_bytes(int32_t batch, int32_t img, int32_t patch, int32_t embed_dim, int32_t window,

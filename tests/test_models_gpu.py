@@ -502,7 +502,8 @@ def test_evaluate_overlapped_equals_back_to_back(ctx, dtype, use_graph):
     m.overlap_sam = False
     s0, m0, b0 = m.evaluate(*args, max_new_tokens=6, temperature=0)
     m.overlap_sam, m.overlap_min_batch = True, 1
-    for _ in range(2):
+    for blocks in (1, 2):     # the 2-block encoder cut after its first block / run completely on the lane
+        m.overlap_sam_blocks = blocks
         s1, m1, b1 = m.evaluate(*args, max_new_tokens=6, temperature=0)
         assert m.overlap_sam, "the SM partition could not be created on this device"
         assert torch.equal(s0, s1)

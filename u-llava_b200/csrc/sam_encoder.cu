@@ -101,6 +101,9 @@ int sam_encoder_run(Context* ctx, const ullava_sam_encoder_args& a, cudaStream_t
   ULLAVA_REQUIRE(a.scratch_bytes >= sam_encoder_scratch(B, a.img, a.patch, D, ws, C), "sam_encoder: scratch too small");
   const int kp = 3 * a.patch * a.patch;
   ULLAVA_REQUIRE(kp % 8 == 0, "sam_encoder: 3*patch*patch must be a multiple of 8");
+  const int blk0 = a.block_begin, blk1 = a.block_end <= 0 ? a.depth : a.block_end;
+  ULLAVA_REQUIRE(blk0 >= 0 && blk0 <= blk1 && blk1 <= a.depth, "sam_encoder: block range [%d, %d) outside [0, %d]", blk0,
+                 blk1, a.depth);
 
   uint8_t* base = static_cast<uint8_t*>(a.scratch);
   size_t off = 0;
@@ -120,15 +123,18 @@ int sam_encoder_run(Context* ctx, const ullava_sam_encoder_args& a, cudaStream_t
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
 
   // ---- patch embedding (+bias, +pos_embed per image) ----
-  RUN(vit_im2col_run(ctx, a.pixels, act, B, a.img, a.patch, kp, dt, s));
-  for (int b = 0; b < B; ++b) {
-    const uint16_t* A = static_cast<const uint16_t*>(act) + static_cast<size_t>(b) * N * kp;
-    uint16_t* Dst = static_cast<uint16_t*>(x) + static_cast<size_t>(b) * N * D;
-    RUN(gemm(ctx, s, dt, A, kp, W[0], kp, Dst, D, N, D, kp, W[1], EPI_NONE, W[2], D));
+  if (blk0 == 0) {
+    RUN(vit_im2col_run(ctx, a.pixels, act, B, a.img, a.patch, kp, dt, s));
+    for (int b = 0; b < B; ++b) {
+      const uint16_t* A = static_cast<const uint16_t*>(act) + static_cast<size_t>(b) * N * kp;
+      uint16_t* Dst = static_cast<uint16_t*>(x) + static_cast<size_t>(b) * N * D;
+      RUN(gemm(ctx, s, dt, A, kp, W[0], kp, Dst, D, N, D, kp, W[1], EPI_NONE, W[2], D));
+    }
+    // pad rows of the window layout stay zero from here on (only valid rows are ever rewritten)
+    if (any_window) RUN(check_cuda(cudaMemsetAsync(xw, 0, static_cast<size_t>(wrows) * D * 2, s), "zero window pads"));
   }
-  if (any_window) RUN(check_cuda(cudaMemsetAsync(xw, 0, static_cast<size_t>(wrows) * D * 2, s), "zero window pads"));
 
-  for (int l = 0; l < a.depth; ++l) {
+  for (int l = blk0; l < blk1; ++l) {
     const void* const* L = W + 3 + 14 * l;
     const bool global = ws <= 0 || ((a.global_mask >> l) & 1ull);
     AttnArgs at{};
@@ -158,6 +164,8 @@ int sam_encoder_run(Context* ctx, const ullava_sam_encoder_args& a, cudaStream_t
     RUN(gemm(ctx, s, dt, xn, D, L[10], D, act, 4 * D, rows, 4 * D, D, L[11], EPI_GELU, nullptr, 0));
     RUN(gemm(ctx, s, dt, act, 4 * D, L[12], 4 * D, x, D, rows, D, 4 * D, L[13], EPI_NONE, x, D));
   }
+
+  if (blk1 < a.depth) return OK;   // the remaining blocks and the neck come with a later call
 
   // ---- neck ----
   const void* const* Nk = W + 3 + 14 * a.depth;

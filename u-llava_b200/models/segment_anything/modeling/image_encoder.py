@@ -161,7 +161,7 @@ class ImageEncoderViT(nn.Module):
                 self._maps[key] = (win, unwin)
         return self._maps[key]
 
-    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+    def _forward_native(self, x: torch.Tensor, blocks=None) -> torch.Tensor:
         if x.device.type != "cuda":
             raise RuntimeError("ImageEncoderViT (B200 build) runs on a CUDA sm_100 device only; there is no CPU fallback")
         params = list(self.parameters())
@@ -173,8 +173,17 @@ class ImageEncoderViT(nn.Module):
         ctx = getattr(self, "native_ctx", None) or native.Context.get(x.device)
         win, unwin = self._row_maps(x.shape[0], x.device)
         out, self._scratch = ctx.sam_encoder_forward(table, len(tensors), x.to(tensors[0].dtype).contiguous(), cfg, win,
-                                                     unwin, self._scratch)
+                                                     unwin, self._scratch, blocks=blocks)
         return out
+
+    def forward_blocks(self, x: torch.Tensor, begin: int, end: int):
+        """Blocks [begin, end) only (patch embedding with begin == 0, neck with end == depth): the encoder cut in two
+        for UllavaForCausalLM.evaluate, which runs the first part on an SM-partition lane beside the decode steps.
+        Returns the embeddings from the call that ends at depth, None before."""
+        if x.shape[0] > self.max_images_per_pass:
+            raise ValueError("forward_blocks works on one pass of at most max_images_per_pass images")
+        with torch.no_grad():
+            return self._forward_native(x, blocks=(begin, end))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         n = self.max_images_per_pass

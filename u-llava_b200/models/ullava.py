@@ -74,8 +74,13 @@ class UllavaForCausalLM(PreTrainedModel):
         # evaluate(): run the SAM ViT-H image encoder (tensor-bound, depends on images_sam only) CONCURRENTLY with the
         # decode steps (HBM-bound) on a spatial split of the SMs (native.Partition, CUDA green contexts): the decode
         # lane gets `overlap_sms_decode` SMs and the higher stream priority, the encoder the rest.
+        # The decode steps barely slow down on ~100 of the 148 SMs while the encoder, on the remaining ones, gets
+        # through most of its blocks in that time; its last blocks + neck then run on the whole machine
+        # (`overlap_sam_blocks` = blocks done on the lane).  Measured curves: tools/bench_overlap.py, DESIGN.md section 5.
         self.overlap_sam = os.environ.get("ULLAVA_OVERLAP", "1") != "0"
-        self.overlap_sms_decode = int(os.environ.get("ULLAVA_OVERLAP_SMS", "72"))
+        self.overlap_sms_decode = int(os.environ.get("ULLAVA_OVERLAP_SMS", "88"))
+        # blocks of the encoder run on the lane; 0 = as many as fit under the decode steps (_blocks_under_decode)
+        self.overlap_sam_blocks = int(os.environ.get("ULLAVA_OVERLAP_BLOCKS", "0"))
         self.overlap_min_batch = 4   # below this the encoder is too short for the split to pay
 
     def _mark(self, name: str):
@@ -221,6 +226,23 @@ class UllavaForCausalLM(PreTrainedModel):
             self.overlap_sam = False
             return None
 
+    def _blocks_under_decode(self, enc, batch: int, max_new_tokens: int, sms_lane: int) -> int:
+        """How many encoder blocks fit under the decode steps.  Decode step: the 16-bit LLaMA weights + the KV rows
+        stream once per token at ~4.5 TB/s (+ ~10 % on the smaller lane); encoder block on the lane: its GEMM /
+        attention FLOPs at ~8 TFLOP/s per SM (tools/bench_overlap.py: ViT-H, B = 32, 60 SMs -> 11.5 ms per block).
+        A block too many costs more (it runs on a fraction of the machine while the rest idles) than a block too few
+        (it runs at full speed afterwards), hence the 0.9."""
+        c = self.llm.config
+        w_bytes = 2.0 * (c.num_hidden_layers * (4 * c.hidden_size ** 2 + 3 * c.hidden_size * c.intermediate_size) +
+                         c.vocab_size * c.hidden_size)
+        kv_bytes = batch * c.num_hidden_layers * 2 * 640 * c.hidden_size * 2.0
+        t_decode = 1.1 * max(max_new_tokens - 1, 0) * (w_bytes + kv_bytes) / 4.5e12
+        n_tok = (enc.img_size // enc.patch_size) ** 2
+        d = enc.embed_dim
+        flop_block = batch * n_tok * (24.0 * d * d + 4.0 * d * min(n_tok, max(enc.window_size, 1) ** 2 * 4))
+        t_block = flop_block / (8.0e12 * max(sms_lane, 1))
+        return max(1, min(enc.depth, int(0.9 * t_decode / max(t_block, 1e-9))))
+
     def evaluate(self, images_sam, images, input_ids, raw_size_list, resize_list, max_new_tokens=32, temperature=0.2,
                  top_p=None, num_beams=1, no_repeat_ngram_size=None, stopping_criteria=None, attention_mask=None):
         """Reference signature (models/ullava.py:335-345) plus `attention_mask` (optional): a right-padded batch of
@@ -235,9 +257,15 @@ class UllavaForCausalLM(PreTrainedModel):
             part = self._partition(input_ids.device, input_ids.shape[0])
             side = {}
             kw = {}
+            enc = self.visual_model.image_encoder
+            if part is not None and images_sam.shape[0] > enc.max_images_per_pass:
+                part = None                                  # several encoder passes: keep the simple order
             if part is not None:
                 main = torch.cuda.current_stream()
-                enc = self.visual_model.image_encoder
+                px = images_sam.to(next(enc.parameters()).dtype)
+                k = int(self.overlap_sam_blocks)
+                k = max(1, min(k, enc.depth)) if k > 0 else self._blocks_under_decode(
+                    enc, input_ids.shape[0], max_new_tokens, part.sms[1])
 
                 def after_prefill():
                     lane_ctx, lane_stream = part.ctx[1], part.streams[1]
@@ -245,11 +273,12 @@ class UllavaForCausalLM(PreTrainedModel):
                     with torch.cuda.stream(lane_stream):
                         enc.native_ctx = lane_ctx
                         try:
-                            side["emb"] = self.get_visual_embs(images_sam)
+                            side["emb"] = enc.forward_blocks(px, 0, k)       # None unless k == depth
                         finally:
                             enc.native_ctx = None
                         side["done"] = torch.cuda.Event()
                         side["done"].record(lane_stream)
+                    side["k"] = k
 
                 kw = dict(_after_prefill=after_prefill, _decode_lane=(part.ctx[0], part.streams[0]))
             outputs = self.llm.generate(input_ids=input_ids, images=images, max_new_tokens=max_new_tokens,
@@ -262,10 +291,13 @@ class UllavaForCausalLM(PreTrainedModel):
             self.llm.timeline = None
             self._mark("decode")
             counts = self._seg_loc_counts(output_ids)   # host sync here, while nothing else is queued
-            if "emb" in side:
+            if "done" in side:
                 torch.cuda.current_stream().wait_event(side["done"])
                 image_embeddings = side["emb"]
-                image_embeddings.record_stream(torch.cuda.current_stream())
+                if image_embeddings is None:                 # remaining blocks + neck on the whole machine
+                    image_embeddings = enc.forward_blocks(px, side["k"], enc.depth)
+                else:
+                    image_embeddings.record_stream(torch.cuda.current_stream())
             else:
                 image_embeddings = self.get_visual_embs(images_sam)
             self._mark("sam_encoder")

@@ -64,7 +64,7 @@ class SamEncoderArgs(C.Structure):
                 ("scratch", _vp), ("scratch_bytes", _sz), ("win_rows", _vp), ("unwin_rows", _vp),
                 ("batch", _i32), ("img", _i32), ("patch", _i32), ("embed_dim", _i32), ("depth", _i32),
                 ("heads", _i32), ("window", _i32), ("out_chans", _i32), ("global_mask", C.c_uint64),
-                ("eps", _f32), ("dtype", _i32)]
+                ("eps", _f32), ("dtype", _i32), ("block_begin", _i32), ("block_end", _i32)]
 
 
 class LlamaArgs(C.Structure):
@@ -526,17 +526,24 @@ class Context:
         self._chk(self.lib.ullava_vit_forward(self.handle, C.byref(a), _stream()))
         return out
 
-    def sam_encoder_forward(self, weight_table, n_weights, pixels, cfg: dict, win_rows, unwin_rows, scratch=None):
-        """SAM ViT image encoder: pixels [B,3,img,img] -> [B,out_chans,g,g] (NCHW)."""
+    def sam_encoder_forward(self, weight_table, n_weights, pixels, cfg: dict, win_rows, unwin_rows, scratch=None,
+                            blocks=None):
+        """SAM ViT image encoder: pixels [B,3,img,img] -> [B,out_chans,g,g] (NCHW).  blocks = (begin, end): only that
+        block range (patch embedding with begin == 0, neck + output with end == depth; the token state stays in
+        `scratch` between the calls); the output is returned (and allocated) by the call that ends at depth."""
         B = pixels.shape[0]
         g = cfg["img"] // cfg["patch"]
-        out = torch.empty((B, cfg["out_chans"], g, g), dtype=pixels.dtype, device=pixels.device)
+        b0, b1 = blocks if blocks is not None else (0, cfg["depth"])
+        last = b1 >= cfg["depth"]
+        out = torch.empty((B, cfg["out_chans"], g, g), dtype=pixels.dtype, device=pixels.device) if last else None
         sb = int(self.lib.ullava_sam_encoder_scratch_bytes(B, cfg["img"], cfg["patch"], cfg["embed_dim"],
                                                            cfg["window"], cfg["out_chans"]))
         if scratch is None or scratch.numel() < sb:
             scratch = torch.empty(sb, dtype=torch.uint8, device=pixels.device)
         a = SamEncoderArgs()
-        a.weights, a.n_weights, a.pixels, a.out = weight_table, n_weights, pixels.data_ptr(), out.data_ptr()
+        a.weights, a.n_weights, a.pixels = weight_table, n_weights, pixels.data_ptr()
+        a.out = out.data_ptr() if last else scratch.data_ptr()   # not written unless the range ends at depth
+        a.block_begin, a.block_end = int(b0), int(b1)
         a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
         a.win_rows, a.unwin_rows = _ptr(win_rows), _ptr(unwin_rows)
         a.batch, a.img, a.patch, a.embed_dim = B, cfg["img"], cfg["patch"], cfg["embed_dim"]
