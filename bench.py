@@ -54,8 +54,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=32)
+    ap.add_argument("--batch-per-gpu", type=int, default=None, help="default: the config's (c2 32, c3 16, c4 8, c5 32)")
     ap.add_argument("--new-tokens", type=int, default=64)
+    ap.add_argument("--config", default="c5", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs: c2 = ViT-L/14-336 only, B=32; c3 = LLaMA-7B prefill only, B=16, L=608; "
+                         "c4 = full pipeline B=8; c5 (default) = full pipeline, 32 images per GPU (the metric's config)")
+    ap.add_argument("--cpu-full-image", action="store_true",
+                    help="--impl reference only: also run ONE whole image through the full-size oracle (no sampling, "
+                         "about 27 GB of host memory and a few minutes) and report the extrapolation error")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
@@ -261,6 +267,13 @@ class CpuSample:
         self.text = synth_normal("bench_text", (1, 256))
 
     @staticmethod
+    def scale_factors(new_tokens: int) -> dict:
+        """multipliers applied to the timed pieces (run_once): per image = sum(piece x factor)"""
+        return {"clip_layer": 23, "prefill_layer": 32, "lm_head_prefill": 1, "decode_layer": 32 * (new_tokens - 1),
+                "lm_head_step": new_tokens - 1, "sam_window_block": 28, "sam_global_block": 4, "sam_embed_neck": 1,
+                "mask_decoder": 1, "postprocess": 1}
+
+    @staticmethod
     def _t(fn):
         t0 = time.perf_counter()
         r = fn()
@@ -303,11 +316,105 @@ class CpuSample:
 
 
 def config_dict(args, world_size):
-    return {"workload": f"c5 shard: full u-LLaVA-7B pipeline (CLIP ViT-L/14-336 + projector + LLaMA-7B prefill 608 + "
+    if args.config == "c2":
+        return {"workload": f"c2: CLIP ViT-L/14-336 encoder only (23 layers, CLS dropped), batch {args.batch_per_gpu}",
+                "global_batch": args.batch_per_gpu * world_size, "batch_per_gpu": args.batch_per_gpu, "image": IMG,
+                "parallelism": f"dp{world_size}", "l2": "L2 flushed between timed iterations (256 MB write)"}
+    if args.config == "c3":
+        return {"workload": f"c3: LLaMA-7B prefill only, 576 visual + 32 text positions from resident embeddings, batch "
+                            f"{args.batch_per_gpu}, KV cache written, last-position logits",
+                "global_batch": args.batch_per_gpu * world_size, "batch_per_gpu": args.batch_per_gpu, "prompt_len": P_LEN,
+                "parallelism": f"dp{world_size}", "l2": "inputs larger than L2 (13.5 GB of weights stream through every step)"}
+    tag = "c4" if args.config == "c4" else "c5 shard"
+    return {"workload": f"{tag}: full u-LLaVA-7B pipeline (CLIP ViT-L/14-336 + projector + LLaMA-7B prefill 608 + "
                         f"{args.new_tokens} greedy tokens + SAM ViT-H + mask decoder), {args.batch_per_gpu} images per GPU",
             "global_batch": args.batch_per_gpu * world_size, "batch_per_gpu": args.batch_per_gpu, "prompt_len": P_LEN,
             "new_tokens": args.new_tokens, "image": IMG, "sam_image": SAM_IMG, "parallelism": f"dp{world_size}",
             "l2": "inputs larger than L2 (13.5 GB of weights stream through every step)"}
+
+
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is one process that owns the host."""
+    n = os.cpu_count() or 1
+    os.environ.pop("OMP_NUM_THREADS", None)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_full_image(new_tokens: int) -> dict:
+    """ONE image through the whole full-size oracle (23 CLIP layers, 32 LLaMA-7B layers with a KV-cached greedy loop,
+    32 SAM ViT-H blocks, mask decoder), nothing sampled or scaled: the check on CpuSample's extrapolation."""
+    from oracle import ullava_oracle as O
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s, std=0.02: torch.randn(s, generator=g) * std  # noqa: E731
+    sd = {}
+    vp = "llm.vision_encoder.vision_model."
+    sd[vp + "embeddings.patch_embedding.weight"] = rn(1024, 3, 14, 14)
+    sd[vp + "embeddings.class_embedding"] = rn(1024)
+    sd[vp + "embeddings.position_embedding.weight"] = rn(577, 1024)
+    for nm in ("pre_layrnorm",):
+        sd[vp + nm + ".weight"], sd[vp + nm + ".bias"] = torch.ones(1024), torch.zeros(1024)
+    for l in range(23):
+        q = vp + f"encoder.layers.{l}."
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[q + f"self_attn.{nm}.weight"], sd[q + f"self_attn.{nm}.bias"] = rn(1024, 1024), torch.zeros(1024)
+        sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"] = rn(4096, 1024), torch.zeros(4096)
+        sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"] = rn(1024, 4096), torch.zeros(1024)
+        for nm in ("layer_norm1", "layer_norm2"):
+            sd[q + nm + ".weight"], sd[q + nm + ".bias"] = torch.ones(1024), torch.zeros(1024)
+    sd["llm.vision_projector.weight"], sd["llm.vision_projector.bias"] = rn(4096, 1024), torch.zeros(4096)
+    sd["llm.model.embed_tokens.weight"] = rn(VOCAB, 4096)
+    for l in range(32):
+        p = f"llm.model.layers.{l}."
+        for nm, shp in {"self_attn.q_proj": (4096, 4096), "self_attn.k_proj": (4096, 4096), "self_attn.v_proj": (4096, 4096),
+                        "self_attn.o_proj": (4096, 4096), "mlp.gate_proj": (11008, 4096), "mlp.up_proj": (11008, 4096),
+                        "mlp.down_proj": (4096, 11008)}.items():
+            sd[p + nm + ".weight"] = rn(*shp)
+        sd[p + "input_layernorm.weight"] = sd[p + "post_attention_layernorm.weight"] = torch.ones(4096)
+    sd["llm.model.norm.weight"] = torch.ones(4096)
+    sd["llm.lm_head.weight"] = rn(VOCAB, 4096)
+    from tests.util_models import load_golden
+    _, meta = load_golden("sam_decoder")
+    for k, shp in meta["shapes"].items():
+        sd["visual_model." + k] = rn(*shp) if len(shp) > 1 else torch.ones(shp)
+    e = "visual_model.image_encoder."
+    sd[e + "patch_embed.proj.weight"], sd[e + "patch_embed.proj.bias"] = rn(1280, 3, 16, 16), torch.zeros(1280)
+    sd[e + "pos_embed"] = rn(1, 64, 64, 1280)
+    for b in range(32):
+        size = 64 if b in (7, 15, 23, 31) else 14
+        q = e + f"blocks.{b}."
+        for nm, shp in {"attn.qkv.weight": (3840, 1280), "attn.proj.weight": (1280, 1280), "mlp.lin1.weight": (5120, 1280),
+                        "mlp.lin2.weight": (1280, 5120), "attn.rel_pos_h": (2 * size - 1, 80),
+                        "attn.rel_pos_w": (2 * size - 1, 80)}.items():
+            sd[q + nm] = rn(*shp)
+        for nm, n in {"attn.qkv.bias": 3840, "attn.proj.bias": 1280, "mlp.lin1.bias": 5120, "mlp.lin2.bias": 1280,
+                      "norm1.bias": 1280, "norm2.bias": 1280}.items():
+            sd[q + nm] = torch.zeros(n)
+        sd[q + "norm1.weight"] = sd[q + "norm2.weight"] = torch.ones(1280)
+    sd[e + "neck.0.weight"], sd[e + "neck.2.weight"] = rn(256, 1280, 1, 1), rn(256, 256, 3, 3)
+    for i in (1, 3):
+        sd[e + f"neck.{i}.weight"], sd[e + f"neck.{i}.bias"] = torch.ones(256), torch.zeros(256)
+    for nm in ("seg_projector",):
+        sd[nm + ".0.weight"], sd[nm + ".0.bias"] = rn(4096, 4096), torch.zeros(4096)
+        sd[nm + ".2.weight"], sd[nm + ".2.bias"] = rn(256, 4096), torch.zeros(256)
+    cfg = dict(LLM)
+    cfg["rope_theta"] = 10000.0
+    ids = make_prompt(0)[None]
+    px = torch.randn((1, 3, IMG, IMG), generator=g)
+    px_sam = torch.randn((1, 3, SAM_IMG, SAM_IMG), generator=g)
+    vith = dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=[7, 15, 23, 31], window_size=14, patch_size=16)
+    t0 = time.perf_counter()
+    seqs, hid, _ = O.greedy_generate(sd, cfg, ids, px, new_tokens, prefix="llm.")
+    t1 = time.perf_counter()
+    emb = O.sam_image_encoder(sd, "visual_model.", px_sam, vith)
+    t2 = time.perf_counter()
+    h = hid[:, -1]                                     # any one hidden state: the mask head's cost does not depend on it
+    text = O.seg_project(sd, "seg_projector.", h)
+    masks, _ = O.sam_mask_decoder(sd, "visual_model.", emb, text)
+    O.postprocess_masks(masks[:, 0:1], (SAM_IMG, SAM_IMG), (IMG, IMG))
+    t3 = time.perf_counter()
+    return {"per_image_s": t3 - t0, "generate_s": t1 - t0, "sam_encoder_s": t2 - t1, "mask_head_s": t3 - t2}
 
 
 def run_reference(args):
@@ -315,22 +422,30 @@ def run_reference(args):
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    threads = use_all_host_threads()
     cpu = CpuSample()
     for _ in range(min(args.warmup, 1)):
         cpu.run_once(args.new_tokens)
-    t0 = time.perf_counter()
     rs = [cpu.run_once(args.new_tokens) for _ in range(args.steps)]
-    wall = time.perf_counter() - t0
     per_image = statistics.median(r["per_image_s"] for r in rs)
     v = 1.0 / per_image
+    B = args.batch_per_gpu
+    # ms_per_step: what ONE step of the arm's config (B images) costs at this rate -- the sample itself is a fraction of
+    # one image (CpuSample.description) scaled by layer / token counts, hence "extrapolated"
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * B / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, ws),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": CpuSample.description, "host_cpus": os.cpu_count(), "parts_s": rs[-1]["parts"]},
+            "config": config_dict(args, ws), "extrapolated": True,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": CpuSample.description, "host_cpus": os.cpu_count(), "parts_s": rs[-1]["parts"],
+                             "scale_factors": CpuSample.scale_factors(args.new_tokens),
+                             "sample_wall_s": round(sum(sum(r["parts"].values()) for r in rs) / max(len(rs), 1), 3)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.cpu_full_image:
+        full = cpu_full_image(args.new_tokens)
+        line["cpu_baseline"]["full_image"] = dict(full, images_per_s=1.0 / full["per_image_s"],
+                                                  extrapolation_error=per_image / full["per_image_s"] - 1.0)
     print(json.dumps(line), flush=True)
 
 
@@ -434,6 +549,12 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), native.Context.total_launches(local) + model.llm.graph_kernel_launches() - n0, r
 
+    if args.config in ("c2", "c3"):
+        run_stage_config(args, model, ctx, timed, (h_ids, h_img, d_ids, d_img), rank, ws, local, dev)
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
     if args.profile_mode:
         step_resident()
         torch.cuda.synchronize()
@@ -480,15 +601,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peaks_src = "measured (MEASURED_PEAKS.json)"
-    if os.path.exists(pk_path):
-        with open(pk_path) as f:
-            peaks = json.load(f)
-    else:
-        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-        peaks_src = "fallback (B200_PROFILING.md)"
+    peaks, peaks_src = load_peaks()
 
     images = B * ws * args.steps
     value = images / (ms_res / 1e3)
@@ -553,17 +666,105 @@ def run_b200(args):
                                    "frac_of_sustained_peak": fl / sec / 1e12 / peaks["bf16_tflops_sustained"],
                                    "batch": B, "ms": sec * 1e3}
     if not args.no_cpu_baseline and ws == 1:
+        threads = use_all_host_threads()
         cpu = CpuSample()
         r = cpu.run_once(args.new_tokens)
-        line["cpu_baseline"] = {"value": 1.0 / r["per_image_s"], "unit": UNIT, "cores": torch.get_num_threads(),
+        line["cpu_baseline"] = {"value": 1.0 / r["per_image_s"], "unit": UNIT, "cores": threads, "extrapolated": True,
                                 "kind": "port", "sample": CpuSample.description, "host_cpus": os.cpu_count()}
     print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()
 
 
+def load_peaks():
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        with open(pk_path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def run_stage_config(args, model, ctx, timed, tensors, rank, ws, local, dev):
+    """BASELINE.json configs[1] / configs[2]: one stage of the path on its own, against the tensor roofline.
+    c2: ViT-L/14-336 (UllavaCoreForCausalLM.encode_image) on 32 images; c3: LLaMA-7B prefill of 16 x 608 positions
+    (forward(inputs_embeds=..., use_cache=True), last-position logits)."""
+    import native
+    h_ids, h_img, d_ids, d_img = tensors
+    B = args.batch_per_gpu
+    llm = model.llm
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if args.config == "c2":
+        flops = B * FLOP_VIT
+        h_out = torch.empty((B, N_PATCH, 1024), dtype=torch.bfloat16).pin_memory()
+
+        def resident():
+            flush.zero_()                      # ViT weights (0.6 GB) + activations: flush L2 between iterations
+            return llm.encode_image(d_img)
+
+        def e2e():
+            out = llm.encode_image(h_img.to(dev, non_blocking=True))
+            h_out.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
+        h2d, d2h = h_img.numel() * 2, h_out.numel() * 2
+    else:
+        flops = B * FLOP_PREFILL_LAST
+        _, emb = llm.embed_images_videos(d_ids, d_img, None)        # ViT + projector + splice: outside the timed region
+        emb = emb.contiguous()
+        h_emb = emb.cpu().pin_memory()
+        h_out = torch.empty((B, 1, VOCAB), dtype=torch.float32).pin_memory()
+
+        def resident():
+            return llm(inputs_embeds=emb, use_cache=True, logits_to_keep=1, logits_fp32=True, return_dict=True).logits
+
+        def e2e():
+            out = llm(inputs_embeds=h_emb.to(dev, non_blocking=True), use_cache=True, logits_to_keep=1, logits_fp32=True,
+                      return_dict=True).logits
+            h_out.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
+        h2d, d2h = h_emb.numel() * 2, h_out.numel() * 4
+    sampler = ClockSampler(physical_gpu_index(local))
+    if rank == 0 and not os.environ.get("ULLAVA_BENCH_NO_CLOCKS"):
+        sampler.start()
+    ms_res, launches, _ = timed(resident, args.warmup, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(e2e, 2, args.steps)
+    ctx.profile_begin()
+    resident()
+    torch.cuda.synchronize()
+    prof = ctx.profile_end()
+    if rank != 0:
+        return
+    peaks, peaks_src = load_peaks()
+    images = B * ws * args.steps
+    sec = ms_res / 1e3 / args.steps
+    gt = prof["gemm_tensor"]
+    a_t = gt["flops"] / max(gt["ms"], 1e-9) / 1e9
+    line = {"metric": METRIC, "value": images / (ms_res / 1e3), "unit": UNIT, "n_gpus": ws, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded random weights, N(0,1) images, random prompt ids)",
+            "config": config_dict(args, ws), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": images / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "stage": {"tflops": flops / sec / 1e12, "frac_of_burst_peak": flops / sec / 1e12 / peaks["bf16_tflops"],
+                      "frac_of_sustained_peak": flops / sec / 1e12 / peaks["bf16_tflops_sustained"],
+                      "algorithmic_flop_per_step": flops},
+            "roofline": {"kernel": "gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel", "bound": "tensor", "achieved": a_t,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": a_t / peaks["bf16_tflops_sustained"], "traffic": None, "launches": gt["launches"],
+                         "avg_launch_ms": gt["ms"] / max(gt["launches"], 1), "peak_source": peaks_src + ", sustained"},
+            "kernel_classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                   "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1),
+                                   "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)}
+                               for k, v in prof.items() if v["launches"]}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    if args.batch_per_gpu is None:
+        args.batch_per_gpu = {"c2": 32, "c3": 16, "c4": 8, "c5": 32}[args.config]
     if args.impl == "reference":
         run_reference(args)
     else:
