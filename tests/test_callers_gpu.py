@@ -177,11 +177,12 @@ def test_resize_u8_is_pillow_exact(ctx, h, w, oh, ow, bicubic):
         assert np.array_equal(got, O.pil_resize(img, oh, ow, bicubic))
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_seg_toolbox_matches_reference_fixture(ctx, dtype):
     from dataset.tools.mask_toolbox import SegToolBox
     z, meta = load_golden("callers_preprocess")
     tool = SegToolBox(dtype=dtype)
+    assert SegToolBox().dtype == torch.float32        # the reference's processors return fp32
     for i, case in enumerate(meta["cases"]):
         img = z[f"img_{i}"]
         resized = tool.apply_image(img)
@@ -196,7 +197,7 @@ def test_seg_toolbox_matches_reference_fixture(ctx, dtype):
         assert torch.equal(x2, x)
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("h,w,pad", [(480, 640, False), (640, 480, True), (336, 336, False), (500, 333, True),
                                      (97, 53, False)])
 def test_clip_processor_matches_oracle(ctx, dtype, h, w, pad):

@@ -191,6 +191,11 @@ int resize_u8_run(Context* ctx, const uint8_t* src, int h, int w, uint8_t* dst, 
 }
 
 // ---- normalisation kernels -------------------------------------------------------------------------------------
+// output element: 16-bit (the model dtype, one rounding of the fp32 value) or fp32 (what the reference's processors
+// return before their callers do .cuda().to(dtype))
+template <typename T> struct PxOut { static __device__ __forceinline__ T cvt(float v) { return T16<T>::from_f(v); } };
+template <> struct PxOut<float> { static __device__ __forceinline__ float cvt(float v) { return v; } };
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 clip_preprocess_kernel(const uint8_t* __restrict__ src, int w, int top, int left, int size, float m0, float m1,
@@ -202,7 +207,7 @@ clip_preprocess_kernel(const uint8_t* __restrict__ src, int w, int top, int left
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float v = __double2float_rn(__dmul_rn(static_cast<double>(p[c]), rescale));
-    out[(static_cast<int64_t>(c) * size + y) * size + x] = T16<T>::from_f(__fdiv_rn(__fsub_rn(v, mean[c]), sd[c]));
+    out[(static_cast<int64_t>(c) * size + y) * size + x] = PxOut<T>::cvt(__fdiv_rn(__fsub_rn(v, mean[c]), sd[c]));
   }
 }
 
@@ -220,6 +225,9 @@ int clip_preprocess_run(Context* ctx, const uint8_t* src, int h, int w, int top,
   else if (dtype == DT_F16)
     clip_preprocess_kernel<__half><<<grid, 256, 0, s>>>(src, w, top, left, size, mean[0], mean[1], mean[2], stdv[0],
                                                         stdv[1], stdv[2], rescale, static_cast<__half*>(out));
+  else if (dtype == DT_F32)
+    clip_preprocess_kernel<float><<<grid, 256, 0, s>>>(src, w, top, left, size, mean[0], mean[1], mean[2], stdv[0],
+                                                       stdv[1], stdv[2], rescale, static_cast<float*>(out));
   else { set_last_error("clip_preprocess: unsupported dtype"); return ERR_UNSUPPORTED; }
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "clip_preprocess launch");
@@ -237,7 +245,7 @@ sam_preprocess_kernel(const uint8_t* __restrict__ src, int h, int w, int S, floa
   for (int c = 0; c < 3; ++c) {
     float v = 0.f;  // F.pad after the normalisation: the border is exactly zero
     if (inside) v = __fdiv_rn(__fsub_rn(static_cast<float>(src[(static_cast<int64_t>(y) * w + x) * 3 + c]), mean[c]), sd[c]);
-    out[(static_cast<int64_t>(c) * S + y) * S + x] = T16<T>::from_f(v);
+    out[(static_cast<int64_t>(c) * S + y) * S + x] = PxOut<T>::cvt(v);
   }
 }
 
@@ -253,6 +261,9 @@ int sam_preprocess_run(Context* ctx, const uint8_t* src, int h, int w, int S, co
   else if (dtype == DT_F16)
     sam_preprocess_kernel<__half><<<grid, 256, 0, s>>>(src, h, w, S, mean[0], mean[1], mean[2], stdv[0], stdv[1],
                                                        stdv[2], static_cast<__half*>(out));
+  else if (dtype == DT_F32)
+    sam_preprocess_kernel<float><<<grid, 256, 0, s>>>(src, h, w, S, mean[0], mean[1], mean[2], stdv[0], stdv[1],
+                                                      stdv[2], static_cast<float*>(out));
   else { set_last_error("sam_preprocess: unsupported dtype"); return ERR_UNSUPPORTED; }
   ctx->launches++;
   return check_cuda(cudaGetLastError(), "sam_preprocess launch");

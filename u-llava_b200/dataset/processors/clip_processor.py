@@ -27,9 +27,11 @@ def _register(cls):
 @_register
 class CLIPProcessor:
     def __init__(self, checkpoint_path=None, aspect_ratio=None, size: int = 336, image_mean=OPENAI_CLIP_MEAN,
-                 image_std=OPENAI_CLIP_STD, rescale_factor: float = 1 / 255, dtype=torch.bfloat16, device=None):
+                 image_std=OPENAI_CLIP_STD, rescale_factor: float = 1 / 255, dtype=torch.float32, device=None):
         """checkpoint_path: directory with a preprocessor_config.json (size / crop_size / mean / std are read from it
-        when present, like CLIPImageProcessor.from_pretrained); aspect_ratio: 'pad', 'keep' or None."""
+        when present, like CLIPImageProcessor.from_pretrained); aspect_ratio: 'pad', 'keep' or None.
+        dtype: fp32 by default, like the reference (whose callers then do `.cuda().to(model dtype)`,
+        inference_ullava.py:78); pass the model dtype to get that single rounding done by the kernel instead."""
         self.aspect_ratio = aspect_ratio
         self.size, self.mean, self.std, self.rescale = int(size), tuple(image_mean), tuple(image_std), rescale_factor
         if checkpoint_path is not None:

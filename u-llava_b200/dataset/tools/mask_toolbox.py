@@ -11,7 +11,9 @@ import native
 
 
 class SegToolBox:
-    def __init__(self, dtype=torch.bfloat16, device=None):
+    def __init__(self, dtype=torch.float32, device=None):
+        """dtype: fp32 by default, like the reference's preprocess (callers cast with `.to(model dtype)`,
+        inference_ullava.py:85); pass the model dtype to let the kernel do that single rounding."""
         self.sam_mean = (123.675, 116.28, 103.53)
         self.sam_std = (58.395, 57.12, 57.375)
         self.sam_size = 1024

@@ -208,6 +208,11 @@ def dtype_code(dt: torch.dtype) -> int:
     raise TypeError(f"the sm_100a path stores activations/weights in bf16 or fp16, got {dt}")
 
 
+def px_dtype_code(dt: torch.dtype) -> int:
+    """pixel tensors of the preprocessing kernels: fp32 (the reference processors' output) or the model dtype"""
+    return F32 if dt == torch.float32 else dtype_code(dt)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -659,7 +664,7 @@ class Context:
         out = torch.empty((3, size, size), dtype=dtype, device=img.device)
         m, s = (_f32 * 3)(*[float(v) for v in mean]), (_f32 * 3)(*[float(v) for v in std])
         self._chk(self.lib.ullava_clip_preprocess(self.handle, img.data_ptr(), img.shape[0], img.shape[1], top, left,
-                                                  size, m, s, float(rescale), out.data_ptr(), dtype_code(dtype),
+                                                  size, m, s, float(rescale), out.data_ptr(), px_dtype_code(dtype),
                                                   _stream()))
         return out
 
@@ -668,7 +673,7 @@ class Context:
         out = torch.empty((3, sam_size, sam_size), dtype=dtype, device=img.device)
         m, s = (_f32 * 3)(*[float(v) for v in mean]), (_f32 * 3)(*[float(v) for v in std])
         self._chk(self.lib.ullava_sam_preprocess(self.handle, img.data_ptr(), img.shape[0], img.shape[1], sam_size, m,
-                                                 s, out.data_ptr(), dtype_code(dtype), _stream()))
+                                                 s, out.data_ptr(), px_dtype_code(dtype), _stream()))
         return out
 
     def fill_llama_args(self, a: "LlamaArgs", weight_table, n_weights, hidden, k_cache, v_cache, scratch, batch, seq,
