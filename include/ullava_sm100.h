@@ -335,6 +335,12 @@ typedef struct ullava_llama_args {
   float eps;
   const float* rope_cos; const float* rope_sin; /* fp32 [max_seq, head_dim/2] */
   int32_t dtype;
+  /* decode step only (ullava_llama_decode_step, batch <= 32), optional: device buffer of ullava_llama_chain_bytes(layers)
+   * bytes holding the decode-layer chain program that ullava_llama_chain_prepare built for EXACTLY these arguments
+   * (pointers, shapes) and this context.  With it the step runs 2 kernels per layer (single-query attention + one
+   * persistent chain kernel: o_proj, RMSNorm, gate/up, down, RMSNorm, next q/k/v, csrc/gemm_chain_sm100.cu) instead of 7;
+   * results are bit-identical. */
+  void* chain_program; size_t chain_bytes;
   /* decode only (seq == 1), optional: device int32 [B]; sample b's token sits at KV / RoPE position
    * pos + pos_offset[b] (<= 0).  Lets one batch hold right-padded prompts of different lengths: the prefill runs on
    * the padded [B, P] block (causal attention keeps valid positions exact), then every sample continues right after
@@ -368,6 +374,10 @@ typedef struct ullava_decode_args {
   int32_t top_k;                /* 0 = off; HF's GenerationConfig default (50) is applied by the Python caller */
 } ullava_decode_args;
 ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, void* stream);
+/* Builds the decode-layer chain program into args->llama.chain_program (synchronous: host-side TMA descriptor encoding +
+ * one cudaMemcpy; call it once per decode session, outside any stream capture). */
+ULLAVA_API size_t ullava_llama_chain_bytes(int32_t layers);
+ULLAVA_API int ullava_llama_chain_prepare(ullava_ctx* ctx, const ullava_decode_args* args);
 /* The bookkeeping tail of a step on its own (used once after the prefill, with *pos_dev = P - 1):
  * argmax + eos/pad handling, cur_ids / seqs[b][pos+1] / hid_buf[b][pos] updates, ++*pos_dev. */
 ULLAVA_API int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, int64_t* cur_ids,

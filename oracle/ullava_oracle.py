@@ -72,7 +72,8 @@ def clip_vit_hidden(sd: SD, prefix: str, pixel_values: torch.Tensor, vcfg: dict,
         vv = F.linear(h, sd[q + "self_attn.v_proj.weight"], sd[q + "self_attn.v_proj.bias"])
         S = h.shape[1]
         qq, kk, vv = (t.view(B, S, heads, hd).transpose(1, 2) for t in (qq, kk, vv))
-        w = torch.softmax(qq @ kk.transpose(-1, -2) * hd ** -0.5, dim=-1)  # eager_attention_forward :261-279
+        # eager_attention_forward :261-279 (softmax in fp32, cast back to the query dtype)
+        w = torch.softmax((qq @ kk.transpose(-1, -2) * hd ** -0.5).float(), dim=-1).to(qq.dtype)
         a = (w @ vv).transpose(1, 2).reshape(B, S, H)
         x = r + F.linear(a, sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"])
         r = x
@@ -147,9 +148,12 @@ def embed_images(sd: SD, input_ids: torch.Tensor, images: Optional[torch.Tensor]
 # LLaMA decoder
 # --------------------------------------------------------------------------------------------
 def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
-    """LlamaRMSNorm (hf:models/llama/modeling_llama.py:52-69)."""
-    v = x.pow(2).mean(-1, keepdim=True)
-    return w * (x * torch.rsqrt(v + eps))
+    """LlamaRMSNorm (hf:models/llama/modeling_llama.py:52-69): statistics in fp32, one cast back to the input dtype
+    before the weight multiply (no-ops for the fp32 oracle; they matter when the restatement is evaluated in 16 bits
+    as the yardstick of what the reference's own bf16 / fp16 path does)."""
+    xf = x.float()
+    v = xf.pow(2).mean(-1, keepdim=True)
+    return w * (xf * torch.rsqrt(v + eps)).to(x.dtype)
 
 
 def rope_tables(positions: torch.Tensor, hd: int, theta: float) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -182,6 +186,7 @@ def llama_layers(sd: SD, x: torch.Tensor, cfg: dict, prefix: str = "", past: Opt
     pos0 = 0 if past is None else past[0][0].shape[2]
     dev = x.device  # the oracle also runs in fp32 on the GPU for the full-size checks (tests/test_fullsize_gpu.py)
     cos, sin = rope_tables(torch.arange(pos0, pos0 + S, device=dev), hd, cfg.get("rope_theta", 10000.0))
+    cos, sin = cos.to(x.dtype), sin.to(x.dtype)   # LlamaRotaryEmbedding returns cos / sin in the activation dtype
     qi = torch.arange(S, device=dev)[:, None] + pos0
     kj = torch.arange(pos0 + S, device=dev)[None, :]
     mask = torch.zeros(S, pos0 + S, device=dev).masked_fill(kj > qi, float("-inf"))
@@ -199,7 +204,8 @@ def llama_layers(sd: SD, x: torch.Tensor, cfg: dict, prefix: str = "", past: Opt
             k = torch.cat([past[l][0], k], dim=2)
             v = torch.cat([past[l][1], v], dim=2)
         new_past.append((k, v))
-        w = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5 + mask, dim=-1)
+        # eager_attention_forward (:199-222): softmax in fp32, cast back to the query dtype
+        w = torch.softmax((q @ k.transpose(-1, -2) * hd ** -0.5 + mask.to(q.dtype)).float(), dim=-1).to(q.dtype)
         a = (w @ v).transpose(1, 2).reshape(B, S, H)
         x = r + F.linear(a, sd[p + "self_attn.o_proj.weight"])
         r = x

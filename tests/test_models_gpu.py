@@ -513,3 +513,45 @@ def test_evaluate_overlapped_equals_back_to_back(ctx, dtype, use_graph):
             assert x.shape == y.shape and (x - y).abs().max().item() <= 2e-2 * max(1.0, y.abs().max().item())
         for x, y in zip(b0, b1):
             assert (x.float() - y.float()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("batch", [32, 5])
+def test_decode_chain_kernel_bit_identical_to_kernel_per_gemm(ctx, dtype, batch):
+    """csrc/gemm_chain_sm100.cu: the decode step with one persistent chain kernel per layer (o_proj, RMSNorm, gate/up,
+    down, RMSNorm, next q/k/v, and final norm + lm_head at the end) against the same step run as one kernel per GEMM /
+    norm, at LLaMA-7B width (2 layers, V = 32 011 so that the last weight tile is partial): same stream-K partition, same
+    summation order, same norm reduction tree -> logits, hidden states and token ids bit-identical, eagerly and through
+    the replayed graph."""
+    from transformers import LlamaConfig, LlamaModel
+    from models.engine import LlamaStack
+    torch.manual_seed(0)
+    lc = LlamaConfig(vocab_size=32011, hidden_size=4096, intermediate_size=11008, num_hidden_layers=2,
+                     num_attention_heads=32, num_key_value_heads=32, rms_norm_eps=1e-6)
+    with torch.device("cuda"):
+        mod = LlamaModel(lc).eval().to(dtype)
+        head = torch.nn.Linear(4096, 32011, bias=False).to(dtype)
+    stack = LlamaStack(mod, head)
+    stack.ensure()
+    P, new = 40, 6
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ids = torch.randint(3, 32000, (batch, P), device="cuda", generator=g)
+
+    def run(use_chain, use_graph):
+        stack._session = None
+        sess = stack.decode_session(ctx, batch, P + new, stack.embed_w, stack.head_w, True)
+        sess.use_chain = use_chain
+        sess.begin(ids, None, 0)
+        x = ctx.embed_gather(ids, stack.embed_w)
+        final, _ = stack.run(ctx, x, sess.cache, batch, P)
+        sess.first_token(final.view(batch, P, 4096)[:, -1].contiguous(), P)
+        sess.steps(new - 1, use_graph=use_graph)
+        torch.cuda.synchronize()
+        return sess.seqs.clone(), sess.logits.clone(), sess.final.clone(), sess.hid_buf[:, P - 1:].clone()
+
+    ref = run(False, False)
+    for use_graph in (False, True):
+        got = run(True, use_graph)
+        for a, b, name in zip(got, ref, ("ids", "logits", "final hidden", "hidden states")):
+            assert torch.equal(a, b), f"{name} differ (graph={use_graph}): max abs {(a.float() - b.float()).abs().max().item()}"
+    assert torch.isfinite(ref[1]).all() and int(ref[0][:, P:].min()) >= 0

@@ -4,12 +4,12 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
-SRCS="runtime.cu gemm_sm100.cu gemm_stream_sm100.cu norm.cu attention.cu fmha_sm100.cu fmha_window_sm100.cu elementwise.cu sampling.cu eval_ops.cu preprocess.cu sam_decoder.cu sam_encoder.cu models.cu partition.cu capi.cu"
+SRCS="runtime.cu gemm_sm100.cu gemm_stream_sm100.cu norm.cu attention.cu fmha_sm100.cu fmha_window_sm100.cu elementwise.cu sampling.cu eval_ops.cu preprocess.cu sam_decoder.cu sam_encoder.cu models.cu partition.cu gemm_chain_sm100.cu capi.cu"
 mkdir -p build
 pids=()
 for f in $SRCS; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ullava_internal.h -nt "$o" ] || [ ../../include/ullava_sm100.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ gemm_stream.cuh -nt "$o" ] || [ ullava_internal.h -nt "$o" ] || [ ../../include/ullava_sm100.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
     pids+=($!)
   fi

@@ -189,6 +189,14 @@ int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, vo
   return llama_decode_step_run(ctx, *args, static_cast<cudaStream_t>(stream));
 }
 
+size_t ullava_llama_chain_bytes(int32_t layers) { return llama_chain_bytes(layers); }
+
+int ullava_llama_chain_prepare(ullava_ctx* ctx, const ullava_decode_args* args) {
+  CTX_CHECK("ullava_llama_chain_prepare");
+  if (!args) { set_last_error("ullava_llama_chain_prepare: args is NULL"); return ERR_BAD_ARG; }
+  return llama_chain_prepare_run(ctx, *args);
+}
+
 int ullava_greedy_step(ullava_ctx* ctx, const float* logits, int64_t ld, int32_t rows, int32_t cols, int64_t* cur_ids,
                        int64_t* seqs, int64_t seqs_ld, const void* final_h, void* hid_buf, int64_t hid_bs, int32_t hdim,
                        uint8_t* finished, int32_t eos_id, int32_t pad_id, int32_t* pos_dev, void* stream) {

@@ -3,6 +3,7 @@
 // Python round trip per op).  Every kernel they enqueue is one of the hand-written sm_100a kernels
 // of this library; nothing here calls cuBLAS/cuDNN/torch.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "ullava_internal.h"
@@ -125,6 +126,99 @@ size_t llama_scratch(int rows, int hidden, int ffn) {
   return t + 4096;
 }
 
+// ---- decode-layer chains (gemm_chain_sm100.cu) -----------------------------------------------------------------
+// Program of one decode step: chain 0 = [RMSNorm(ln1_0) -> qkv_0]; after the attention of layer l, chain l + 1 =
+// [o_l (+residual) | RMSNorm(ln2_l) -> gate/up_l (SiLU*mul) | down_l (+residual) | RMSNorm(ln1_{l+1}) -> qkv_{l+1}], the
+// last one ending in [final RMSNorm -> lm_head (fp32 logits)] instead.  Device layout of the program buffer:
+// [2 ints of grid-barrier state per step, padded to 128 B][ChainStep x (1 + 4 * layers)].
+static inline int chain_total_steps(int layers) { return 1 + 4 * layers; }
+static inline size_t chain_sync_bytes(int layers) { return align_up(static_cast<size_t>(2) * chain_total_steps(layers) * sizeof(int), 128); }
+size_t llama_chain_bytes(int layers) { return chain_sync_bytes(layers) + chain_total_steps(layers) * chain_step_bytes() + 256; }
+
+static inline uint8_t* chain_base(const ullava_llama_args& a) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.chain_program) + 127) & ~uintptr_t(127));
+}
+
+int llama_chain_prepare_run(Context* ctx, const ullava_decode_args& d) {
+  const ullava_llama_args& a = d.llama;
+  ULLAVA_REQUIRE(a.seq == 1 && a.final_out && a.chain_program && d.lm_head && d.logits, "chain_prepare: decode-step arguments expected");
+  ULLAVA_REQUIRE(a.batch >= 1 && a.batch <= 32, "chain_prepare: batch %d not in 1..32 (larger decode batches take the GEMM-per-kernel path)", a.batch);
+  ULLAVA_REQUIRE(a.chain_bytes >= llama_chain_bytes(a.layers), "chain_prepare: program buffer too small (%zu < %zu)",
+                 a.chain_bytes, llama_chain_bytes(a.layers));
+  ULLAVA_REQUIRE(a.n_weights == 6 * a.layers + 1 && a.layers >= 1, "chain_prepare: expected %d weights", 6 * a.layers + 1);
+  const int rows = a.batch, H = a.hidden_size, F = a.ffn, V = d.vocab;
+  const int bn = rows <= 16 ? 16 : 32;
+  Arena ar(a.scratch, a.scratch_bytes);
+  void* xn = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* qkv = ar.take(static_cast<size_t>(rows) * 3 * H * 2);
+  void* att = ar.take(static_cast<size_t>(rows) * H * 2);
+  void* act = ar.take(static_cast<size_t>(rows) * F * 2);
+  if (!ar.ok) { set_last_error("chain_prepare: scratch too small (%zu bytes)", a.scratch_bytes); return ERR_WORKSPACE; }
+  const int total = chain_total_steps(a.layers);
+  const size_t sb = chain_step_bytes();
+  std::vector<uint8_t> host(static_cast<size_t>(total) * sb + 128);
+  uint8_t* hs = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(host.data()) + 127) & ~uintptr_t(127));
+  int k = 0;
+  auto step = [&](const void* W, int64_t ldb, const void* X, int64_t lda, int N, int K, void* D, int64_t ldd,
+                  const void* resid, int ek, int out_f32, const void* nsrc, const void* nw, void* ndst) {
+    return chain_encode_step(hs + static_cast<size_t>(k++) * sb, bn, W, ldb, X, lda, rows, N, K, D, ldd, resid, H, ek,
+                             out_f32, nsrc, nw, ndst, H, a.eps);
+  };
+  const void* const* W = a.weights;
+  RUN(step(W[1], H, xn, H, 3 * H, H, qkv, 3 * H, nullptr, 0, 0, a.hidden, W[0], xn));
+  for (int l = 0; l < a.layers; ++l) {
+    const void* const* L = W + 6 * l;
+    RUN(step(L[2], H, att, H, H, H, a.hidden, H, a.hidden, 0, 0, nullptr, nullptr, nullptr));
+    RUN(step(L[4], H, xn, H, 2 * F, H, act, F, nullptr, 1, 0, a.hidden, L[3], xn));
+    RUN(step(L[5], F, act, F, H, F, a.hidden, H, a.hidden, 0, 0, nullptr, nullptr, nullptr));
+    if (l + 1 < a.layers) {
+      RUN(step(W[6 * (l + 1) + 1], H, xn, H, 3 * H, H, qkv, 3 * H, nullptr, 0, 0, a.hidden, W[6 * (l + 1)], xn));
+    } else {
+      RUN(step(d.lm_head, H, a.final_out, H, V, H, d.logits, V, nullptr, 0, 1, a.hidden, W[6 * a.layers], a.final_out));
+    }
+  }
+  uint8_t* base = chain_base(a);
+  ULLAVA_CHECK_CUDA(cudaMemcpy(base + chain_sync_bytes(a.layers), hs, static_cast<size_t>(total) * sb, cudaMemcpyHostToDevice));
+  ULLAVA_CHECK_CUDA(cudaMemset(base, 0, chain_sync_bytes(a.layers)));
+  return OK;
+}
+
+// One decode step through the chains (a.chain_program prepared for exactly these arguments and this context).
+static int llama_decode_chained(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev) {
+  const int H = a.hidden_size, hd = a.head_dim;
+  Arena ar(a.scratch, a.scratch_bytes);
+  ar.take(static_cast<size_t>(a.batch) * H * 2);                      // xn
+  void* qkv = ar.take(static_cast<size_t>(a.batch) * 3 * H * 2);
+  void* att = ar.take(static_cast<size_t>(a.batch) * H * 2);
+  const int dt = a.dtype;
+  const int64_t cache_hs = static_cast<int64_t>(a.max_seq) * hd;
+  const int64_t cache_bs = cache_hs * a.heads;
+  const int64_t layer_stride = cache_bs * a.batch;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  uint16_t* kc0 = static_cast<uint16_t*>(a.k_cache);
+  uint16_t* vc0 = static_cast<uint16_t*>(a.v_cache);
+  uint8_t* base = chain_base(a);
+  int* sync = reinterpret_cast<int*>(base);
+  const uint8_t* steps = base + chain_sync_bytes(a.layers);
+  const size_t sb = chain_step_bytes();
+  // grid-barrier state of every chain of this step: one memset node in front of the ~2 * layers kernels
+  ULLAVA_CHECK_CUDA(cudaMemsetAsync(sync, 0, chain_sync_bytes(a.layers), s));
+  const double w_bytes = 2.0 * (4.0 * H * H + 3.0 * H * a.ffn);
+  {
+    ProfScope _ps(ctx, s, ULLAVA_PROF_GEMM_STREAM, 2.0 * a.batch * 3.0 * H * H, 2.0 * 3.0 * H * H);
+    RUN(gemm_chain_run(ctx, steps, 1, a.batch, dt, sync, s));
+  }
+  for (int l = 0; l < a.layers; ++l) {
+    RUN(attention_decode_run(ctx, qkv, 3 * H, kc0 + l * layer_stride, vc0 + l * layer_stride, cache_bs, cache_hs, att, H,
+                             a.batch, a.heads, hd, a.pos0 + 1, scale, dt, s, pos_dev, a.max_seq, a.rope_cos, a.rope_sin,
+                             a.pos_offset));
+    const int first = 1 + 4 * l;
+    ProfScope _ps(ctx, s, ULLAVA_PROF_GEMM_STREAM, a.batch * w_bytes, w_bytes);
+    RUN(gemm_chain_run(ctx, steps + static_cast<size_t>(first) * sb, 4, a.batch, dt, sync + 2 * first, s));
+  }
+  return OK;
+}
+
 int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev,
                       const void* tail_w, int tail_n) {
   ULLAVA_REQUIRE(pos_dev == nullptr || a.seq == 1, "llama_forward: a device-side position needs seq == 1");
@@ -139,6 +233,11 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
   ULLAVA_REQUIRE(a.pos_offset == nullptr || a.seq == 1, "llama_forward: pos_offset applies to the decode step (seq == 1)");
   const int rows = a.batch * a.seq, H = a.hidden_size, F = a.ffn, hd = a.head_dim;
   if (rows == 0) return OK;
+  if (a.chain_program != nullptr) {
+    ULLAVA_REQUIRE(a.seq == 1 && a.final_out && !a.all_hidden && a.batch <= 32 && tail_w != nullptr,
+                   "llama_forward: a chain program serves the decode step (ullava_llama_decode_step) only");
+    return llama_decode_chained(ctx, a, s, pos_dev);
+  }
   Arena ar(a.scratch, a.scratch_bytes);
   void* xn = ar.take(static_cast<size_t>(rows) * H * 2);
   void* qkv = ar.take(static_cast<size_t>(rows) * 3 * H * 2);
@@ -211,10 +310,12 @@ int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_
   ULLAVA_REQUIRE(a.pos_dev && a.embed_table && a.lm_head && a.cur_ids && a.logits, "decode_step: null pointer");
   RUN(embed_gather_run(ctx, a.cur_ids, a.embed_table, L.hidden, L.batch, L.hidden_size, a.vocab, L.dtype, s));
   RUN(llama_forward_run(ctx, L, s, a.pos_dev, a.lm_head, a.vocab));
-  GemmArgs g{};
-  g.A = L.final_out; g.lda = L.hidden_size; g.B = a.lm_head; g.ldb = L.hidden_size; g.D = a.logits; g.ldd = a.vocab;
-  g.M = L.batch; g.N = a.vocab; g.K = L.hidden_size; g.dtype = L.dtype; g.out_f32 = 1; g.epilogue = EPI_NONE;
-  RUN(gemm_run(ctx, g, s));
+  if (L.chain_program == nullptr) {   // (the last chain of the program ends with final norm -> lm_head)
+    GemmArgs g{};
+    g.A = L.final_out; g.lda = L.hidden_size; g.B = a.lm_head; g.ldb = L.hidden_size; g.D = a.logits; g.ldd = a.vocab;
+    g.M = L.batch; g.N = a.vocab; g.K = L.hidden_size; g.dtype = L.dtype; g.out_f32 = 1; g.epilogue = EPI_NONE;
+    RUN(gemm_run(ctx, g, s));
+  }
   if (a.uniforms) {
     RUN(sample_step_run(ctx, a.logits, a.vocab, L.batch, a.vocab, a.temperature, a.top_p, a.top_k, a.uniforms, a.uniforms_ld,
                         a.cur_ids, a.seqs, a.seqs_ld, L.final_out, a.hid_buf, a.hid_bs, L.hidden_size, a.finished,

@@ -72,6 +72,13 @@ static constexpr size_t kStreamCounterBytes = 64 * 1024;
 int gemm_stream_run(Context* ctx, const GemmArgs& a, cudaStream_t stream);
 size_t gemm_stream_workspace_bytes(int sm_count);
 
+// gemm_chain_sm100.cu -- the GEMMs + RMSNorms of a decode layer as one persistent kernel (program in device memory)
+size_t chain_step_bytes();
+int chain_encode_step(void* host_step, int bn, const void* W, int64_t ldb, const void* X, int64_t lda, int M, int N, int K,
+                      void* D, int64_t ldd, const void* residual, int64_t ldr, int ek, int out_f32, const void* norm_src,
+                      const void* norm_w, void* norm_dst, int norm_cols, float norm_eps);
+int gemm_chain_run(Context* ctx, const void* steps_dev, int n_steps, int M, int dtype, int* sync_dev, cudaStream_t stream);
+
 // norm.cu
 int layernorm_run(Context* ctx, const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
                   int rows, int cols, float eps, int act, int dtype, cudaStream_t stream,
@@ -167,5 +174,7 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
                       const void* tail_w = nullptr, int tail_n = 0);
 int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_t s);
 size_t llama_scratch(int rows, int hidden, int ffn);
+size_t llama_chain_bytes(int layers);
+int llama_chain_prepare_run(Context* ctx, const ullava_decode_args& a);
 
 }  // namespace ullava

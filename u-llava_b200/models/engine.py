@@ -10,6 +10,7 @@ Everything here is host logic + pointer plumbing; all arithmetic happens in the 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -315,6 +316,10 @@ class DecodeSession:
         self.hid_buf = torch.empty((batch, max_seq - 1, H), dtype=dt, device=dev) if keep_hidden else None
         self.scratch = torch.empty(ctx.llama_scratch_bytes(batch, H, stack.cfg["ffn"]), dtype=torch.uint8, device=dev)
         self.embed_table, self.lm_head = embed_table, lm_head
+        # decode-layer chains (csrc/gemm_chain_sm100.cu): per step context, the argument block with its own chain
+        # program (the program holds TMA descriptors of this session's buffers and is partitioned over the context's SMs)
+        self.use_chain = batch <= 32 and os.environ.get("ULLAVA_DECODE_CHAIN", "1") != "0"
+        self.chain_args = {}      # id(step context) -> (DecodeArgs, program buffer)
         self.graphs = {}          # id(step context) -> (CUDAGraph, kernel nodes): persistent grids are sized per context
         self.graph_nodes = 0
         self.eos_id, self.pad_id = -1, 0
@@ -359,6 +364,7 @@ class DecodeSession:
             self.eos_id, self.pad_id, self.sampling = eos, int(pad_id), sampling
             self._build_args()
             self.graphs = {}   # eos / pad ids and the sampling parameters are baked into the captured kernel arguments
+            self.chain_args = {}
         P = input_ids.shape[1]
         self.cache.length = 0
         self.finished.zero_()
@@ -385,11 +391,12 @@ class DecodeSession:
         if n <= 0:
             return 0
         ctx = ctx or self.ctx
+        args = self._step_args(ctx)
         replayed = 0
         done = 0
         entry = self.graphs.get(id(ctx))
         if use_graph and entry is None:
-            ctx.llama_decode_step(self.args)  # eager warm-up step (also a real step)
+            ctx.llama_decode_step(args)  # eager warm-up step (also a real step)
             done = 1
             if n > 1:
                 c0 = ctx.launch_count()
@@ -399,7 +406,7 @@ class DecodeSession:
                 # kernel nodes stay confined to the lane's SMs; the legacy default stream cannot capture at all
                 on_lane = cur != torch.cuda.default_stream(cur.device)
                 with torch.cuda.graph(g, **(dict(stream=cur) if on_lane else {})):
-                    ctx.llama_decode_step(self.args)
+                    ctx.llama_decode_step(args)
                 nodes = ctx.launch_count() - c0
                 replayed -= nodes  # capture bumped the native counter without launching anything
                 entry = self.graphs[id(ctx)] = (g, nodes)
@@ -409,6 +416,22 @@ class DecodeSession:
                 entry[0].replay()
                 replayed += entry[1]
             else:
-                ctx.llama_decode_step(self.args)
+                ctx.llama_decode_step(args)
         self.cache.length += n
         return replayed
+
+    def _step_args(self, ctx):
+        """The argument block of ullava_llama_decode_step for steps launched through `ctx`: with use_chain a copy of
+        self.args that carries the chain program built for this context (its SM count fixes the stream-K partition)."""
+        if not self.use_chain:
+            return self.args
+        entry = self.chain_args.get(id(ctx))
+        if entry is None:
+            a = native.DecodeArgs.from_buffer_copy(self.args)
+            nbytes = ctx.llama_chain_bytes(self.stack.cfg["layers"])
+            prog = torch.empty(nbytes, dtype=torch.uint8, device=self.stack.device)
+            a.llama.chain_program, a.llama.chain_bytes = prog.data_ptr(), nbytes
+            torch.cuda.synchronize(self.stack.device)      # the program is written with a synchronous copy
+            ctx.llama_chain_prepare(a)
+            entry = self.chain_args[id(ctx)] = (a, prog)
+        return entry[0]

@@ -72,7 +72,8 @@ class LlamaArgs(C.Structure):
                 ("all_hidden", _vp), ("k_cache", _vp), ("v_cache", _vp), ("scratch", _vp), ("scratch_bytes", _sz),
                 ("batch", _i32), ("seq", _i32), ("pos0", _i32), ("max_seq", _i32),
                 ("layers", _i32), ("hidden_size", _i32), ("heads", _i32), ("head_dim", _i32), ("ffn", _i32),
-                ("eps", _f32), ("rope_cos", _vp), ("rope_sin", _vp), ("dtype", _i32), ("pos_offset", _vp)]
+                ("eps", _f32), ("rope_cos", _vp), ("rope_sin", _vp), ("dtype", _i32),
+                ("chain_program", _vp), ("chain_bytes", _sz), ("pos_offset", _vp)]
 
 
 class DecodeArgs(C.Structure):
@@ -130,6 +131,8 @@ _SIGNATURES = {
     "ullava_llama_forward": (_i32, [_vp, C.POINTER(LlamaArgs), _vp]),
     "ullava_llama_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
+    "ullava_llama_chain_bytes": (_sz, [_i32]),
+    "ullava_llama_chain_prepare": (_i32, [_vp, C.POINTER(DecodeArgs)]),
     "ullava_greedy_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
                                   _vp, _vp]),
     "ullava_sample_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _f32, _f32, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64,
@@ -556,6 +559,13 @@ class Context:
         a.global_mask, a.eps, a.dtype = cfg["global_mask"], cfg["eps"], dtype_code(pixels.dtype)
         self._chk(self.lib.ullava_sam_encoder_forward(self.handle, C.byref(a), _stream()))
         return out, scratch
+
+    def llama_chain_bytes(self, layers: int) -> int:
+        return int(self.lib.ullava_llama_chain_bytes(int(layers)))
+
+    def llama_chain_prepare(self, args: "DecodeArgs"):
+        """Builds the decode-layer chain program into args.llama.chain_program (synchronous; not under capture)."""
+        self._chk(self.lib.ullava_llama_chain_prepare(self.handle, C.byref(args)))
 
     def llama_decode_step(self, args: "DecodeArgs"):
         """One greedy decode step with the position in device memory (CUDA-graph replayable)."""
