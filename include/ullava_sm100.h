@@ -335,7 +335,7 @@ typedef struct ullava_llama_args {
   float eps;
   const float* rope_cos; const float* rope_sin; /* fp32 [max_seq, head_dim/2] */
   int32_t dtype;
-  /* decode step only (ullava_llama_decode_step, batch <= 32), optional: device buffer of ullava_llama_chain_bytes(layers)
+  /* decode step only (ullava_llama_decode_step, batch <= 32), optional: device buffer of ullava_llama_chain_bytes(...)
    * bytes holding the decode-layer chain program that ullava_llama_chain_prepare built for EXACTLY these arguments
    * (pointers, shapes) and this context.  With it the step runs 2 kernels per layer (single-query attention + one
    * persistent chain kernel: o_proj, RMSNorm, gate/up, down, RMSNorm, next q/k/v, csrc/gemm_chain_sm100.cu) instead of 7;
@@ -376,7 +376,10 @@ typedef struct ullava_decode_args {
 ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, void* stream);
 /* Builds the decode-layer chain program into args->llama.chain_program (synchronous: host-side TMA descriptor encoding +
  * one cudaMemcpy; call it once per decode session, outside any stream capture). */
-ULLAVA_API size_t ullava_llama_chain_bytes(int32_t layers);
+/* Debug aid (tools/bench_chain.py): buf != NULL makes every chain kernel launched through ctx write globaltimer
+ * stamps [grid][steps][8] (W issued, X ready, first MMA, last MMA, step done, W first, norm begin, norm done) to buf. */
+ULLAVA_API int ullava_debug_chain_trace(ullava_ctx* ctx, void* buf);
+ULLAVA_API size_t ullava_llama_chain_bytes(int32_t layers, int32_t hidden, int32_t ffn, int32_t vocab);
 ULLAVA_API int ullava_llama_chain_prepare(ullava_ctx* ctx, const ullava_decode_args* args);
 /* The bookkeeping tail of a step on its own (used once after the prefill, with *pos_dev = P - 1):
  * argmax + eos/pad handling, cur_ids / seqs[b][pos+1] / hid_buf[b][pos] updates, ++*pos_dev. */

@@ -189,7 +189,15 @@ int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, vo
   return llama_decode_step_run(ctx, *args, static_cast<cudaStream_t>(stream));
 }
 
-size_t ullava_llama_chain_bytes(int32_t layers) { return llama_chain_bytes(layers); }
+int ullava_debug_chain_trace(ullava_ctx* ctx, void* buf) {
+  CTX_CHECK("ullava_debug_chain_trace");
+  ctx->chain_trace = buf;
+  return OK;
+}
+
+size_t ullava_llama_chain_bytes(int32_t layers, int32_t hidden, int32_t ffn, int32_t vocab) {
+  return llama_chain_bytes(layers, hidden, ffn, vocab);
+}
 
 int ullava_llama_chain_prepare(ullava_ctx* ctx, const ullava_decode_args* args) {
   CTX_CHECK("ullava_llama_chain_prepare");

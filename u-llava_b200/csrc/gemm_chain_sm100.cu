@@ -36,6 +36,7 @@ struct alignas(128) ChainStep {
   const void* residual;
   int64_t ldr;
   int N, K, num_t, kb_total, units, ek, out_f32, has_norm;
+  int* counters;     // [num_t] arrival counters of this step's tiles, zeroed by the host side before every launch
   // RMSNorm in front of the step (has_norm): norm_dst[r] = rmsnorm(norm_src[r]) * norm_w, then read through tmX
   const void* norm_src;
   const void* norm_w;
@@ -50,13 +51,37 @@ struct ChainParams {
   int n_steps;
   int M;             // valid batch rows
   float* partials;   // stream-K partial tiles (context workspace)
-  int* counters;     // per-tile arrival counters (context workspace), zero between uses
   int* sync;         // [2 * n_steps]: sync[2s] = CTAs done with step s, sync[2s+1] = rows normalised for step s; zeroed
                      // by the host side before every launch
   int lookahead;     // W tiles pulled into L2 ahead of the ring
+  unsigned long long* trace;  // optional [grid][n_steps][8] globaltimer stamps (tools/bench_chain.py TRACE=1), else NULL
 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CHAIN_TRACE(slot) \
+  do { if (p.trace) p.trace[(static_cast<size_t>(cta) * p.n_steps + s) * 8 + (slot)] = gtime(); } while (0)
+
 static constexpr int kChainMaxVec = 4;  // norm_kernel's kMaxVec
+
+// Stream-K range of CTA `cta` in a step: the step's units are cut over Gs = min(units, grid) CTAs, exactly like a
+// stand-alone gemm_stream_kernel launch (grid = min(units, SMs)) -- every participating CTA owns at least one unit, which
+// the split reduction relies on (contributors of a tile = a contiguous CTA interval); the other CTAs sit the step out.
+struct ChainRange { int lo, hi, Gs; };
+__device__ __forceinline__ ChainRange chain_range(int units, int cta, int G) {
+  ChainRange r;
+  r.Gs = units < G ? units : G;
+  if (cta < r.Gs) {
+    r.lo = gs_lo(cta, units, r.Gs);
+    r.hi = gs_lo(cta + 1, units, r.Gs);
+  } else {
+    r.lo = r.hi = 0;
+  }
+  return r;
+}
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -76,54 +101,247 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // VT = min(512, ceil32(cols / 8)) threads (what rmsnorm_run launches for M <= 32 rows): thread (warp w, lane l) plays
 // the virtual warps w, w + 4, ...; sums are combined in the same order, so the result is bit-identical.
 template <typename T>
-__device__ __forceinline__ void chain_rmsnorm_row(const T* __restrict__ xr, const T* __restrict__ w, T* __restrict__ yr,
-                                                  int cols, float eps, int etid, float* red) {
+__device__ __forceinline__ uint4 chain_norm_vec(uint4 r, uint4 wv, float rstd) {
+  // HF: weight * (x_fp32 * rstd).to(dtype) -- one rounding before the weight multiply (as norm_kernel)
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w}, wu[4] = {wv.x, wv.y, wv.z, wv.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack2<T>(u[j]);
+    const float2 g = unpack2<T>(wu[j]);
+    const float2 n = unpack2<T>(pack2<T>(f.x * rstd, f.y * rstd));
+    o[j] = pack2<T>(g.x * n.x, g.y * n.y);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <typename T>
+__device__ __forceinline__ float chain_sumsq(uint4 r) {
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack2<T>(u[j]);
+    sq += f.x * f.x + f.y * f.y;
+  }
+  return sq;
+}
+
+template <typename T>
+__device__ __forceinline__ void chain_rmsnorm_row(const T* xr, const T* __restrict__ w, T* yr, int cols, float eps, int etid,
+                                                  float* red) {
   const int nvec = cols >> 3;
   int VT = ((nvec + 31) / 32) * 32;
   if (VT > 512) VT = 512;
   while (VT * kChainMaxVec < nvec) VT += 32;
   const int nvw = VT >> 5;                    // virtual warps
   const int w4 = etid >> 5, l = etid & 31;
-  // pass 1: sum of squares per virtual thread, warp_sum per virtual warp
-  for (int vw = w4; vw < nvw; vw += 4) {
-    const int vt = vw * 32 + l;
-    float sq = 0.f;
+  // x is rewritten by other CTAs inside this kernel: read it past L1 (__ldcg)
+  if (nvec <= VT && nvw <= 16) {
+    // the common shapes (one vector per virtual thread, cols <= 4096): the whole row and its weights in ONE round of
+    // loads, kept in registers for the second pass (virtual thread vt = etid + 128 k handles vector vt in both passes)
+    uint4 r[4], wv[4];
 #pragma unroll
-    for (int i = 0; i < kChainMaxVec; ++i) {
-      const int vi = vt + i * VT;
-      if (vi < nvec) {
-        const uint4 r = *reinterpret_cast<const uint4*>(xr + vi * 8);
-        const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+    for (int k = 0; k < 4; ++k) {
+      const int vi = etid + 128 * k;
+      const bool ok = (w4 + 4 * k < nvw) && vi < nvec;
+      r[k] = ok ? __ldcg(reinterpret_cast<const uint4*>(xr + vi * 8)) : make_uint4(0, 0, 0, 0);
+      wv[k] = ok ? *reinterpret_cast<const uint4*>(w + vi * 8) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack2<T>(u[j]);
-          sq += f.x * f.x + f.y * f.y;
+    for (int k = 0; k < 4; ++k) {
+      if (w4 + 4 * k < nvw) {
+        const float sq = warp_sum(chain_sumsq<T>(r[k]));
+        if (l == 0) red[w4 + 4 * k] = sq;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float t = (l < nvw) ? red[l] : 0.f;
+    t = warp_sum(t);
+    const float rstd = rsqrtf(t / cols + eps);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int vi = etid + 128 * k;
+      if ((w4 + 4 * k < nvw) && vi < nvec) *reinterpret_cast<uint4*>(yr + vi * 8) = chain_norm_vec<T>(r[k], wv[k], rstd);
+    }
+  } else {
+    for (int vw = w4; vw < nvw; vw += 4) {
+      const int vt = vw * 32 + l;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChainMaxVec; ++i) {
+        const int vi = vt + i * VT;
+        if (vi < nvec) sq += chain_sumsq<T>(__ldcg(reinterpret_cast<const uint4*>(xr + vi * 8)));
+      }
+      sq = warp_sum(sq);
+      if (l == 0) red[vw] = sq;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float t = (l < nvw) ? red[l] : 0.f;
+    t = warp_sum(t);
+    const float rstd = rsqrtf(t / cols + eps);
+    for (int vi = etid; vi < nvec; vi += 128)
+      *reinterpret_cast<uint4*>(yr + vi * 8) = chain_norm_vec<T>(__ldcg(reinterpret_cast<const uint4*>(xr + vi * 8)),
+                                                                 *reinterpret_cast<const uint4*>(w + vi * 8), rstd);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // red[] is reused by the next row / step
+}
+
+// Split reduction of one tile segment, cooperative flavour.  In gemm_stream_kernel the LAST contributor of a tile sums
+// every partial (a serial chain: wait for the last arrival, then ceil(n / 2) dependent L2 round trips, then the whole
+// epilogue) while the other contributors are done -- fine when nobody may wait, but in the chain every CTA has to wait
+// for the step to complete anyway, and that tail (8-15 us on the slowest CTA, traced) was the longest part of every
+// step boundary.  Here all n contributors of a tile arrive at about the same time (same number of units each), so they
+// share the work: everyone parks its partial, waits until all n have arrived (spin on the tile counter), then
+// contributor j sums -- in CTA order, so the result is bit-identical -- and finishes the batch-column groups g with
+// g % n == j: one round of loads per CTA, 1 / n of the epilogue each.  Every step has its own tile counters (zeroed by
+// the host side with the grid-barrier state), so nothing has to be reset inside the kernel.
+// (b) of the cooperative split reduction: the epilogue of the batch-column groups in `mine` of tile t from v[].
+template <typename T, int BN, int EK>
+__device__ __forceinline__ void chain_epilogue(const GsOut& p, int t, uint32_t mine, float (&v)[BN], int q, int lane, int etid) {
+  if (mine == 0u) return;
+  const T* resid = reinterpret_cast<const T*>(p.residual);
+  const int n_row = t * GS_BM + etid;  // weight row = output column
+  const bool n_ok = n_row < p.N;
+  if constexpr (EK == 1) {
+    // SiLU(gate) * up: lanes 0-15 hold gate rows, lanes 16-31 the partner up rows (packed weight layout)
+    const int oc = ((t * GS_BM + q * 32) >> 1) + (lane & 15);
+    T* out = reinterpret_cast<T*>(p.D) + oc;
+    const bool st_ok = lane < 16 && n_ok;
+#pragma unroll
+    for (int i = 0; i < BN; ++i) {
+      if (mine & (1u << (i >> 2))) {       // CTA-uniform: all lanes take part in the shuffle
+        const float up = __shfl_xor_sync(0xffffffffu, v[i], 16);
+        const float gte = v[i];
+        const float o = __fdividef(gte, 1.f + __expf(fminf(-gte, 80.f))) * up;
+        if (st_ok && i < p.M) out[static_cast<int64_t>(i) * p.ldd] = T16<T>::from_f(o);
+      }
+    }
+  } else if (n_ok) {
+    if (resid != nullptr) {
+      float rr[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i)
+        rr[i] = (i < p.M && (mine & (1u << (i >> 2)))) ? T16<T>::to_f(resid[static_cast<int64_t>(i) * p.ldr + n_row]) : 0.f;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) v[i] += rr[i];
+    }
+    if (p.out_f32) {
+      float* out = reinterpret_cast<float*>(p.D) + n_row;
+#pragma unroll
+      for (int i = 0; i < BN; ++i)
+        if (i < p.M && (mine & (1u << (i >> 2)))) out[static_cast<int64_t>(i) * p.ldd] = v[i];
+    } else {
+      T* out = reinterpret_cast<T*>(p.D) + n_row;
+#pragma unroll
+      for (int i = 0; i < BN; ++i)
+        if (i < p.M && (mine & (1u << (i >> 2)))) out[static_cast<int64_t>(i) * p.ldd] = T16<T>::from_f(v[i]);
+    }
+  }
+}
+
+// (a) park the partial of a cut tile and announce it -- WITHOUT waiting: a CTA parks every partial segment of the step
+// first and only then waits for the other contributors (waiting per segment would chain CTA k's first segment to CTA
+// k-1's last one across the whole grid).
+template <int BN>
+__device__ __forceinline__ void chain_park(const GsOut& p, int lo, int t, const float (&v)[BN], int etid) {
+  const int t0 = t * p.kb_total;
+  const int which = (lo >= t0) ? 0 : 1;
+  float4* slot = reinterpret_cast<float4*>(p.partials) + static_cast<size_t>(2 * blockIdx.x + which) * (GS_BM * BN / 4) + etid;
+#pragma unroll
+  for (int i = 0; i < BN / 4; ++i) slot[i * GS_BM] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // every thread's partial stores precede thread 0's release
+  if (etid == 0) red_release_add(p.counters + t, 1);
+}
+
+// Sums, for up to GI column groups of this CTA (g = j + gi * n), the partials of contributors c_first .. c_last in CTA
+// order; CI loads per group and round, all rounds' loads of a group issued before the first add.
+template <int BN, int GI, int CI>
+__device__ __forceinline__ void chain_sum_groups(const GsOut& p, int U, int G, int t0, int c_first, int c_last, int j, int n,
+                                                 int etid, float (&v)[BN]) {
+  constexpr int NG = BN / 4;
+  const float4* base = reinterpret_cast<const float4*>(p.partials) + etid;
+  float4 acc[GI];
+#pragma unroll
+  for (int gi = 0; gi < GI; ++gi) acc[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = c_first; c0 <= c_last; c0 += CI) {     // one round unless n > CI
+    float4 f[GI][CI];
+#pragma unroll
+    for (int gi = 0; gi < GI; ++gi) {
+      const int g = j + gi * n;
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const int c = c0 + ci;
+        const bool ok = g < NG && c <= c_last;
+        const int slot = 2 * c + ((gs_lo(c, U, G) >= t0) ? 0 : 1);   // contributor c's slot: 0 when its range starts inside the tile
+        f[gi][ci] = ok ? __ldcg(base + static_cast<size_t>(slot) * (GS_BM * BN / 4) + g * GS_BM) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int gi = 0; gi < GI; ++gi) {
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        if (c0 + ci <= c_last) {
+          acc[gi].x += f[gi][ci].x; acc[gi].y += f[gi][ci].y; acc[gi].z += f[gi][ci].z; acc[gi].w += f[gi][ci].w;
         }
       }
     }
-    sq = warp_sum(sq);
-    if (l == 0) red[vw] = sq;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  float t = (l < nvw) ? red[l] : 0.f;
-  t = warp_sum(t);
-  const float rstd = rsqrtf(t / cols + eps);
-  // pass 2: normalise (HF: weight * (x_fp32 * rstd).to(dtype) -- one rounding before the weight multiply)
-  for (int vi = etid; vi < nvec; vi += 128) {
-    const uint4 r = *reinterpret_cast<const uint4*>(xr + vi * 8);
-    const uint4 wv = *reinterpret_cast<const uint4*>(w + vi * 8);
-    const uint32_t u[4] = {r.x, r.y, r.z, r.w}, wu[4] = {wv.x, wv.y, wv.z, wv.w};
-    uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack2<T>(u[j]);
-      const float2 g = unpack2<T>(wu[j]);
-      const float2 n = unpack2<T>(pack2<T>(f.x * rstd, f.y * rstd));
-      o[j] = pack2<T>(g.x * n.x, g.y * n.y);
+  for (int gi = 0; gi < GI; ++gi) {
+    const int g = j + gi * n;
+    // v[] is indexed with a run-time g: select statically
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) {
+      if (gg == g) { v[4 * gg] = acc[gi].x; v[4 * gg + 1] = acc[gi].y; v[4 * gg + 2] = acc[gi].z; v[4 * gg + 3] = acc[gi].w; }
     }
-    *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // red[] is reused by the next row / step
+}
+
+// (c) wait until all n contributors of tile t have parked, sum -- in CTA order, bit-identical to gs_finish_segment --
+// the column groups g with g % n == j (j = this CTA's rank among the contributors) and finish them.  Every load of the
+// reduction (about NG + n float4 per thread whatever n is) and the residual values are issued in one round.
+template <typename T, int BN, int EK>
+__device__ __forceinline__ void chain_reduce(const GsOut& p, int U, int G, int t, int q, int lane, int etid) {
+  constexpr int NG = BN / 4;
+  const int t0 = t * p.kb_total;
+  const int c_first = gs_owner(t0, U, G), c_last = gs_owner(t0 + p.kb_total - 1, U, G);
+  const int n = c_last - c_first + 1, j = static_cast<int>(blockIdx.x) - c_first;
+  uint32_t mine = 0u;
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+    if (g % n == j) mine |= 1u << g;
+  // residual values of my columns: independent of the other contributors, so they travel under the wait
+  const T* resid = reinterpret_cast<const T*>(p.residual);
+  const int n_row = t * GS_BM + etid;
+  float rr[BN];
+  if constexpr (EK != 1) {
+#pragma unroll
+    for (int i = 0; i < BN; ++i)
+      rr[i] = (resid != nullptr && n_row < p.N && i < p.M && (mine & (1u << (i >> 2))))
+                  ? T16<T>::to_f(resid[static_cast<int64_t>(i) * p.ldr + n_row]) : 0.f;
+  }
+  if (etid == 0) spin_until(p.counters + t, n);
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // thread 0's acquire precedes every thread's loads
+  float v[BN];
+#pragma unroll
+  for (int i = 0; i < BN; ++i) v[i] = 0.f;
+  if (mine != 0u) {
+    // my groups are j, j + n, j + 2n, ...: at most GI of them, each summed over the n contributors.  (GI, CI) variants
+    // keep the loads of ONE round in registers with compile-time indices: n <= 2 -> 4 x 2, n == 3 -> 3 x 3,
+    // n <= 8 -> 2 x 8, else 1 x 16 (n > 16 cannot happen with >= 8 k-blocks per CTA and <= 172 per tile; looped anyway)
+    if (n <= 2) chain_sum_groups<BN, 4, 2>(p, U, G, t0, c_first, c_last, j, n, etid, v);
+    else if (n == 3) chain_sum_groups<BN, 3, 3>(p, U, G, t0, c_first, c_last, j, n, etid, v);
+    else if (n <= 8) chain_sum_groups<BN, 2, 8>(p, U, G, t0, c_first, c_last, j, n, etid, v);
+    else chain_sum_groups<BN, 1, 16>(p, U, G, t0, c_first, c_last, j, n, etid, v);
+  }
+  if constexpr (EK != 1) {
+#pragma unroll
+    for (int i = 0; i < BN; ++i) v[i] += rr[i];
+  }
+  GsOut pp = p;
+  pp.residual = nullptr;                           // already added
+  chain_epilogue<T, BN, EK>(pp, t, mine, v, q, lane, etid);
 }
 
 template <int BN>
@@ -151,7 +369,6 @@ gemm_chain_kernel(const ChainParams p) {
   uint64_t* tmem_full = empty_bar + GS_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
   float* red = reinterpret_cast<float*>(tmem_ptr + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -190,8 +407,9 @@ gemm_chain_kernel(const ChainParams p) {
         ++pu;
         while (pu >= p_hi) {
           if (++ps >= p.n_steps) return false;
-          pu = gs_lo(cta, p.steps[ps].units, G);
-          p_hi = gs_lo(cta + 1, p.steps[ps].units, G);
+          const ChainRange r = chain_range(p.steps[ps].units, cta, G);
+          pu = r.lo;
+          p_hi = r.hi;
         }
         return true;
       };
@@ -199,8 +417,10 @@ gemm_chain_kernel(const ChainParams p) {
       bool pf_live = p.lookahead > 0 && pf_advance();   // cursor on the first unit
       for (int s = 0; s < p.n_steps; ++s) {
         const ChainStep& st = p.steps[s];
-        const int lo = gs_lo(cta, st.units, G), hi = gs_lo(cta + 1, st.units, G);
+        const ChainRange rg = chain_range(st.units, cta, G);
+        const int lo = rg.lo, hi = rg.hi;
         if (lo < hi) tma_prefetch_desc(&st.tmW);
+        CHAIN_TRACE(5);
         for (int u = lo; u < hi; ++u) {
           while (pf_live && n_pf <= n_loaded) {   // the ring load itself covers this unit: skip it
             pf_live = pf_advance();
@@ -225,6 +445,7 @@ gemm_chain_kernel(const ChainParams p) {
             phase ^= 1;
           }
         }
+        CHAIN_TRACE(0);
       }
     }
   } else if (warp == 3) {
@@ -235,12 +456,14 @@ gemm_chain_kernel(const ChainParams p) {
       pdl_wait();  // the chain's first input comes from the previous kernel
       for (int s = 0; s < p.n_steps; ++s) {
         const ChainStep& st = p.steps[s];
-        const int lo = gs_lo(cta, st.units, G), hi = gs_lo(cta + 1, st.units, G);
+        const ChainRange rg = chain_range(st.units, cta, G);
+        const int lo = rg.lo, hi = rg.hi;
         if (lo >= hi) continue;
         tma_prefetch_desc(&st.tmX);
         if (st.has_norm) spin_until(p.sync + 2 * s + 1, p.M);
         else if (s > 0) spin_until(p.sync + 2 * (s - 1), G);
         fence_proxy_async_global();
+        CHAIN_TRACE(1);
         for (int u = lo; u < hi; ++u) {
           const int kb = u % st.kb_total;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -262,7 +485,8 @@ gemm_chain_kernel(const ChainParams p) {
       uint32_t acc_phase = 0;
       for (int s = 0; s < p.n_steps; ++s) {
         const ChainStep& st = p.steps[s];
-        const int lo = gs_lo(cta, st.units, G), hi = gs_lo(cta + 1, st.units, G);
+        const ChainRange rg = chain_range(st.units, cta, G);
+        const int lo = rg.lo, hi = rg.hi;
         int u = lo;
         while (u < hi) {
           const int t = u / st.kb_total;
@@ -274,6 +498,7 @@ gemm_chain_kernel(const ChainParams p) {
             mbar_wait(&full_w[stage], phase);
             mbar_wait(&full_x[stage], phase);
             tc_fence_after();
+            if (v == lo) CHAIN_TRACE(2);
             const uint32_t sw = smem_u32(smem + stage * S::kStageBytes);
             const uint64_t a_desc = make_kmajor_sw128_desc(sw);
             const uint64_t b_desc = make_kmajor_sw128_desc(sw + S::kWBytes);
@@ -293,6 +518,7 @@ gemm_chain_kernel(const ChainParams p) {
           }
           u = seg_end;
         }
+        CHAIN_TRACE(3);
       }
     }
   } else if (warp >= 4) {
@@ -311,18 +537,21 @@ gemm_chain_kernel(const ChainParams p) {
         }
         const T* xr = reinterpret_cast<const T*>(st.norm_src) + static_cast<int64_t>(cta) * st.norm_cols;
         T* yr = reinterpret_cast<T*>(st.norm_dst) + static_cast<int64_t>(cta) * st.norm_cols;
+        if (etid == 0) CHAIN_TRACE(6);
         chain_rmsnorm_row<T>(xr, reinterpret_cast<const T*>(st.norm_w), yr, st.norm_cols, st.norm_eps, etid, red);
         if (etid == 0) {
-          __threadfence();
-          red_release_add(p.sync + 2 * s + 1, 1);
+          red_release_add(p.sync + 2 * s + 1, 1);   // (the bar.sync at the end of the norm ordered every thread's stores)
+          CHAIN_TRACE(7);
         }
       }
       const int U = st.units;
-      const int lo = gs_lo(cta, U, G), hi = gs_lo(cta + 1, U, G);
+      const ChainRange rg = chain_range(U, cta, G);
+      const int lo = rg.lo, hi = rg.hi, Gs = rg.Gs;
       GsOut out;
       out.D = st.D; out.ldd = st.ldd; out.bias = nullptr; out.residual = st.residual; out.ldr = st.ldr;
       out.M = p.M; out.N = st.N; out.epilogue = EPI_NONE; out.out_f32 = st.out_f32; out.kb_total = st.kb_total;
-      out.partials = p.partials; out.counters = p.counters;
+      out.partials = p.partials; out.counters = st.counters;
+      int pend[2], n_pend = 0;   // cut tiles of this CTA's range (its first and / or last segment)
       int u = lo;
       while (u < hi) {
         const int t = u / st.kb_total;
@@ -354,15 +583,24 @@ gemm_chain_kernel(const ChainParams p) {
           acc = 0;
           acc_phase ^= 1;
         }
-        if (st.ek == 1) gs_finish_segment<T, BN, 1>(out, U, G, lo, t, whole, v, last_flag, q, lane, etid);
-        else gs_finish_segment<T, BN, 0>(out, U, G, lo, t, whole, v, last_flag, q, lane, etid);
+        if (whole) {
+          if (st.ek == 1) chain_epilogue<T, BN, 1>(out, t, (1u << (BN / 4)) - 1u, v, q, lane, etid);
+          else chain_epilogue<T, BN, 0>(out, t, (1u << (BN / 4)) - 1u, v, q, lane, etid);
+        } else {
+          chain_park<BN>(out, lo, t, v, etid);
+          pend[n_pend++] = t;
+        }
         u = seg_end;
+      }
+      for (int k = 0; k < n_pend; ++k) {
+        if (st.ek == 1) chain_reduce<T, BN, 1>(out, U, Gs, pend[k], q, lane, etid);
+        else chain_reduce<T, BN, 0>(out, U, Gs, pend[k], q, lane, etid);
       }
       // this CTA's share of step s is stored (including every tile it finished as the last arriver)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (etid == 0) {
-        __threadfence();
         red_release_add(p.sync + 2 * s, 1);
+        CHAIN_TRACE(4);
       }
     }
   }
@@ -383,9 +621,10 @@ size_t chain_step_bytes() { return sizeof(ChainStep); }
 // Fills one step (host copy).  W [N, K] (ldb), X [M, K] (lda) read through TMA; D / residual as in gemm_stream_run.
 int chain_encode_step(void* host_step, int bn, const void* W, int64_t ldb, const void* X, int64_t lda, int M, int N, int K,
                       void* D, int64_t ldd, const void* residual, int64_t ldr, int ek, int out_f32, const void* norm_src,
-                      const void* norm_w, void* norm_dst, int norm_cols, float norm_eps) {
+                      const void* norm_w, void* norm_dst, int norm_cols, float norm_eps, int* counters_dev) {
   ChainStep* s = static_cast<ChainStep*>(host_step);
   memset(s, 0, sizeof(ChainStep));
+  s->counters = counters_dev;
   s->D = D; s->ldd = ldd; s->residual = residual; s->ldr = ldr;
   s->N = N; s->K = K; s->ek = ek; s->out_f32 = out_f32;
   s->num_t = N > 0 ? (N + GS_BM - 1) / GS_BM : 0;
@@ -424,10 +663,10 @@ int gemm_chain_run(Context* ctx, const void* steps_dev, int n_steps, int M, int 
   p.steps = static_cast<const ChainStep*>(steps_dev);
   p.n_steps = n_steps;
   p.M = M;
-  p.counters = reinterpret_cast<int*>(ctx->workspace);
   p.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(ctx->workspace) + kStreamCounterBytes);
   p.sync = sync_dev;
   p.lookahead = ctx->prefetch_units > 0 ? 2 * ctx->prefetch_units : 0;
+  p.trace = static_cast<unsigned long long*>(ctx->chain_trace);
   ctx->next_w = nullptr;
   const bool pdl = ctx->pdl != 0;
   int st;

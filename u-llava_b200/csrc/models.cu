@@ -130,10 +130,20 @@ size_t llama_scratch(int rows, int hidden, int ffn) {
 // Program of one decode step: chain 0 = [RMSNorm(ln1_0) -> qkv_0]; after the attention of layer l, chain l + 1 =
 // [o_l (+residual) | RMSNorm(ln2_l) -> gate/up_l (SiLU*mul) | down_l (+residual) | RMSNorm(ln1_{l+1}) -> qkv_{l+1}], the
 // last one ending in [final RMSNorm -> lm_head (fp32 logits)] instead.  Device layout of the program buffer:
-// [2 ints of grid-barrier state per step, padded to 128 B][ChainStep x (1 + 4 * layers)].
+// [2 ints of grid-barrier state per step + one arrival counter per weight tile of every step, padded to 128 B]
+// [ChainStep x (1 + 4 * layers)].  The first part is zeroed with ONE memset node at the start of every decode step.
 static inline int chain_total_steps(int layers) { return 1 + 4 * layers; }
-static inline size_t chain_sync_bytes(int layers) { return align_up(static_cast<size_t>(2) * chain_total_steps(layers) * sizeof(int), 128); }
-size_t llama_chain_bytes(int layers) { return chain_sync_bytes(layers) + chain_total_steps(layers) * chain_step_bytes() + 256; }
+static inline int chain_tiles(int n) { return (n + 127) / 128; }
+static inline size_t chain_state_ints(int layers, int H, int F, int V) {
+  return static_cast<size_t>(2) * chain_total_steps(layers) +
+         static_cast<size_t>(layers) * (chain_tiles(3 * H) + chain_tiles(H) + chain_tiles(2 * F) + chain_tiles(H)) + chain_tiles(V);
+}
+static inline size_t chain_state_bytes(int layers, int H, int F, int V) {
+  return align_up(chain_state_ints(layers, H, F, V) * sizeof(int), 128);
+}
+size_t llama_chain_bytes(int layers, int hidden, int ffn, int vocab) {
+  return chain_state_bytes(layers, hidden, ffn, vocab) + chain_total_steps(layers) * chain_step_bytes() + 256;
+}
 
 static inline uint8_t* chain_base(const ullava_llama_args& a) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a.chain_program) + 127) & ~uintptr_t(127));
@@ -143,8 +153,9 @@ int llama_chain_prepare_run(Context* ctx, const ullava_decode_args& d) {
   const ullava_llama_args& a = d.llama;
   ULLAVA_REQUIRE(a.seq == 1 && a.final_out && a.chain_program && d.lm_head && d.logits, "chain_prepare: decode-step arguments expected");
   ULLAVA_REQUIRE(a.batch >= 1 && a.batch <= 32, "chain_prepare: batch %d not in 1..32 (larger decode batches take the GEMM-per-kernel path)", a.batch);
-  ULLAVA_REQUIRE(a.chain_bytes >= llama_chain_bytes(a.layers), "chain_prepare: program buffer too small (%zu < %zu)",
-                 a.chain_bytes, llama_chain_bytes(a.layers));
+  ULLAVA_REQUIRE(a.chain_bytes >= llama_chain_bytes(a.layers, a.hidden_size, a.ffn, d.vocab),
+                 "chain_prepare: program buffer too small (%zu < %zu)", a.chain_bytes,
+                 llama_chain_bytes(a.layers, a.hidden_size, a.ffn, d.vocab));
   ULLAVA_REQUIRE(a.n_weights == 6 * a.layers + 1 && a.layers >= 1, "chain_prepare: expected %d weights", 6 * a.layers + 1);
   const int rows = a.batch, H = a.hidden_size, F = a.ffn, V = d.vocab;
   const int bn = rows <= 16 ? 16 : 32;
@@ -159,10 +170,14 @@ int llama_chain_prepare_run(Context* ctx, const ullava_decode_args& d) {
   std::vector<uint8_t> host(static_cast<size_t>(total) * sb + 128);
   uint8_t* hs = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(host.data()) + 127) & ~uintptr_t(127));
   int k = 0;
+  uint8_t* base = chain_base(a);
+  int* tile_counters = reinterpret_cast<int*>(base) + 2 * total;   // behind the grid-barrier state
   auto step = [&](const void* W, int64_t ldb, const void* X, int64_t lda, int N, int K, void* D, int64_t ldd,
                   const void* resid, int ek, int out_f32, const void* nsrc, const void* nw, void* ndst) {
+    int* cnt = tile_counters;
+    tile_counters += chain_tiles(N);
     return chain_encode_step(hs + static_cast<size_t>(k++) * sb, bn, W, ldb, X, lda, rows, N, K, D, ldd, resid, H, ek,
-                             out_f32, nsrc, nw, ndst, H, a.eps);
+                             out_f32, nsrc, nw, ndst, H, a.eps, cnt);
   };
   const void* const* W = a.weights;
   RUN(step(W[1], H, xn, H, 3 * H, H, qkv, 3 * H, nullptr, 0, 0, a.hidden, W[0], xn));
@@ -177,14 +192,15 @@ int llama_chain_prepare_run(Context* ctx, const ullava_decode_args& d) {
       RUN(step(d.lm_head, H, a.final_out, H, V, H, d.logits, V, nullptr, 0, 1, a.hidden, W[6 * a.layers], a.final_out));
     }
   }
-  uint8_t* base = chain_base(a);
-  ULLAVA_CHECK_CUDA(cudaMemcpy(base + chain_sync_bytes(a.layers), hs, static_cast<size_t>(total) * sb, cudaMemcpyHostToDevice));
-  ULLAVA_CHECK_CUDA(cudaMemset(base, 0, chain_sync_bytes(a.layers)));
+  const size_t state = chain_state_bytes(a.layers, H, F, V);
+  ULLAVA_REQUIRE(static_cast<size_t>(tile_counters - reinterpret_cast<int*>(base)) * sizeof(int) <= state, "chain_prepare: internal");
+  ULLAVA_CHECK_CUDA(cudaMemcpy(base + state, hs, static_cast<size_t>(total) * sb, cudaMemcpyHostToDevice));
+  ULLAVA_CHECK_CUDA(cudaMemset(base, 0, state));
   return OK;
 }
 
 // One decode step through the chains (a.chain_program prepared for exactly these arguments and this context).
-static int llama_decode_chained(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev) {
+static int llama_decode_chained(Context* ctx, const ullava_llama_args& a, cudaStream_t s, const int32_t* pos_dev, int vocab) {
   const int H = a.hidden_size, hd = a.head_dim;
   Arena ar(a.scratch, a.scratch_bytes);
   ar.take(static_cast<size_t>(a.batch) * H * 2);                      // xn
@@ -199,10 +215,12 @@ static int llama_decode_chained(Context* ctx, const ullava_llama_args& a, cudaSt
   uint16_t* vc0 = static_cast<uint16_t*>(a.v_cache);
   uint8_t* base = chain_base(a);
   int* sync = reinterpret_cast<int*>(base);
-  const uint8_t* steps = base + chain_sync_bytes(a.layers);
+  const size_t state = chain_state_bytes(a.layers, H, a.ffn, vocab);
+  const uint8_t* steps = base + state;
   const size_t sb = chain_step_bytes();
-  // grid-barrier state of every chain of this step: one memset node in front of the ~2 * layers kernels
-  ULLAVA_CHECK_CUDA(cudaMemsetAsync(sync, 0, chain_sync_bytes(a.layers), s));
+  // grid-barrier state + tile arrival counters of every chain of this step: one memset node in front of the
+  // ~2 * layers kernels
+  ULLAVA_CHECK_CUDA(cudaMemsetAsync(sync, 0, state, s));
   const double w_bytes = 2.0 * (4.0 * H * H + 3.0 * H * a.ffn);
   {
     ProfScope _ps(ctx, s, ULLAVA_PROF_GEMM_STREAM, 2.0 * a.batch * 3.0 * H * H, 2.0 * 3.0 * H * H);
@@ -236,7 +254,7 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
   if (a.chain_program != nullptr) {
     ULLAVA_REQUIRE(a.seq == 1 && a.final_out && !a.all_hidden && a.batch <= 32 && tail_w != nullptr,
                    "llama_forward: a chain program serves the decode step (ullava_llama_decode_step) only");
-    return llama_decode_chained(ctx, a, s, pos_dev);
+    return llama_decode_chained(ctx, a, s, pos_dev, tail_n);
   }
   Arena ar(a.scratch, a.scratch_bytes);
   void* xn = ar.take(static_cast<size_t>(rows) * H * 2);

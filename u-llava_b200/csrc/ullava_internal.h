@@ -32,6 +32,7 @@ struct ullava_ctx {
   int prefetch_units = 12;  // 16 KB tiles per SM pulled into L2 (0 = off); ULLAVA_PREFETCH_UNITS overrides at create
   int gemm_pair = 1;  // large-M GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles); ULLAVA_GEMM_PAIR=0 turns it off
   int group_m = 0;    // 0 = default rasterisation group of the large-M GEMM; ULLAVA_GROUP_M overrides at create (tuning)
+  void* chain_trace = nullptr;  // debug: globaltimer stamps of the next chain kernels (ullava_debug_chain_trace)
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path
   bool prof_on = false;
@@ -76,7 +77,7 @@ size_t gemm_stream_workspace_bytes(int sm_count);
 size_t chain_step_bytes();
 int chain_encode_step(void* host_step, int bn, const void* W, int64_t ldb, const void* X, int64_t lda, int M, int N, int K,
                       void* D, int64_t ldd, const void* residual, int64_t ldr, int ek, int out_f32, const void* norm_src,
-                      const void* norm_w, void* norm_dst, int norm_cols, float norm_eps);
+                      const void* norm_w, void* norm_dst, int norm_cols, float norm_eps, int* counters_dev);
 int gemm_chain_run(Context* ctx, const void* steps_dev, int n_steps, int M, int dtype, int* sync_dev, cudaStream_t stream);
 
 // norm.cu
@@ -174,7 +175,7 @@ int llama_forward_run(Context* ctx, const ullava_llama_args& a, cudaStream_t s, 
                       const void* tail_w = nullptr, int tail_n = 0);
 int llama_decode_step_run(Context* ctx, const ullava_decode_args& a, cudaStream_t s);
 size_t llama_scratch(int rows, int hidden, int ffn);
-size_t llama_chain_bytes(int layers);
+size_t llama_chain_bytes(int layers, int hidden, int ffn, int vocab);
 int llama_chain_prepare_run(Context* ctx, const ullava_decode_args& a);
 
 }  // namespace ullava

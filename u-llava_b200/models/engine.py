@@ -317,8 +317,10 @@ class DecodeSession:
         self.scratch = torch.empty(ctx.llama_scratch_bytes(batch, H, stack.cfg["ffn"]), dtype=torch.uint8, device=dev)
         self.embed_table, self.lm_head = embed_table, lm_head
         # decode-layer chains (csrc/gemm_chain_sm100.cu): per step context, the argument block with its own chain
-        # program (the program holds TMA descriptors of this session's buffers and is partitioned over the context's SMs)
-        self.use_chain = batch <= 32 and os.environ.get("ULLAVA_DECODE_CHAIN", "1") != "0"
+        # program (the program holds TMA descriptors of this session's buffers and is partitioned over the context's SMs).
+        # Bit-identical to the kernel-per-GEMM step, but measured SLOWER on B200 (profiles/r02_decode_chain.md: 163-176 vs
+        # 154 us per layer), so it is opt-in: ULLAVA_DECODE_CHAIN=1.
+        self.use_chain = batch <= 32 and os.environ.get("ULLAVA_DECODE_CHAIN", "0") == "1"
         self.chain_args = {}      # id(step context) -> (DecodeArgs, program buffer)
         self.graphs = {}          # id(step context) -> (CUDAGraph, kernel nodes): persistent grids are sized per context
         self.graph_nodes = 0
@@ -428,7 +430,8 @@ class DecodeSession:
         entry = self.chain_args.get(id(ctx))
         if entry is None:
             a = native.DecodeArgs.from_buffer_copy(self.args)
-            nbytes = ctx.llama_chain_bytes(self.stack.cfg["layers"])
+            c = self.stack.cfg
+            nbytes = ctx.llama_chain_bytes(c["layers"], c["hidden"], c["ffn"], self.lm_head.shape[0])
             prog = torch.empty(nbytes, dtype=torch.uint8, device=self.stack.device)
             a.llama.chain_program, a.llama.chain_bytes = prog.data_ptr(), nbytes
             torch.cuda.synchronize(self.stack.device)      # the program is written with a synchronous copy

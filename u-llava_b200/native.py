@@ -131,7 +131,8 @@ _SIGNATURES = {
     "ullava_llama_forward": (_i32, [_vp, C.POINTER(LlamaArgs), _vp]),
     "ullava_llama_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
-    "ullava_llama_chain_bytes": (_sz, [_i32]),
+    "ullava_debug_chain_trace": (_i32, [_vp, _vp]),
+    "ullava_llama_chain_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ullava_llama_chain_prepare": (_i32, [_vp, C.POINTER(DecodeArgs)]),
     "ullava_greedy_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
                                   _vp, _vp]),
@@ -560,8 +561,8 @@ class Context:
         self._chk(self.lib.ullava_sam_encoder_forward(self.handle, C.byref(a), _stream()))
         return out, scratch
 
-    def llama_chain_bytes(self, layers: int) -> int:
-        return int(self.lib.ullava_llama_chain_bytes(int(layers)))
+    def llama_chain_bytes(self, layers: int, hidden: int, ffn: int, vocab: int) -> int:
+        return int(self.lib.ullava_llama_chain_bytes(int(layers), int(hidden), int(ffn), int(vocab)))
 
     def llama_chain_prepare(self, args: "DecodeArgs"):
         """Builds the decode-layer chain program into args.llama.chain_program (synchronous; not under capture)."""
