@@ -10,6 +10,7 @@ which EVERY compared greedy decision has a margin above the threshold:
 
     python tests/golden/find_seed.py core 0 16000     # ~0.1 s per seed; seed 14400 -> 0.163
     python tests/golden/find_seed.py full 0 400       # seed 332 -> 0.252
+    python tests/golden/find_seed.py coherent 0 200   # image seed of the coherent-mask fixture (oracle/synth.py): 96
 The goldens themselves are then written by make_golden.py from the REAL reference with those seeds.
 """
 import os
@@ -29,7 +30,32 @@ from tests.util_models import core_cfg, load_golden  # noqa: E402
 torch.set_grad_enabled(False)
 
 
+COH_SIZES = [(336, 336), (300, 420)]
+COH_RESIZES = [(1024, 1024), (731, 1024)]
+
+
+def coherent(lo, hi):
+    """image seeds for which all three masks of the tiny_full prompts are non-trivial and sharp"""
+    from oracle.synth import coherent_image, coherent_overrides
+    meta = load_golden("tiny_full")[1]
+    cfg = core_cfg()
+    sd = coherent_overrides(synth_state_dict(meta["shapes"], meta["seed"]))
+    ids = C.tiny_prompt(2, seg_loc=True)
+    ref = O.core_forward(sd, cfg, ids, synth_normal("images", (2, 3, 28, 28)), prefix="llm.")
+    scfg = dict(seg_token_idx=C.SEG_ID, loc_token_idx=C.LOC_ID)
+    for seed in range(lo, hi):
+        emb = O.sam_image_encoder(sd, "visual_model.", coherent_image(2, seed=seed), C.TINY_SAM_ENCODER)
+        pm, _, _ = O.masks_from_hidden(sd, scfg, ids, ref["last_hidden"], emb, COH_SIZES, COH_RESIZES)
+        stats = [((x > 0).float().mean().item(), (x.abs() < 0.01 * x.abs().max()).float().mean().item())
+                 for m in pm for x in m]
+        if all(0.05 < p < 0.95 and n < 1e-3 for p, n in stats):
+            print(f"image seed {seed}: (positive share, share within 1 % of max |logit|) = "
+                  f"{[(round(p, 3), round(n, 5)) for p, n in stats]}")
+
+
 def main():
+    if sys.argv[1] == "coherent":
+        return coherent(int(sys.argv[2]), int(sys.argv[3]))
     which, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     thr = float(sys.argv[4]) if len(sys.argv) > 4 else 0.16
     cfg = core_cfg()

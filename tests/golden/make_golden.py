@@ -126,6 +126,42 @@ def tiny_full():
                    "prompt encoder / mask decoder at build_sam geometry; .cuda() shim"))
 
 
+def tiny_full_coherent():
+    """The tiny_full model with the coherent-mask overrides (oracle/synth.py) on a piecewise-constant SAM image: the REAL
+    reference's forward(inference=True) masks at 336 x 336 / 300 x 420, for the IoU >= 0.999 gate."""
+    from oracle.synth import coherent_image, coherent_overrides
+    llm = dict(C.TINY_LLM)
+    cfg = ref_models.UllavaConfig(llm_config=llm, seg_token_idx=C.SEG_ID, loc_token_idx=C.LOC_ID)
+    cfg.llm_config._attn_implementation = "eager"
+    cfg.llm_config.vision_config._attn_implementation = "eager"
+    e = C.TINY_SAM_ENCODER
+    import models.ullava as ref_ullava
+    ref_ullava.build_sam_vit_h = lambda checkpoint=None: ref_build_sam(e["embed_dim"], e["depth"], e["num_heads"],
+                                                                        e["global_attn_indexes"])
+    m = ref_models.UllavaForCausalLM(cfg).eval().float()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(coherent_overrides(synth_state_dict(shapes, SEED_TINY_FULL)), strict=True)
+    B = 2
+    ids = C.tiny_prompt(B, seg_loc=True)
+    images = synth_normal("images", (B, 3, 28, 28))
+    images_sam = coherent_image(B)
+    sizes = [(336, 336), (300, 420)]
+    resizes = [(1024, 1024), (731, 1024)]
+    out = m(images_sam=images_sam, images=images, input_ids=ids, labels=ids.clone(),
+            attention_mask=torch.ones_like(ids).bool(), mask_list=[None] * B, size_list=sizes, resize_list=resizes,
+            bbox_list=[None] * B, inference=True)
+    arrays, stats = {}, []
+    for i in range(B):
+        pm = out["pred_masks"][i]
+        arrays[f"mask_bits_{i}"] = np.packbits((pm > 0).numpy().reshape(pm.shape[0], -1), axis=1)
+        arrays[f"mask_sub_{i}"] = pm.reshape(pm.shape[0], -1)[:, ::37].numpy().astype(np.float32)
+        stats.append([[float((x > 0).float().mean()), float(x.abs().max())] for x in pm])
+    save("tiny_full_coherent", arrays,
+         dict(seed=SEED_TINY_FULL, sizes=sizes, resizes=resizes, sub_stride=37, positive_share_and_max=stats,
+              note="reference UllavaForCausalLM.forward(inference=True) with oracle.synth.coherent_overrides / "
+                   "coherent_image: thresholded masks (packbits) + every 37th logit"))
+
+
 def sam_decoder_full():
     sam = ref_build_sam(64, 1, 2, [0]).float()
     shapes, sd = load_synth(sam, seed=1)

@@ -36,13 +36,17 @@ def build_tiny_core(dtype, device="cuda"):
     return m.to(device=device, dtype=dtype), sd, core_cfg()
 
 
-def build_tiny_full(dtype, device="cuda"):
+def build_tiny_full(dtype, device="cuda", coherent=False):
     """UllavaForCausalLM (B200 build) with the tiny_full golden weights (2-block SAM image encoder,
-    full-geometry prompt encoder / mask decoder)."""
+    full-geometry prompt encoder / mask decoder).  coherent: with oracle.synth.coherent_overrides (masks with large
+    margins, for the IoU >= 0.999 gate)."""
     import models
     from models.segment_anything.build_sam import _build_sam
     _, meta = load_golden("tiny_full")
     sd = synth_state_dict(meta["shapes"], meta["seed"])
+    if coherent:
+        from oracle.synth import coherent_overrides
+        sd = coherent_overrides(sd)
     e = C.TINY_SAM_ENCODER
     cfg = models.UllavaConfig(llm_config=dict(C.TINY_LLM), seg_token_idx=C.SEG_ID, loc_token_idx=C.LOC_ID)
 

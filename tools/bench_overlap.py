@@ -23,15 +23,35 @@ def child(sms):
     main = torch.cuda.current_stream()
     enc = model.visual_model.image_encoder
 
-    def timed(fn, reps=3):
+    power = {}
+
+    def timed(fn, reps=3, tag=None):
         fn()
         torch.cuda.synchronize()
+        sampler = None
+        if tag and os.environ.get("POWER"):
+            sampler = bench.ClockSampler(0)
+            sampler.start()
+            reps = max(reps, 8)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        if sampler:
+            import statistics
+            sm, pw = [], []
+            sampler.proc.terminate()
+            for ln in sampler.lines:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[0])); pw.append(float(f[2]))
+                except Exception:
+                    pass
+            if sm:
+                power[tag] = {"sm_mhz_median": statistics.median(sm), "power_w_median": statistics.median(pw),
+                              "power_w_max": max(pw), "samples": len(sm)}
         return e0.elapsed_time(e1) / reps
 
     def gen(lane):
@@ -50,20 +70,23 @@ def child(sms):
     sizes, resizes = [(bench.IMG, bench.IMG)] * B, [(bench.SAM_IMG, bench.SAM_IMG)] * B
     out = {"sms_decode": sms}
     if not sms:
-        out["generate_full_machine_ms"] = timed(lambda: gen(False))
-        out["sam_full_machine_ms"] = timed(lambda: model.get_visual_embs(sam))
+        out["generate_full_machine_ms"] = timed(lambda: gen(False), tag="generate_full")
+        out["sam_full_machine_ms"] = timed(lambda: model.get_visual_embs(sam), tag="sam_full")
         model.overlap_sam = False
         out["evaluate_ms"] = timed(lambda: model.evaluate(sam, img, ids, sizes, resizes, max_new_tokens=new, temperature=0))
     else:
         out["lanes"] = part.sms
-        out["generate_decode_on_lane_ms"] = timed(lambda: gen(True))
-        out["sam_on_lane_ms"] = timed(sam_lane)
+        out["generate_decode_on_lane_ms"] = timed(lambda: gen(True), tag="generate_lane")
+        out["sam_on_lane_ms"] = timed(sam_lane, tag="sam_lane")
         model.overlap_sms_decode = sms
         out["evaluate_overlapped_ms"] = {}
         for blocks in [int(b) for b in os.environ.get("OVERLAP_BLOCKS", "32").split(",")]:
             model.overlap_sam_blocks = blocks
             out["evaluate_overlapped_ms"][blocks] = round(timed(
-                lambda: model.evaluate(sam, img, ids, sizes, resizes, max_new_tokens=new, temperature=0)), 1)
+                lambda: model.evaluate(sam, img, ids, sizes, resizes, max_new_tokens=new, temperature=0),
+                tag=f"evaluate_overlapped_{blocks}"), 1)
+    if power:
+        out["power"] = power
     print(json.dumps(out), flush=True)
 
 
