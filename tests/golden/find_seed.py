@@ -46,10 +46,11 @@ def coherent(lo, hi):
     for seed in range(lo, hi):
         emb = O.sam_image_encoder(sd, "visual_model.", coherent_image(2, seed=seed), C.TINY_SAM_ENCODER)
         pm, _, _ = O.masks_from_hidden(sd, scfg, ids, ref["last_hidden"], emb, COH_SIZES, COH_RESIZES)
-        stats = [((x > 0).float().mean().item(), (x.abs() < 0.01 * x.abs().max()).float().mean().item())
+        # bf16 activations move a logit by up to ~2 % of the largest |logit|: ask for a 5 % band that is (nearly) empty
+        stats = [((x > 0).float().mean().item(), (x.abs() < 0.05 * x.abs().max()).float().mean().item())
                  for m in pm for x in m]
-        if all(0.05 < p < 0.95 and n < 1e-3 for p, n in stats):
-            print(f"image seed {seed}: (positive share, share within 1 % of max |logit|) = "
+        if all(0.05 < p < 0.95 and n < 2e-4 for p, n in stats):
+            print(f"image seed {seed}: (positive share, share within 5 % of max |logit|) = "
                   f"{[(round(p, 3), round(n, 5)) for p, n in stats]}")
 
 

@@ -8,7 +8,7 @@
 //   * SAM ViT-H windowed (14x14) and global (64x64) attention with decomposed relative-position bias,
 //     hd 80                                               segment_anything/modeling/image_encoder.py:196-260,355-392
 //
-// One CTA = one 128-row query tile of one (batch, head).  192 threads:
+// One CTA = one 128-row query tile of one (batch, head).  64 + 128 * TPR threads (TPR = 4; 2 for hd 128):
 //   warp 0      TMA producer: Q once, then K/V tiles of 128 keys through a STAGES-deep ring
 //               (cp.async.bulk.tensor.4d over the strided [d, token, head, batch] view, SWIZZLE_128B slabs of
 //               64 columns plus, for hd 80, one SWIZZLE_32B slab of 16 columns);
@@ -17,9 +17,10 @@
 //                 O    += P_j V_j        (TS form: A = P_j in TMEM, B = V smem MN-major, N = hd)
 //               S is double buffered in TMEM (2 x 128 columns) so QK^T of tile j+1 runs under the softmax of tile j;
 //               P_j overwrites the first 64 columns of its own S buffer as packed 16-bit pairs;
-//   warps 2-5   softmax: one thread per query row (no shuffles).  Pass 1 takes the row maximum straight from
-//               TMEM, pass 2 re-reads, exponentiates (one MUFU.EX2 per score), accumulates the row sum and
-//               stores P.  O lives in TMEM for the whole CTA; it is only rescaled when the running maximum grew by
+//   warps 2..   softmax: TPR threads per query row (warps w, w + 4, ... share a TMEM lane quadrant and take 128 / TPR key
+//               columns of every tile each; no shuffles, one named barrier of 32 * TPR threads per tile to exchange the
+//               partial row maximum).  The scores stay in registers between the max pass and the exp pass (one
+//               MUFU.EX2 per score); the row sum is kept as TPR partial sums, P is stored to TMEM.  O lives in TMEM for the whole CTA; it is only rescaled when the running maximum grew by
 //               more than 2^8 ("lazy rescale" - the stale maximum is used consistently for P and the row sum, so the
 //               result is exact), which after the first tiles practically never happens.
 // Rel-pos bias: the prologue runs Q Rh^T and Q Rw^T through the same MMA path into the two S buffers; each softmax
@@ -33,7 +34,16 @@ namespace ullava {
 
 static constexpr int FM_BM = 128;       // query rows per CTA (= TMEM lanes)
 static constexpr int FM_BN = 128;       // keys per tile
-static constexpr int FM_THREADS = 192;
+// Softmax threads per query row: the 128 key columns of a tile are split among TPR threads of TPR different warps that
+// share a TMEM lane quadrant (warps w, w + 4, ...).  Measured on the path's shapes (tools/bench_attn.py, B200): TPR = 2 is
+// 5 - 11 % faster than one thread per row (CLIP 0.174 -> 0.166 ms, LLaMA prefill 0.312 -> 0.291 ms, SAM global 1.66 ->
+// 1.50 ms per 8 images); TPR = 4 is no faster (1.55 ms) -- per tile the kernel is bound by the S -> softmax -> P -> PV
+// latency chain, not by softmax issue slots (profiles/r02_ncu_fmha.md).
+static constexpr int fm_tpr(int hd) { return 2 + 0 * hd; }
+static constexpr int fm_threads(int hd) { return 64 + 128 * fm_tpr(hd); }   // TMA warp, MMA warp, 4 * TPR softmax warps
+// exchange of the partial row maxima (and, at the end, row sums) among the threads of a row: [tile parity][part][row]
+// floats; hd 128 uses one parity and a second barrier per tile
+static constexpr int fm_xch_floats(int hd) { return (hd == 128 ? 1 : 2) * fm_tpr(hd) * FM_BM; }
 static constexpr int FM_TMEM_COLS = 512;
 static constexpr int FM_COL_S = 0;      // S buffers: columns [0,128) and [128,256)
 static constexpr int FM_COL_O = 256;    // O accumulator: columns [256, 256 + hd)
@@ -63,7 +73,7 @@ struct FmhaCfg {
   static constexpr int BAR_BYTES = (1 + 3 * STAGES + 2 + 2 + 1 + 1 + 1) * 8 + 16;
   static_assert(TAIL == 0 || TAIL == 16, "head_dim must be 64, 80 or 128");
   static constexpr int smem_bytes(int table_floats) {
-    return 1024 + TILE * (1 + 2 * STAGES) + table_floats * 4 + BAR_BYTES;
+    return 1024 + TILE * (1 + 2 * STAGES) + (table_floats + fm_xch_floats(HD)) * 4 + BAR_BYTES;
   }
 };
 
@@ -106,9 +116,11 @@ __device__ __forceinline__ void fmha_issue_pv(uint32_t o_tmem, uint32_t p_tmem, 
 
 // Lazy rescale of O (TMEM) and the running row sum when the row maximum of tile j (`mx`, log2 units) exceeds the
 // maximum in use by more than the threshold.  Warp-uniform control flow around the TMEM accesses.
-template <int HD>
+// The TPR threads of a row take the same decision (same mx, same history); thread `part` rescales the O chunks c with
+// c % TPR == part.
+template <int HD, int TPR>
 __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, float& l_run, uint32_t o_taddr,
-                                             uint64_t* pv_done) {
+                                             uint64_t* pv_done, int part) {
   bool grow;
   float alpha = 1.f;
   if (j == 0) {
@@ -127,19 +139,21 @@ __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, flo
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < HD / 16; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x16(o_taddr + c * 16, r);
-      tmem_ld_wait();
+      if (c % TPR == part) {
+        uint32_t r[16];
+        tmem_ld_32x16(o_taddr + c * 16, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-      tmem_st_32x16(o_taddr + c * 16, r);
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+        tmem_st_32x16(o_taddr + c * 16, r);
+      }
     }
   }
 }
 
 // RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
 template <typename T, int HD, int RP>
-__global__ void __launch_bounds__(FM_THREADS, 1)
+__global__ void __launch_bounds__(fm_threads(HD), 1)
 fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   using C = FmhaCfg<HD>;
   constexpr int ST = C::STAGES;
@@ -150,7 +164,12 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   const int S = RP ? p.S : 0;
   const int pstride = 2 * S + 1;  // odd: the 32 rows of a warp hit 32 different banks
   float* tabs = reinterpret_cast<float*>(smem + C::TILE * (1 + 2 * ST));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tabs) + (RP ? FM_BM * pstride * 4 : 0));
+  float* xch = tabs + (RP ? FM_BM * pstride : 0);
+  constexpr int TPR = 2;                                    // == fm_tpr(HD)
+  constexpr int CPT = FM_BN / TPR;                          // key columns per softmax thread and tile
+  constexpr int kXchFloats = (HD == 128 ? 1 : 2) * TPR * FM_BM;   // == fm_xch_floats(HD)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kXchFloats);
+  constexpr bool kXchDouble = HD != 128;
   bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
   uint64_t* q_full = bars;
   uint64_t* k_full = q_full + 1;
@@ -174,7 +193,6 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   if (p.causal) k_end = min(k_end, p.q_pos0 + m0 + FM_BM);
   const int n_tiles = (k_end + FM_BN - 1) / FM_BN;
   constexpr int kRP = RP ? 1 : 0;
-  constexpr int kChunkUnroll = (RP == 1) ? 1 : 4;  // the generic-grid bias path keeps one 32-column chunk live
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -188,10 +206,10 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 128 * TPR);
     }
     mbar_init(pv_done, 1);
-    mbar_init(pro_done, 128);
+    mbar_init(pro_done, 128 * TPR);
     mbar_init(o_final, 1);
     fence_mbar_init();
   }
@@ -284,7 +302,16 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       umma_commit<1>(o_final);
     }
   } else {
-    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    // ===================== softmax / correction / epilogue: TPR threads per query row =====================
+    // Softmax warp sw = warp - 2 takes the key columns [CPT * part, CPT * (part + 1)) of every tile, part = sw / 4, for
+    // the 32 rows of TMEM lane quadrant warp % 4 (a warp may only touch that quadrant; warps w, w + 4, ... share it).
+    // With one warp per SM sub-partition the softmax was latency-bound (XU pipe 39 %, tensor pipe 16 - 25 % in the
+    // round-1 captures); TPR warps per sub-partition hide each other's TMEM loads and MUFU latency.  The threads of a
+    // row exchange their partial row maximum through shared memory (one named barrier of 32 * TPR threads per tile),
+    // keep partial row sums that are added once at the end, and split the O columns for the lazy rescale and the final
+    // store.  The scores stay in registers between the max pass and the exp pass, so P (which overwrites the first 64
+    // columns of the S buffer) is only written after ALL threads of the row have read their scores (the barrier).
+    const int part = (warp - 2) >> 2;            // which CPT-column part of the tile
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;            // row inside the tile
     const int qrow = m0 + row;
@@ -293,7 +320,9 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     const float sl2 = p.scale_log2;
     float* Ah = tabs + row * pstride;
     float* Aw = Ah + S;
-    float aw[RP == 2 ? 64 : 1];
+    float aw[RP == 2 ? CPT : 1];
+    constexpr int kOChunks = HD / 16;            // O columns in chunks of 16: chunk c belongs to part c % TPR
+#define FMHA_ROW_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * TPR) : "memory")
 
     if constexpr (RP != 0) {
       constexpr float kLog2e = 1.4426950408889634f;
@@ -302,13 +331,14 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       mbar_wait(&s_full[0], 0);
       mbar_wait(&s_full[1], 0);
       tc_fence_after();
-#pragma unroll 1
-      for (int tb = 0; tb < 2; ++tb) {
+      {
+        // parts [0, TPR/2) turn Q Rh^T into A_h, parts [TPR/2, TPR) turn Q Rw^T into A_w (32-column chunks interleaved)
+        const int tb = part / (TPR / 2), sub_part = part % (TPR / 2);
         const uint32_t ts = tmem_base + lane_off + FM_COL_S + tb * FM_BN;
         float* dst = tb ? Aw : Ah;
         const int base = (tb ? qw : qh) + S - 1;   // table column r  ->  index base - r
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = sub_part; c < 4; c += TPR / 2) {
           if (c * 32 >= 2 * S - 1) break;
           uint32_t r[32];
           tmem_ld_32x32(ts + c * 32, r);
@@ -322,9 +352,10 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       }
       tc_fence_before();
       mbar_arrive(pro_done);
+      FMHA_ROW_SYNC();                           // both tables of the row are complete
       if constexpr (RP == 2) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) aw[i] = Aw[i];
+        for (int i = 0; i < CPT; ++i) aw[i] = Aw[(CPT * part) % 64 + i];   // S == 64: my columns are kw0 .. kw0 + CPT - 1
       }
     }
 
@@ -332,179 +363,116 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     for (int j = 0; j < n_tiles; ++j) {
       const int buf = j & 1;
       const uint32_t ts = tmem_base + lane_off + FM_COL_S + buf * FM_BN;
-      const int key0 = j * FM_BN;
-      const bool need_mask = (key0 + FM_BN > p.seq_k) || (p.causal && (key0 + FM_BN - 1 > p.q_pos0 + m0));
+      const int key0 = j * FM_BN + CPT * part;   // first key of this thread's part
+      const bool need_mask = (j * FM_BN + FM_BN > p.seq_k) || (p.causal && (j * FM_BN + FM_BN - 1 > p.q_pos0 + m0));
       mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) + kRP) & 1u);
       tc_fence_after();
+      uint32_t r[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT / 32; ++c)
+        tmem_ld_32x32(ts + CPT * part + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * c]));
+      tmem_ld_wait();
+      float ah = 0.f;
+      if constexpr (RP == 2) ah = Ah[min(2 * j + (CPT * part) / 64, S - 1)];   // S == 64: my part lies in one grid row
+      const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
+      int kh0 = 0, kw0 = 0;
+      if constexpr (RP == 1) {
+        kh0 = key0 / S;
+        kw0 = key0 - kh0 * S;
+      }
 
-      if (RP == 0 && !need_mask) {
-        // ---- fast path, no bias: the 128 raw scores stay in registers between the two passes ----
-        uint32_t r[128];
-        tmem_ld_32x32(ts, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld_32x32(ts + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_32x32(ts + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
-        tmem_ld_32x32(ts + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
-        tmem_ld_wait();
+      // ---- pass 1: my scores in log2 units (in place, bias and mask applied; the per-thread constant ah of the
+      //      64 x 64 grid is added later) and their maximum.  Without bias or mask the raw scores stay as they are
+      //      and the scale is folded into pass 2. ----
+      const bool raw_scores = (RP == 0) && !need_mask;
+      float mx;
+      {
         float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (raw_scores) {
 #pragma unroll
-        for (int i = 0; i < 128; i += 8) {
+          for (int i = 0; i < CPT; i += 2)
+            mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+        } else if (RP == 2 && !need_mask) {
+          const uint64_t sl2v = pk2(sl2, sl2);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            mxa[e] = fmaxf(mxa[e], fmaxf(__uint_as_float(r[i + 2 * e]), __uint_as_float(r[i + 2 * e + 1])));
-        }
-        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;  // scale > 0
-        fmha_rescale<HD>(j, mx, m_used, l_run, o_taddr, pv_done);
-        const uint64_t sl2v = pk2(sl2, sl2), nm = pk2(-m_used, -m_used);
-        uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint64_t x = ffma2(pk2(__uint_as_float(r[c * 32 + i]), __uint_as_float(r[c * 32 + i + 1])), sl2v, nm);
+          for (int i = 0; i < CPT; i += 2) {
+            const uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v, pk2(aw[i], aw[i + 1]));
             float x0, x1;
             upk2(x, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
-            pk[i >> 1] = pack2<T>(p0, p1);
+            r[i] = __float_as_uint(x0);
+            r[i + 1] = __float_as_uint(x1);
+            mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(x0, x1));
           }
-          tmem_st_32x16(ts + c * 16, pk);
+        } else {
+          int kh = kh0, kw = kw0;
+#pragma unroll   // fully: r[] must be indexed with compile-time constants to stay in registers
+          for (int i = 0; i < CPT; ++i) {
+            float x;
+            if constexpr (RP == 0) x = __uint_as_float(r[i]) * sl2;
+            else if constexpr (RP == 2) x = fmaf(__uint_as_float(r[i]), sl2, aw[i]);
+            else x = fmaf(__uint_as_float(r[i]), sl2, Ah[min(kh, S - 1)] + Aw[kw]);
+            if (key0 + i >= key_lim) x = -INFINITY;
+            r[i] = __float_as_uint(x);
+            mxa[i & 3] = fmaxf(mxa[i & 3], x);
+            if constexpr (RP == 1) {
+              if (++kw == S) { kw = 0; ++kh; }
+            }
+          }
         }
-        float s0, s1, s2, s3;
-        upk2(sum[0], s0, s1);
-        upk2(sum[1], s2, s3);
-        l_run += (s0 + s1) + (s2 + s3);
-      } else if (RP == 2 && !need_mask) {
-        // ---- fast path, 64 x 64 grid: this tile is grid rows 2j and 2j+1; A_w (registers) is the same for both ----
-        const float ah0 = Ah[2 * j], ah1 = Ah[2 * j + 1];
+        mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        mx = raw_scores ? mx * sl2 : mx + ah;   // scale > 0; ah == 0 unless RP == 2
+      }
+      // ---- the row maximum of the whole tile: exchange with the threads that hold the other columns ----
+      const int xs = kXchDouble ? buf * TPR : 0;
+      xch[(xs + part) * FM_BM + row] = mx;
+      FMHA_ROW_SYNC();
+#pragma unroll
+      for (int q2 = 0; q2 < TPR; ++q2) mx = fmaxf(mx, xch[(xs + q2) * FM_BM + row]);
+      if constexpr (!kXchDouble) FMHA_ROW_SYNC();   // single slot: read before the next tile's write
+      fmha_rescale<HD, TPR>(j, mx, m_used, l_run, o_taddr, pv_done, part);
+
+      // ---- pass 2: p = 2^(x - m), partial row sum, P -> TMEM (packed pairs: words [CPT/2 * part, +CPT/2) of the S buffer) ----
+      {
         const uint64_t sl2v = pk2(sl2, sl2);
-        float mxh[2];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            uint32_t r[32];
-            tmem_ld_32x32(ts + hh * 64 + c2 * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int kw = (RP == 2) ? c2 * 32 + i : 0;
-              const uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v, pk2(aw[kw], aw[kw + (RP == 2)]));
-              float x0, x1;
-              upk2(x, x0, x1);
-              mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(x0, x1));
-            }
-          }
-          mxh[hh] = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-        }
-        const float mx = fmaxf(mxh[0] + ah0, mxh[1] + ah1);
-        fmha_rescale<HD>(j, mx, m_used, l_run, o_taddr, pv_done);
+        const float off = ah - m_used;
+        const uint64_t offv = pk2(off, off);
         uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float off = ((c >> 1) ? ah1 : ah0) - m_used;
-          const uint64_t offv = pk2(off, off);
-          uint32_t r[32];
-          tmem_ld_32x32(ts + c * 32, r);
-          tmem_ld_wait();
+        for (int c = 0; c < CPT / 32; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const int kw = (RP == 2) ? (c & 1) * 32 + i : 0;
-            uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v, pk2(aw[kw], aw[kw + (RP == 2)]));
-            x = fadd2(x, offv);
+            const int e = c * 32 + i;
+            const uint64_t v2 = pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+            const uint64_t x = raw_scores ? ffma2(v2, sl2v, offv) : fadd2(v2, offv);
             float x0, x1;
             upk2(x, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);   // 2^(-inf) = 0 for masked keys
             sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
             pk[i >> 1] = pack2<T>(p0, p1);
           }
-          tmem_st_32x16(ts + c * 16, pk);
+          tmem_st_32x16(ts + (CPT / 2) * part + c * 16, pk);
         }
         float s0, s1, s2, s3;
         upk2(sum[0], s0, s1);
         upk2(sum[1], s2, s3);
         l_run += (s0 + s1) + (s2 + s3);
-      } else {
-        // ---- generic path: boundary tiles (key / causal mask) and rel-pos bias on an arbitrary grid ----
-        const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
-        float ah0 = 0.f, ah1 = 0.f;
-        if constexpr (RP == 2) {
-          ah0 = Ah[2 * j];
-          ah1 = Ah[2 * j + 1];
-        }
-        int kh0 = 0, kw0 = 0;
-        if constexpr (RP == 1) {
-          kh0 = key0 / S;
-          kw0 = key0 - kh0 * S;
-        }
-        // score of column `col` of this tile in log2 units
-#define FMHA_SCORE(raw, c, i, kh, kw)                                                              \
-        ((RP == 0) ? (raw) * sl2                                                                      \
-         : (RP == 2) ? fmaf((raw), sl2, aw[(RP == 2) ? (((c) & 1) * 32 + (i)) : 0]) + (((c) >> 1) ? ah1 : ah0) \
-                     : fmaf((raw), sl2, Ah[min((kh), S - 1)] + Aw[(kw)]))
-        float mx = -INFINITY;
-        {
-          int kh = kh0, kw = kw0;
-#pragma unroll(kChunkUnroll)
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(ts + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
-              if (key0 + c * 32 + i >= key_lim) x = -INFINITY;
-              mx = fmaxf(mx, x);
-              if constexpr (RP == 1) {
-                if (++kw == S) { kw = 0; ++kh; }
-              }
-            }
-          }
-        }
-        fmha_rescale<HD>(j, mx, m_used, l_run, o_taddr, pv_done);
-        {
-          int kh = kh0, kw = kw0;
-          float sum = 0.f;
-#pragma unroll(kChunkUnroll)
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(ts + c * 32, r);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float x0 = FMHA_SCORE(__uint_as_float(r[i]), c, i, kh, kw);
-              if (key0 + c * 32 + i >= key_lim) x0 = -INFINITY;
-              if constexpr (RP == 1) {
-                if (++kw == S) { kw = 0; ++kh; }
-              }
-              float x1 = FMHA_SCORE(__uint_as_float(r[i + 1]), c, i + 1, kh, kw);
-              if (key0 + c * 32 + i + 1 >= key_lim) x1 = -INFINITY;
-              if constexpr (RP == 1) {
-                if (++kw == S) { kw = 0; ++kh; }
-              }
-              const float p0 = ex2_approx(x0 - m_used);
-              const float p1 = ex2_approx(x1 - m_used);
-              sum += p0 + p1;
-              pk[i >> 1] = pack2<T>(p0, p1);
-            }
-            tmem_st_32x16(ts + c * 16, pk);
-          }
-          l_run += sum;
-        }
-#undef FMHA_SCORE
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
     }
 
-    // ---- epilogue: O / l -> global ----
+    // ---- epilogue: O / l -> global; the row sum is the sum of the threads' partial sums ----
+    const int ls = kXchDouble ? (n_tiles & 1) * TPR : 0;   // the parity the last tile did not use (its reads may be in flight)
+    xch[(ls + part) * FM_BM + row] = l_run;
+    FMHA_ROW_SYNC();
+    float l_tot = 0.f;
+#pragma unroll
+    for (int q2 = 0; q2 < TPR; ++q2) l_tot += xch[(ls + q2) * FM_BM + row];
     mbar_wait(o_final, 0);
     tc_fence_after();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
     T* orow = nullptr;
     if (qrow < p.seq_q) {
       if (p.o_row_map) {
@@ -515,24 +483,27 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       }
     }
 #pragma unroll
-    for (int c = 0; c < HD / 16; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x16(o_taddr + c * 16, r);
-      tmem_ld_wait();
-      if (orow) {
-        uint4 w0, w1;
-        w0.x = pack2<T>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-        w0.y = pack2<T>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-        w0.z = pack2<T>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-        w0.w = pack2<T>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-        w1.x = pack2<T>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
-        w1.y = pack2<T>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
-        w1.z = pack2<T>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
-        w1.w = pack2<T>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
-        *reinterpret_cast<uint4*>(orow + c * 16) = w0;
-        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = w1;
+    for (int c = 0; c < kOChunks; ++c) {
+      if (c % TPR == part) {                     // warp-uniform
+        uint32_t r[16];
+        tmem_ld_32x16(o_taddr + c * 16, r);
+        tmem_ld_wait();
+        if (orow) {
+          uint4 w0, w1;
+          w0.x = pack2<T>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+          w0.y = pack2<T>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+          w0.z = pack2<T>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+          w0.w = pack2<T>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+          w1.x = pack2<T>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
+          w1.y = pack2<T>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
+          w1.z = pack2<T>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
+          w1.w = pack2<T>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 16) = w0;
+          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = w1;
+        }
       }
     }
+#undef FMHA_ROW_SYNC
   }
 
   tc_fence_before();
@@ -568,7 +539,7 @@ static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int
   static SmemOptIn opt_in;   // per device (common.cuh)
   { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
   dim3 grid((p.seq_q + FM_BM - 1) / FM_BM, heads, batch);
-  kern<<<grid, FM_THREADS, smem, stream>>>(maps, p);
+  kern<<<grid, fm_threads(HD), smem, stream>>>(maps, p);
   return check_cuda(cudaGetLastError(), "fmha_tcgen05 launch");
 }
 
