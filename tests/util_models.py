@@ -124,7 +124,7 @@ class PeftModelStub(torch.nn.Module):
 
 def inject_lora(llama_model, targets=("q_proj", "v_proj"), r=4, alpha=8.0):
     """Wraps the target projections of every decoder layer in LoraLinearStub (train_ullava.py:42 default targets);
-    returns {state_dict key of the base weight: delta} for the oracle."""
+    returns {state_dict key of the base weight: the stub} (stub.delta() = scaling * B @ A of its current weights)."""
     deltas = {}
     for i, lay in enumerate(llama_model.layers):
         for t in targets:
@@ -132,7 +132,7 @@ def inject_lora(llama_model, targets=("q_proj", "v_proj"), r=4, alpha=8.0):
             stub = LoraLinearStub(getattr(parent, t), r, alpha, f"lora.{i}.{t}")
             setattr(parent, t, stub)
             sub = "self_attn" if parent is lay.self_attn else "mlp"
-            deltas[f"model.layers.{i}.{sub}.{t}.weight"] = stub.delta()
+            deltas[f"model.layers.{i}.{sub}.{t}.weight"] = stub
     return deltas
 
 

@@ -50,6 +50,7 @@ struct GemmKernelParams {
   int kb_per_split;   // k-blocks handled by one split
   int splits;         // >1: D is an fp32 workspace [splits][M][N], epilogue deferred
   int group_m;        // rasterisation group: M tiles swept together over N (their A panel stays L2 resident)
+  uint64_t hint_a, hint_b;  // L2 eviction priority of the A / B tile loads (CTA-pair kernel)
 };
 
 template <int BN, int STAGES>
@@ -462,8 +463,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, row_a);
-          tma_load_2d_2sm(sa + S::kABytes, &tmB, &full_bar[stage], kb * BK, row_b);
+          tma_load_2d_2sm_hint(sa, &tmA, &full_bar[stage], kb * BK, row_a, p.hint_a);
+          tma_load_2d_2sm_hint(sa + S::kABytes, &tmB, &full_bar[stage], kb * BK, row_b, p.hint_b);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -744,6 +745,20 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
     p.group_m = g;
   }
   if (ctx->group_m > 0) p.group_m = ctx->group_m;
+  // L2 eviction priorities (CTA-pair kernel).  Whichever operand is re-used ACROSS waves should survive the stream of
+  // the other one: a B that fits in L2 beside a wave's working set (<= ~96 MB) while A is the big streamed operand
+  // (LLaMA down: A 428 MB, B 90 MB) is loaded evict_last / A evict_first; when B is too large and the raster keeps a
+  // tall A panel resident instead (qkv, gate/up), the panel is evict_last and B streams evict_first.
+  // MEASURED (ncu dram__bytes_read, tools/gemm_traffic.py, round 2): the hints make it worse -- qkv 1.04 -> 2.68 GB,
+  // gate/up 2.0 -> 5.1 GB, down 2.7 -> 4.0 GB read, 3-6 % slower: evict_first also throws out the tiles that the OTHER
+  // CTAs of the same wave are about to re-read (the within-wave reuse is what keeps the traffic at 2-4x the operands).
+  // Off by default; kept as an experiment switch.
+  p.hint_a = p.hint_b = kEvictNormal;
+  if (ctx->gemm_hints) {
+    const double a_bytes = 2.0 * a.M * a.K, b_bytes = 2.0 * a.N * a.K;
+    if (b_bytes <= 96e6 && a_bytes > 1.5 * b_bytes && b_bytes > 16e6) { p.hint_a = kEvictFirst; p.hint_b = kEvictLast; }
+    else if (b_bytes >= 48e6) { p.hint_a = kEvictLast; p.hint_b = kEvictFirst; }
+  }
   p.epilogue = a.epilogue;
   p.out_f32 = a.out_f32;
   p.bias = a.bias;

@@ -31,6 +31,8 @@ struct ullava_ctx {
   int64_t next_ldb = 0;
   int prefetch_units = 12;  // 16 KB tiles per SM pulled into L2 (0 = off); ULLAVA_PREFETCH_UNITS overrides at create
   int gemm_pair = 1;  // large-M GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles); ULLAVA_GEMM_PAIR=0 turns it off
+  int gemm_hints = 0; // L2 eviction-priority hints on the large-M GEMM operand loads (ULLAVA_GEMM_HINTS=1): measured
+                      // counter-productive on B200, see gemm_sm100.cu
   int group_m = 0;    // 0 = default rasterisation group of the large-M GEMM; ULLAVA_GROUP_M overrides at create (tuning)
   void* chain_trace = nullptr;  // debug: globaltimer stamps of the next chain kernels (ullava_debug_chain_trace)
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled

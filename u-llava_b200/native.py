@@ -745,6 +745,16 @@ class Partition:
         self.ctx[1].set_sm_limit(self.sms[1])
 
     @classmethod
+    def current(cls, device):
+        """The partition already created on `device` (there is at most one), or None."""
+        if isinstance(device, torch.device):
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        for (d, _), q in cls._by_key.items():
+            if d == device:
+                return q
+        return None
+
+    @classmethod
     def get(cls, device, sms_a: int) -> "Partition":
         if isinstance(device, torch.device):
             device = device.index if device.index is not None else torch.cuda.current_device()
