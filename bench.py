@@ -470,8 +470,8 @@ def run_b200(args):
     ctx = native.Context.get(local)
     model = build_model(dev, dtype)
     model.pack_mask_bits = True
-    if args.no_overlap:
-        model.overlap_sam = False
+    if args.no_overlap or args.profile_mode:
+        model.overlap_sam = False     # (ncu cannot attach to kernels launched into green-context streams)
     if args.overlap_sms:
         model.overlap_sms_decode = args.overlap_sms
     if args.overlap_blocks:

@@ -588,3 +588,30 @@ def test_coherent_masks_iou_0999_vs_reference(ctx, dtype):
             assert inter / union >= 0.999, (i, k, inter / union, int((got[k] != ref[k]).sum()))
             n_masks += 1
     assert n_masks == 3
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_dense_pe_against_the_reference_evaluated_in_the_buffer_dtype(ctx, dtype):
+    """PositionEmbeddingRandom (segment_anything/modeling/prompt_encoder.py:203-229) is evaluated by the reference in the
+    dtype of its Gaussian-matrix buffer, i.e. in 16 bits after `.to(dtype)`: coords @ G, 2 pi x, sin / cos each round to
+    8 (bf16) or 11 (fp16) mantissa bits, and the angle reaches +-10 rad.  This build evaluates the same expression in fp32
+    on the 16-bit-stored matrix and rounds ONCE.  Both against the fp32 truth: ours is within one rounding of it, the
+    reference's own 16-bit evaluation is not better, and the two agree within the reference's own error."""
+    from models.segment_anything.build_sam import _build_sam
+    sam = _build_sam(64, 1, 2, [0])
+    shapes = {k: tuple(v.shape) for k, v in sam.state_dict().items()}
+    sd = synth_state_dict(shapes, 1)
+    sam.load_state_dict(sd, strict=True)
+    sam = sam.cuda().to(dtype)
+    gkey = "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"
+    g16 = sd[gkey].to(dtype)
+    truth = O.sam_dense_pe({gkey: g16.float()}, "")                      # fp32 arithmetic on the stored matrix
+    ref16 = O.sam_dense_pe({gkey: g16.cuda()}, "").float().cpu()          # the reference's ops in the buffer dtype
+    ours = sam.prompt_encoder.get_dense_pe().float().cpu()
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    err_ours = (ours - truth).abs().max().item()
+    err_ref = (ref16 - truth).abs().max().item()
+    print(f"dense PE vs fp32 truth ({dtype}): this build {err_ours:.5f}, reference arithmetic in the buffer dtype {err_ref:.5f}")
+    assert err_ours <= ulp                                                # |sin|, |cos| <= 1: one rounding
+    assert err_ours <= err_ref + 1e-7
+    assert (ours - ref16).abs().max().item() <= err_ref + ulp

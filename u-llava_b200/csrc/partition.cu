@@ -79,6 +79,12 @@ int ullava_partition_create(int device, int sms_a, int priority_a, int priority_
     set_last_error("SM partition: the driver does not export the green-context API (needs CUDA >= 12.4)");
     return ERR_UNSUPPORTED;
   }
+  int prev_device = -1;
+  ULLAVA_CHECK_CUDA(cudaGetDevice(&prev_device));
+  struct Restore {   // the caller's current device is not ours to change
+    int dev;
+    ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+  } restore{prev_device != device ? prev_device : -1};
   ULLAVA_CHECK_CUDA(cudaSetDevice(device));
   ULLAVA_CHECK_CUDA(cudaFree(nullptr));  // primary context up before the green contexts retain it
   CUdevice dev;
