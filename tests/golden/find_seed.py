@@ -10,7 +10,7 @@ which EVERY compared greedy decision has a margin above the threshold:
 
     python tests/golden/find_seed.py core 0 16000     # ~0.1 s per seed; seed 14400 -> 0.163
     python tests/golden/find_seed.py full 0 400       # seed 332 -> 0.252
-    python tests/golden/find_seed.py coherent 0 200   # image seed of the coherent-mask fixture (oracle/synth.py): 96
+    python tests/golden/find_seed.py coherent 0 2500  # CLIP-image seed of the coherent-mask fixture (oracle/synth.py): 2105
 The goldens themselves are then written by make_golden.py from the REAL reference with those seeds.
 """
 import os
@@ -35,23 +35,25 @@ COH_RESIZES = [(1024, 1024), (731, 1024)]
 
 
 def coherent(lo, hi):
-    """image seeds for which all three masks of the tiny_full prompts are non-trivial and sharp"""
-    from oracle.synth import coherent_image, coherent_overrides
+    """CLIP-image seeds (the SAM image stays at COHERENT_SEED, so its embedding is computed once) for which all three
+    masks of the tiny_full prompts are two-signed and only their interpolated boundary lies near the threshold: a 16-bit
+    evaluation moves a logit by ~1 % of the largest |logit|; a sharp two-level mask of this size has ~3e-4 of its
+    pixels within 3 % of it (the boundary), a mask with a whole class of near-zero pixels has 1e-2."""
+    from oracle.synth import COHERENT_SEED, coherent_image, coherent_overrides
     meta = load_golden("tiny_full")[1]
     cfg = core_cfg()
     sd = coherent_overrides(synth_state_dict(meta["shapes"], meta["seed"]))
     ids = C.tiny_prompt(2, seg_loc=True)
-    ref = O.core_forward(sd, cfg, ids, synth_normal("images", (2, 3, 28, 28)), prefix="llm.")
+    emb = O.sam_image_encoder(sd, "visual_model.", coherent_image(2, seed=COHERENT_SEED), C.TINY_SAM_ENCODER)
     scfg = dict(seg_token_idx=C.SEG_ID, loc_token_idx=C.LOC_ID)
     for seed in range(lo, hi):
-        emb = O.sam_image_encoder(sd, "visual_model.", coherent_image(2, seed=seed), C.TINY_SAM_ENCODER)
+        ref = O.core_forward(sd, cfg, ids, synth_normal("images", (2, 3, 28, 28), seed=seed), prefix="llm.")
         pm, _, _ = O.masks_from_hidden(sd, scfg, ids, ref["last_hidden"], emb, COH_SIZES, COH_RESIZES)
-        # bf16 activations move a logit by up to ~2 % of the largest |logit|: ask for a 5 % band that is (nearly) empty
-        stats = [((x > 0).float().mean().item(), (x.abs() < 0.05 * x.abs().max()).float().mean().item())
+        stats = [((x > 0).float().mean().item(), (x.abs() < 0.03 * x.abs().max()).float().mean().item())
                  for m in pm for x in m]
-        if all(0.05 < p < 0.95 and n < 2e-4 for p, n in stats):
-            print(f"image seed {seed}: (positive share, share within 5 % of max |logit|) = "
-                  f"{[(round(p, 3), round(n, 5)) for p, n in stats]}")
+        if all(0.03 < p < 0.97 and n < 6e-4 for p, n in stats):
+            print(f"CLIP-image seed {seed}: (positive share, share within 3 % of max |logit|) = "
+                  f"{[(round(p, 3), round(n, 5)) for p, n in stats]}", flush=True)
 
 
 def main():

@@ -129,7 +129,7 @@ def tiny_full():
 def tiny_full_coherent():
     """The tiny_full model with the coherent-mask overrides (oracle/synth.py) on a piecewise-constant SAM image: the REAL
     reference's forward(inference=True) masks at 336 x 336 / 300 x 420, for the IoU >= 0.999 gate."""
-    from oracle.synth import coherent_image, coherent_overrides
+    from oracle.synth import coherent_clip_images, coherent_image, coherent_overrides
     llm = dict(C.TINY_LLM)
     cfg = ref_models.UllavaConfig(llm_config=llm, seg_token_idx=C.SEG_ID, loc_token_idx=C.LOC_ID)
     cfg.llm_config._attn_implementation = "eager"
@@ -143,7 +143,7 @@ def tiny_full_coherent():
     m.load_state_dict(coherent_overrides(synth_state_dict(shapes, SEED_TINY_FULL)), strict=True)
     B = 2
     ids = C.tiny_prompt(B, seg_loc=True)
-    images = synth_normal("images", (B, 3, 28, 28))
+    images = coherent_clip_images(B)
     images_sam = coherent_image(B)
     sizes = [(336, 336), (300, 420)]
     resizes = [(1024, 1024), (731, 1024)]

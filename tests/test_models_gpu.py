@@ -565,10 +565,11 @@ def test_coherent_masks_iou_0999_vs_reference(ctx, dtype):
     up-scaling sub-kernels, everything else seeded random -- the thresholded masks of forward(inference=True) are
     compared with the REAL reference's (golden bits) at 336 x 336 / 300 x 420: IoU >= 0.999 for every mask, in fp16
     and in bf16 (the bench dtype), and every mask is two-signed (19 - 27 % foreground)."""
-    from oracle.synth import coherent_image
+    from oracle.synth import coherent_clip_images, coherent_image
     g, meta = load_golden("tiny_full_coherent")
     m, sd, cfg = build_tiny_full(dtype, coherent=True)
-    ids, images, _, _, _ = oracle_inputs_full()
+    ids, _, _, _, _ = oracle_inputs_full()
+    images = coherent_clip_images(2)
     sizes, resizes = [tuple(s) for s in meta["sizes"]], [tuple(s) for s in meta["resizes"]]
     images_sam = coherent_image(2)
     out = m(images_sam=images_sam.cuda().to(dtype), images=images.cuda().to(dtype), input_ids=ids.cuda(), labels=None,
@@ -585,6 +586,8 @@ def test_coherent_masks_iou_0999_vs_reference(ctx, dtype):
             inter, union = (got[k] & ref[k]).sum(), (got[k] | ref[k]).sum()
             share = ref[k].mean()
             assert 0.05 < share < 0.95
+            print(f"coherent mask ({i}, {k}) {dtype}: IoU {inter / union:.5f} ({int((got[k] != ref[k]).sum())} of {got[k].size} "
+                  f"pixels differ, foreground {share:.3f})")
             assert inter / union >= 0.999, (i, k, inter / union, int((got[k] != ref[k]).sum()))
             n_masks += 1
     assert n_masks == 3

@@ -92,8 +92,8 @@ class LoraLinearStub(torch.nn.Linear):
         self.r, self.scaling = {adapter: r}, {adapter: alpha / r}
         self.active_adapter, self.merged, self.disable_adapters, self.fan_in_fan_out = adapter, False, False, False
         with torch.no_grad():
-            self.lora_A[adapter].weight.copy_(synth_normal(key + ".A", (r, base.in_features), scale=0.3))
-            self.lora_B[adapter].weight.copy_(synth_normal(key + ".B", (base.out_features, r), scale=0.3))
+            self.lora_A[adapter].weight.copy_(synth_normal(key + ".A", (r, base.in_features), scale=0.12))
+            self.lora_B[adapter].weight.copy_(synth_normal(key + ".B", (base.out_features, r), scale=0.12))
 
     def delta(self) -> torch.Tensor:
         a = self.active_adapter
