@@ -51,6 +51,25 @@ def main():
             fn = lambda: ctx.attention_relpos(q, k, v, rh, rw, G, out=out)
         else:
             fn = lambda: ctx.attention(q, k, v, causal=causal, out=out)
+        if os.environ.get("TRACE"):
+            # per-tile timeline of CTA (0, 0, 0): cycles relative to the first stamp
+            ctx.set_attention_impl(2)
+            fn()
+            buf = torch.zeros((64, 32), dtype=torch.int64, device="cuda")
+            ctx.lib.ullava_debug_fmha_trace(ctx.handle, buf.data_ptr())
+            fn()
+            torch.cuda.synchronize()
+            ctx.lib.ullava_debug_fmha_trace(ctx.handle, None)
+            t = buf.cpu().numpy()
+            t0 = t[t > 0].min()
+            names = ["KV issued", "K landed", "QK issued", "V landed", "P landed", "S landed", "max done", "P arrived",
+                     "rescaled", "P chunk 0", "P chunk 1", "st waited", "S loaded", "local max"]
+            print(name, "tile: " + ", ".join(names))
+            for j in range(min(12, (S + 127) // 128)):
+                print(j, [int(v - t0) if v > 0 else None for v in t[j][:14]])
+                print("   P arrived, warps 2..9:", [int(v - t0) for v in t[j][16:24]], " max done:", [int(v - t0) for v in t[j][24:32]])
+            ctx.set_attention_impl(0)
+            continue
         for impl in (2, 1):
             ctx.set_attention_impl(impl)
             ms = timeit(fn)

@@ -189,6 +189,12 @@ int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_args* args, vo
   return llama_decode_step_run(ctx, *args, static_cast<cudaStream_t>(stream));
 }
 
+int ullava_debug_fmha_trace(ullava_ctx* ctx, void* buf) {
+  CTX_CHECK("ullava_debug_fmha_trace");
+  ctx->fmha_trace = buf;
+  return OK;
+}
+
 int ullava_debug_chain_trace(ullava_ctx* ctx, void* buf) {
   CTX_CHECK("ullava_debug_chain_trace");
   ctx->chain_trace = buf;

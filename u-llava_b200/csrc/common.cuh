@@ -399,6 +399,43 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   return d;
 }
 
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for two values on the FMA / ALU pipes instead of the MUFU (16 ex2 / clk / SM on B200 -- the pipe that bounds an
+// attention tile: 128 x 128 exponentials = 1024 cycles against 512 cycles of tcgen05 work at head_dim 64).
+// x = n + f, n = floor(x) from a round-down add of 1.5 * 2^23 (n lands in the low mantissa bits), 2^f from a minimax
+// polynomial with p(0) = 1 (degree 3: relative error 8.6e-5, below the rounding of a bf16 P; degree 4: 3.0e-6, below
+// fp16's), times the exact power of two (n + 127) << 23.  x <= -127 (masked keys are -inf) gives exactly 0; x up to
+// +127 is fine (the lazy rescale keeps x <= 8).
+template <int DEG>
+__device__ __forceinline__ uint64_t ex2_fma2(float x0, float x1) {
+  static_assert(DEG == 3 || DEG == 4, "ex2_fma2: degree 3 or 4");
+  const uint64_t x = pk2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+  const uint64_t magic = pk2(12582912.f, 12582912.f);
+  uint64_t r, fl, f;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(magic));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(fl) : "l"(r), "l"(magic));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(fl));
+  uint64_t p;
+  if constexpr (DEG == 3) {
+    p = ffma2(pk2(0.07706641405820847f, 0.07706641405820847f), f, pk2(0.22764568030834198f, 0.22764568030834198f));
+    p = ffma2(p, f, pk2(0.6951166391372681f, 0.6951166391372681f));
+  } else {
+    p = ffma2(pk2(0.013426647521555424f, 0.013426647521555424f), f, pk2(0.05224253237247467f, 0.05224253237247467f));
+    p = ffma2(p, f, pk2(0.2412801831960678f, 0.2412801831960678f));
+    p = ffma2(p, f, pk2(0.6930448412895203f, 0.6930448412895203f));
+  }
+  p = ffma2(p, f, pk2(1.f, 1.f));
+  uint32_t n0, n1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(n0), "=r"(n1) : "l"(r));
+  const uint64_t scale = pk2(__uint_as_float((n0 << 23) + 0x3F800000u), __uint_as_float((n1 << 23) + 0x3F800000u));
+  return fmul2(p, scale);
+}
+
 // ---- fast activations (MUFU based) ------------------------------------------------------------
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;

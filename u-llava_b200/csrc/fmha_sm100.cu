@@ -60,7 +60,13 @@ struct FmhaParams {
   int seq_q, seq_k, causal, q_pos0;
   float scale_log2;
   int S;  // rel-pos grid side (RP != 0)
+  long long* trace;  // debug (ullava_debug_fmha_trace): clock64 stamps of CTA (0, 0, 0), [tile < 64][32], else NULL
 };
+#define FMHA_TRACE(tile, slot)                                                                      \
+  do {                                                                                              \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 64)            \
+      p.trace[(tile) * 32 + (slot)] = clock64();                                                     \
+  } while (0)
 
 template <int HD>
 struct FmhaCfg {
@@ -152,7 +158,8 @@ __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, flo
 }
 
 // RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
-template <typename T, int HD, int RP>
+// EMU: of every 8 pairs of exponentials, EMU are computed on the FMA pipe (ex2_fma2) and 8 - EMU on the MUFU
+template <typename T, int HD, int RP, int EMU>
 __global__ void __launch_bounds__(fm_threads(HD), 1)
 fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   using C = FmhaCfg<HD>;
@@ -221,7 +228,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, C::TILE);
 #pragma unroll
       for (int s = 0; s < C::NS; ++s) tma_load_4d(sQ + s * C::SLAB, &maps.q, q_full, s * 64, m0, h, b);
@@ -244,6 +251,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         const int st = it % ST;
         const uint32_t ph = static_cast<uint32_t>(it / ST) & 1u;
         mbar_wait(&kv_empty[st], ph ^ 1u);
+        FMHA_TRACE(j, 0);
         uint8_t* sk = sKV + st * 2 * C::TILE;
         uint8_t* sv = sk + C::TILE;
         mbar_expect_tx(&k_full[st], C::TILE);
@@ -258,7 +266,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t q_s = smem_u32(sQ);
       const uint32_t kv_s = smem_u32(sKV);
       const uint32_t o_tmem = tmem_base + FM_COL_O;
@@ -285,13 +293,17 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         if (j + 1 < n_tiles) {
           const int it = j + 1 + kRP, st = it % ST;
           mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
+          FMHA_TRACE(j + 1, 1);
           tc_fence_after();
           fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + ((j + 1) & 1) * FM_BN, q_s, kv_s + st * 2 * C::TILE);
           umma_commit<1>(&s_full[(j + 1) & 1]);
+          FMHA_TRACE(j + 1, 2);
         }
         const int it = j + kRP, st = it % ST;
         mbar_wait(&v_full[st], static_cast<uint32_t>(it / ST) & 1u);
+        FMHA_TRACE(j, 3);
         mbar_wait(&p_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);
+        FMHA_TRACE(j, 4);
         tc_fence_after();
         fmha_issue_pv<T, HD>(o_tmem, tmem_base + FM_COL_S + (j & 1) * FM_BN, kv_s + st * 2 * C::TILE + C::TILE, j == 0);
         umma_commit<1>(&kv_empty[st]);
@@ -366,12 +378,14 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       const int key0 = j * FM_BN + CPT * part;   // first key of this thread's part
       const bool need_mask = (j * FM_BN + FM_BN > p.seq_k) || (p.causal && (j * FM_BN + FM_BN - 1 > p.q_pos0 + m0));
       mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) + kRP) & 1u);
+      if (threadIdx.x == 64) FMHA_TRACE(j, 5);
       tc_fence_after();
       uint32_t r[CPT];
 #pragma unroll
       for (int c = 0; c < CPT / 32; ++c)
         tmem_ld_32x32(ts + CPT * part + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * c]));
       tmem_ld_wait();
+      if (threadIdx.x == 64) FMHA_TRACE(j, 12);
       float ah = 0.f;
       if constexpr (RP == 2) ah = Ah[min(2 * j + (CPT * part) / 64, S - 1)];   // S == 64: my part lies in one grid row
       const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
@@ -424,16 +438,23 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       }
       // ---- the row maximum of the whole tile: exchange with the threads that hold the other columns ----
       const int xs = kXchDouble ? buf * TPR : 0;
+      if (threadIdx.x == 64) FMHA_TRACE(j, 13);
       xch[(xs + part) * FM_BM + row] = mx;
       FMHA_ROW_SYNC();
 #pragma unroll
       for (int q2 = 0; q2 < TPR; ++q2) mx = fmaxf(mx, xch[(xs + q2) * FM_BM + row]);
       if constexpr (!kXchDouble) FMHA_ROW_SYNC();   // single slot: read before the next tile's write
+      if (threadIdx.x == 64) FMHA_TRACE(j, 6);
+      if (lane == 0) FMHA_TRACE(j, 24 + warp - 2);
       fmha_rescale<HD, TPR>(j, mx, m_used, l_run, o_taddr, pv_done, part);
+      if (threadIdx.x == 64) FMHA_TRACE(j, 8);
 
       // ---- pass 2: p = 2^(x - m), partial row sum, P -> TMEM (packed pairs: words [CPT/2 * part, +CPT/2) of the S buffer) ----
       {
-        const uint64_t sl2v = pk2(sl2, sl2);
+        // one FFMA2 per pair either way (x * 1 + off is exactly x + off): a select between an FFMA2 and an FADD2 made
+        // the compiler funnel every exponential through the same two temporaries, a serial chain of ~18 cycles a pair
+        const float mul = raw_scores ? sl2 : 1.f;
+        const uint64_t sl2v = pk2(mul, mul);
         const float off = ah - m_used;
         const uint64_t offv = pk2(off, off);
         uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
@@ -444,14 +465,23 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
           for (int i = 0; i < 32; i += 2) {
             const int e = c * 32 + i;
             const uint64_t v2 = pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-            const uint64_t x = raw_scores ? ffma2(v2, sl2v, offv) : fadd2(v2, offv);
+            const uint64_t x = ffma2(v2, sl2v, offv);
             float x0, x1;
             upk2(x, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);   // 2^(-inf) = 0 for masked keys
-            sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
+            float p0, p1;                                           // 2^(-inf) = 0 for masked keys
+            if (((i >> 1) & 7) < EMU) {
+              const uint64_t pe = ex2_fma2<sizeof(T) == 2 && std::is_same<T, __half>::value ? 4 : 3>(x0, x1);
+              upk2(pe, p0, p1);
+              sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pe);
+            } else {
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+              sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
+            }
             pk[i >> 1] = pack2<T>(p0, p1);
           }
           tmem_st_32x16(ts + (CPT / 2) * part + c * 16, pk);
+          if (threadIdx.x == 64) FMHA_TRACE(j, 9 + c);
         }
         float s0, s1, s2, s3;
         upk2(sum[0], s0, s1);
@@ -459,8 +489,11 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         l_run += (s0 + s1) + (s2 + s3);
       }
       tmem_st_wait();
+      if (threadIdx.x == 64) FMHA_TRACE(j, 11);
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
+      if (threadIdx.x == 64) FMHA_TRACE(j, 7);
+      if (lane == 0) FMHA_TRACE(j, 16 + warp - 2);
     }
 
     // ---- epilogue: O / l -> global; the row sum is the sum of the threads' partial sums ----
@@ -531,16 +564,32 @@ static int fmha_map(CUtensorMap* main_map, CUtensorMap* tail_map, const void* ba
   return e;
 }
 
-template <typename T, int HD, int RP>
-static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int heads, cudaStream_t stream) {
+template <typename T, int HD, int RP, int EMU>
+static int fmha_launch_emu(const FmhaMaps& maps, const FmhaParams& p, int batch, int heads, cudaStream_t stream) {
   using C = FmhaCfg<HD>;
   const int smem = C::smem_bytes(RP ? FM_BM * (2 * p.S + 1) : 0);
-  auto kern = fmha_tcgen05_kernel<T, HD, RP>;
+  auto kern = fmha_tcgen05_kernel<T, HD, RP, EMU>;
   static SmemOptIn opt_in;   // per device (common.cuh)
   { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
   dim3 grid((p.seq_q + FM_BM - 1) / FM_BM, heads, batch);
   kern<<<grid, fm_threads(HD), smem, stream>>>(maps, p);
   return check_cuda(cudaGetLastError(), "fmha_tcgen05 launch");
+}
+
+static int g_fmha_emu = -1;   // sweep knob (ULLAVA_FMHA_EMU), -1 = default
+
+template <typename T, int HD, int RP>
+static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int heads, cudaStream_t stream) {
+  if (g_fmha_emu < 0) {
+    const char* e = getenv("ULLAVA_FMHA_EMU");
+    g_fmha_emu = e ? atoi(e) : 3;
+  }
+  switch (g_fmha_emu) {
+    case 2: return fmha_launch_emu<T, HD, RP, 2>(maps, p, batch, heads, stream);
+    case 4: return fmha_launch_emu<T, HD, RP, 4>(maps, p, batch, heads, stream);
+    case 0: return fmha_launch_emu<T, HD, RP, 0>(maps, p, batch, heads, stream);
+    default: return fmha_launch_emu<T, HD, RP, 3>(maps, p, batch, heads, stream);
+  }
 }
 
 bool fmha_supported(const AttnArgs& a, bool relpos, int S) {
@@ -573,6 +622,7 @@ int fmha_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel
   p.seq_q = a.seq_q; p.seq_k = a.seq_k; p.causal = a.causal; p.q_pos0 = a.q_pos0;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.S = S;
+  p.trace = static_cast<long long*>(ctx->fmha_trace);
   int st = ERR_UNSUPPORTED;
 #define ULLAVA_FMHA(TT)                                                                                   \
   if (relpos) {                                                                                            \

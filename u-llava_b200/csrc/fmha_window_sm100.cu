@@ -89,7 +89,7 @@ fmha_window_kernel(const __grid_constant__ FwMaps maps, const FwParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(qk_full, FW_Q_BYTES + FW_SEQ * FW_HD * 2 + 2 * FW_NREL * FW_HD * 2);
       tma_load_4d(sQ, &maps.q, qk_full, 0, m0, h, b);
       tma_load_4d(sQ + 128 * 128, &maps.qt, qk_full, 64, m0, h, b);
@@ -103,7 +103,7 @@ fmha_window_kernel(const __grid_constant__ FwMaps maps, const FwParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV);
       constexpr uint32_t idesc_qk = make_idesc_f16(T16<T>::kUmmaFormat, 128, FW_KROWS);
       constexpr uint32_t idesc_pv = make_idesc_f16(T16<T>::kUmmaFormat, 128, 64) | (1u << 16);

@@ -397,7 +397,7 @@ gemm_chain_kernel(const ChainParams p) {
 
   if (warp == 0) {
     // ===================== W producer: never waits for anything but ring slots =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       // L2 look-ahead: a cursor (ps, pu) over this CTA's units of the WHOLE chain, in load order, kept in front of the
@@ -450,7 +450,7 @@ gemm_chain_kernel(const ChainParams p) {
     }
   } else if (warp == 3) {
     // ===================== X producer: waits for the step's input to be complete grid-wide =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       pdl_wait();  // the chain's first input comes from the previous kernel
@@ -478,7 +478,7 @@ gemm_chain_kernel(const ChainParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

@@ -268,7 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -292,7 +292,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -451,7 +451,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own A rows, own half of B) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
@@ -474,7 +474,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

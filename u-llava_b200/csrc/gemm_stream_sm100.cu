@@ -77,7 +77,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const int pre_end = (hi - lo) < GS_STAGES ? hi : lo + GS_STAGES;
@@ -121,7 +121,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

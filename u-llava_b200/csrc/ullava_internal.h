@@ -34,6 +34,7 @@ struct ullava_ctx {
   int gemm_hints = 0; // L2 eviction-priority hints on the large-M GEMM operand loads (ULLAVA_GEMM_HINTS=1): measured
                       // counter-productive on B200, see gemm_sm100.cu
   int group_m = 0;    // 0 = default rasterisation group of the large-M GEMM; ULLAVA_GROUP_M overrides at create (tuning)
+  void* fmha_trace = nullptr;   // debug: clock64 stamps of CTA (0,0,0) of the next fmha_tcgen05 launches
   void* chain_trace = nullptr;  // debug: globaltimer stamps of the next chain kernels (ullava_debug_chain_trace)
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
   // per-kernel-class CUDA-event profiling (ullava_profile_begin/end); off on the normal path

@@ -132,6 +132,7 @@ _SIGNATURES = {
     "ullava_llama_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "ullava_llama_decode_step": (_i32, [_vp, C.POINTER(DecodeArgs), _vp]),
     "ullava_debug_chain_trace": (_i32, [_vp, _vp]),
+    "ullava_debug_fmha_trace": (_i32, [_vp, _vp]),
     "ullava_llama_chain_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ullava_llama_chain_prepare": (_i32, [_vp, C.POINTER(DecodeArgs)]),
     "ullava_greedy_step": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
