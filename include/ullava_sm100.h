@@ -380,7 +380,7 @@ ULLAVA_API int ullava_llama_decode_step(ullava_ctx* ctx, const ullava_decode_arg
  * stamps [grid][steps][8] (W issued, X ready, first MMA, last MMA, step done, W first, norm begin, norm done) to buf. */
 ULLAVA_API int ullava_debug_chain_trace(ullava_ctx* ctx, void* buf);
 /* Debug aid (tools/bench_attn.py TRACE=1): buf != NULL makes CTA (0, 0, 0) of every fmha_tcgen05 launch write clock64
- * stamps [tile < 64][32] (slot names in tools/bench_attn.py). */
+ * stamps [tile < 64][48] (slot names in tools/bench_attn.py). */
 ULLAVA_API int ullava_debug_fmha_trace(ullava_ctx* ctx, void* buf);
 ULLAVA_API size_t ullava_llama_chain_bytes(int32_t layers, int32_t hidden, int32_t ffn, int32_t vocab);
 ULLAVA_API int ullava_llama_chain_prepare(ullava_ctx* ctx, const ullava_decode_args* args);

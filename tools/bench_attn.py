@@ -55,19 +55,21 @@ def main():
             # per-tile timeline of CTA (0, 0, 0): cycles relative to the first stamp
             ctx.set_attention_impl(2)
             fn()
-            buf = torch.zeros((64, 32), dtype=torch.int64, device="cuda")
+            buf = torch.zeros((64, 48), dtype=torch.int64, device="cuda")
             ctx.lib.ullava_debug_fmha_trace(ctx.handle, buf.data_ptr())
             fn()
             torch.cuda.synchronize()
             ctx.lib.ullava_debug_fmha_trace(ctx.handle, None)
             t = buf.cpu().numpy()
             t0 = t[t > 0].min()
-            names = ["KV issued", "K landed", "QK issued", "V landed", "P landed", "S landed", "max done", "P arrived",
-                     "rescaled", "P chunk 0", "P chunk 1", "st waited", "S loaded", "local max"]
-            print(name, "tile: " + ", ".join(names))
-            for j in range(min(12, (S + 127) // 128)):
-                print(j, [int(v - t0) if v > 0 else None for v in t[j][:14]])
-                print("   P arrived, warps 2..9:", [int(v - t0) for v in t[j][16:24]], " max done:", [int(v - t0) for v in t[j][24:32]])
+            rel = lambda v: [int(x - t0) if x > 0 else None for x in v]
+            print(name, "per tile: [K issued, K landed, QK issued, V landed, P landed, PV issued]; then per softmax warp 0..7")
+            for j in range(4, min(14, (S + 127) // 128)):
+                print(j, rel(t[j][[0, 1, 2, 3, 4, 14]]))
+                print("    S landed  ", rel(t[j][32:40]))
+                print("    max done  ", rel(t[j][24:32]))
+                print("    handed on ", rel(t[j][40:48]))
+                print("    P arrived ", rel(t[j][16:24]))
             ctx.set_attention_impl(0)
             continue
         for impl in (2, 1):

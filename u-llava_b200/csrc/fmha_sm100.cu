@@ -40,13 +40,18 @@ static constexpr int FM_BN = 128;       // keys per tile
 // 1.50 ms per 8 images); TPR = 4 is no faster (1.55 ms) -- per tile the kernel is bound by the S -> softmax -> P -> PV
 // latency chain, not by softmax issue slots (profiles/r02_ncu_fmha.md).
 static constexpr int fm_tpr(int hd) { return 2 + 0 * hd; }
-static constexpr int fm_threads(int hd) { return 64 + 128 * fm_tpr(hd); }   // TMA warp, MMA warp, 4 * TPR softmax warps
+// Warps 0-7 softmax (two warpgroups), warp 8 TMA producer, warps 9 / 10 Q K^T / P V issuers, warp 11 idle: the third warpgroup
+// hands its registers to the softmax warpgroups (setmaxnreg 40 / 232), whose threads hold 128 scores each.
+static constexpr int FM_TMA_WARP = 8, FM_MMA_WARP = 9, FM_PV_WARP = 10;   // FM_MMA_WARP: TMEM owner, Q K^T issuer
+static constexpr int FM_REGS_SOFTMAX = 232, FM_REGS_OTHER = 40;
+static constexpr int fm_threads(int hd) { return 128 * fm_tpr(hd) + 128 + 0 * hd; }
 // exchange of the partial row maxima (and, at the end, row sums) among the threads of a row: [tile parity][part][row]
 // floats; hd 128 uses one parity and a second barrier per tile
 static constexpr int fm_xch_floats(int hd) { return (hd == 128 ? 1 : 2) * fm_tpr(hd) * FM_BM; }
 static constexpr int FM_TMEM_COLS = 512;
-static constexpr int FM_COL_S = 0;      // S buffers: columns [0,128) and [128,256)
-static constexpr int FM_COL_O = 256;    // O accumulator: columns [256, 256 + hd)
+static constexpr int FM_SBUFS = 3;      // S / P buffers in TMEM
+static constexpr int FM_COL_S = 0;      // S buffers: columns [0,128), [128,256), [256,384)
+static constexpr int FM_COL_O = 384;    // O accumulator: columns [384, 384 + hd)
 static constexpr float FM_RESCALE_THRESHOLD = 8.f;  // log2 units
 
 struct FmhaMaps {
@@ -60,12 +65,12 @@ struct FmhaParams {
   int seq_q, seq_k, causal, q_pos0;
   float scale_log2;
   int S;  // rel-pos grid side (RP != 0)
-  long long* trace;  // debug (ullava_debug_fmha_trace): clock64 stamps of CTA (0, 0, 0), [tile < 64][32], else NULL
+  long long* trace;  // debug (ullava_debug_fmha_trace): clock64 stamps of CTA (0, 0, 0), [tile < 64][48], else NULL
 };
 #define FMHA_TRACE(tile, slot)                                                                      \
   do {                                                                                              \
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 64)            \
-      p.trace[(tile) * 32 + (slot)] = clock64();                                                     \
+      p.trace[(tile) * 48 + (slot)] = clock64();                                                     \
   } while (0)
 
 template <int HD>
@@ -76,7 +81,7 @@ struct FmhaCfg {
   static constexpr int TAIL_BYTES = 128 * TAIL * 2;
   static constexpr int TILE = NS * SLAB + TAIL_BYTES;     // one Q / K / V tile
   static constexpr int STAGES = HD == 64 ? 4 : 3;
-  static constexpr int BAR_BYTES = (1 + 3 * STAGES + 2 + 2 + 1 + 1 + 1) * 8 + 16;
+  static constexpr int BAR_BYTES = (1 + 4 * STAGES + 3 * FM_SBUFS + 1 + 1) * 8 + 16;
   static_assert(TAIL == 0 || TAIL == 16, "head_dim must be 64, 80 or 128");
   static constexpr int smem_bytes(int table_floats) {
     return 1024 + TILE * (1 + 2 * STAGES) + (table_floats + fm_xch_floats(HD)) * 4 + BAR_BYTES;
@@ -108,15 +113,16 @@ __device__ __forceinline__ void fmha_issue_pv(uint32_t o_tmem, uint32_t p_tmem, 
   // B = V tile [128 keys x hd], hd contiguous: MN-major
   constexpr uint32_t idesc_main = make_idesc_f16(T16<T>::kUmmaFormat, FM_BM, C::NS * 64) | (1u << 16);
   constexpr uint32_t idesc_tail = make_idesc_f16(T16<T>::kUmmaFormat, FM_BM, 16) | (1u << 16);
+  // one descriptor per slab kind; 16 keys further = + 2048 B (SWIZZLE_128B slab) / + 512 B (tail slab) in the
+  // 16-byte-unit address field, which cannot carry out of its 14 bits for a valid shared address
+  const uint64_t b0 = make_smem_desc(v_smem, C::SLAB, 1024, 2);
+  const uint64_t bt0 = make_smem_desc(v_smem + C::NS * C::SLAB, 16, 256, 6);
 #pragma unroll
   for (int ks = 0; ks < FM_BN / 16; ++ks) {
     const uint32_t acc = (first_tile && ks == 0) ? 0u : 1u;
-    const uint64_t b = make_smem_desc(v_smem + ks * 2048, C::SLAB, 1024, 2);
-    umma_f16_ts(o_tmem, p_tmem + ks * 8, b, idesc_main, acc);
-    if constexpr (C::TAIL != 0) {
-      const uint64_t bt = make_smem_desc(v_smem + C::NS * C::SLAB + ks * 512, 16, 256, 6);
-      umma_f16_ts(o_tmem + C::NS * 64, p_tmem + ks * 8, bt, idesc_tail, acc);
-    }
+    umma_f16_ts(o_tmem, p_tmem + ks * 8, b0 + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_main, acc);
+    if constexpr (C::TAIL != 0)
+      umma_f16_ts(o_tmem + C::NS * 64, p_tmem + ks * 8, bt0 + static_cast<uint64_t>(ks * (512 >> 4)), idesc_tail, acc);
   }
 }
 
@@ -141,7 +147,9 @@ __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, flo
     }
   }
   if (__any_sync(0xffffffffu, grow)) {
-    mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);  // O holds tiles 0..j-1
+    // O holds tiles 0..j-1.  One barrier per S buffer: Q K^T runs FM_SBUFS tiles ahead, so S_j having landed only
+    // proves P V of tile j - FM_SBUFS complete, and a single barrier's parity could be two completions behind
+    mbar_wait(&pv_done[(j - 1) % FM_SBUFS], static_cast<uint32_t>((j - 1) / FM_SBUFS) & 1u);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < HD / 16; ++c) {
@@ -159,7 +167,7 @@ __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, flo
 
 // RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
 // EMU: of every 8 pairs of exponentials, EMU are computed on the FMA pipe (ex2_fma2) and 8 - EMU on the MUFU
-template <typename T, int HD, int RP, int EMU>
+template <typename T, int HD, int RP, int EMU, bool ALT>
 __global__ void __launch_bounds__(fm_threads(HD), 1)
 fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   using C = FmhaCfg<HD>;
@@ -173,7 +181,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   float* tabs = reinterpret_cast<float*>(smem + C::TILE * (1 + 2 * ST));
   float* xch = tabs + (RP ? FM_BM * pstride : 0);
   constexpr int TPR = 2;                                    // == fm_tpr(HD)
-  constexpr int CPT = FM_BN / TPR;                          // key columns per softmax thread and tile
+  constexpr int CPT = ALT ? FM_BN : FM_BN / TPR;            // key columns per softmax thread and tile
   constexpr int kXchFloats = (HD == 128 ? 1 : 2) * TPR * FM_BM;   // == fm_xch_floats(HD)
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kXchFloats);
   constexpr bool kXchDouble = HD != 128;
@@ -181,11 +189,12 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   uint64_t* q_full = bars;
   uint64_t* k_full = q_full + 1;
   uint64_t* v_full = k_full + ST;
-  uint64_t* kv_empty = v_full + ST;
-  uint64_t* s_full = kv_empty + ST;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* pv_done = p_full + 2;
-  uint64_t* pro_done = pv_done + 1;
+  uint64_t* k_empty = v_full + ST;
+  uint64_t* v_empty = k_empty + ST;
+  uint64_t* s_full = v_empty + ST;
+  uint64_t* p_full = s_full + FM_SBUFS;
+  uint64_t* pv_done = p_full + FM_SBUFS;
+  uint64_t* pro_done = pv_done + FM_SBUFS;
   uint64_t* o_final = pro_done + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
 
@@ -201,7 +210,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   const int n_tiles = (k_end + FM_BN - 1) / FM_BN;
   constexpr int kRP = RP ? 1 : 0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == FM_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&maps.q);
     tma_prefetch_desc(&maps.k);
     tma_prefetch_desc(&maps.v);
@@ -209,24 +218,27 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     for (int s = 0; s < ST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FM_SBUFS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128 * TPR);
+      mbar_init(&p_full[i], ALT ? 128 : 128 * TPR);
     }
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < FM_SBUFS; ++i) mbar_init(&pv_done[i], 1);
     mbar_init(pro_done, 128 * TPR);
     mbar_init(o_final, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<1>(tmem_ptr, FM_TMEM_COLS);
+  if (warp == FM_MMA_WARP) tmem_alloc<1>(tmem_ptr, FM_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FM_REGS_OTHER));
+  if (warp == FM_TMA_WARP) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(q_full, C::TILE);
@@ -246,30 +258,34 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.rw, &v_full[0], s * 64, 0, 0, 0);
         if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.rwt, &v_full[0], C::NS * 64, 0, 0, 0);
       }
-      for (int j = 0; j < n_tiles; ++j) {
-        const int it = j + kRP;
-        const int st = it % ST;
-        const uint32_t ph = static_cast<uint32_t>(it / ST) & 1u;
-        mbar_wait(&kv_empty[st], ph ^ 1u);
+      // K runs one tile ahead of V: a K slot is free again once its QK^T has completed, a V slot once its P V has
+      auto load_k = [&](int j) {
+        const int it = j + kRP, st = it % ST;
+        mbar_wait(&k_empty[st], (static_cast<uint32_t>(it / ST) & 1u) ^ 1u);
         FMHA_TRACE(j, 0);
         uint8_t* sk = sKV + st * 2 * C::TILE;
-        uint8_t* sv = sk + C::TILE;
         mbar_expect_tx(&k_full[st], C::TILE);
 #pragma unroll
         for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.k, &k_full[st], s * 64, j * FM_BN, h, b);
         if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.kt, &k_full[st], C::NS * 64, j * FM_BN, h, b);
+      };
+      load_k(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) load_k(j + 1);
+        const int it = j + kRP, st = it % ST;
+        mbar_wait(&v_empty[st], (static_cast<uint32_t>(it / ST) & 1u) ^ 1u);
+        uint8_t* sv = sKV + st * 2 * C::TILE + C::TILE;
         mbar_expect_tx(&v_full[st], C::TILE);
 #pragma unroll
         for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.v, &v_full[st], s * 64, j * FM_BN, h, b);
         if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.vt, &v_full[st], C::NS * 64, j * FM_BN, h, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == FM_MMA_WARP) {
     // ===================== MMA issuer (one thread) =====================
     if (elect_one()) {
       const uint32_t q_s = smem_u32(sQ);
       const uint32_t kv_s = smem_u32(sKV);
-      const uint32_t o_tmem = tmem_base + FM_COL_O;
       mbar_wait(q_full, 0);
       if constexpr (RP != 0) {
         mbar_wait(&k_full[0], 0);
@@ -279,51 +295,70 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         umma_commit<1>(&s_full[0]);
         fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + FM_BN, q_s, kv_s + C::TILE);     // Pw = Q Rw^T
         umma_commit<1>(&s_full[1]);
-        umma_commit<1>(&kv_empty[0]);
+        umma_commit<1>(&k_empty[0]);
+        umma_commit<1>(&v_empty[0]);
         mbar_wait(pro_done, 0);  // softmax threads have moved both tables out of TMEM
       }
-      {
-        const int it = kRP, st = it % ST;
-        mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
-        tc_fence_after();
-        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S, q_s, kv_s + st * 2 * C::TILE);
-        umma_commit<1>(&s_full[0]);
-      }
+      // S_j goes to buffer j % 3 as soon as P_{j-3} V_{j-3} has completed (pv_done of that buffer), so Q K^T runs up
+      // to three tiles ahead of the softmax and a group finds its next S_{j+2} complete when it hands in P_j.
+      // Q K^T and P V are issued by two different warps: the issuing thread stalls on its uniform registers until
+      // the tensor pipe has taken the instructions over, and one thread doing both spent ~1300 cycles per tile on
+      // 512 cycles of tensor work.
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          const int it = j + 1 + kRP, st = it % ST;
-          mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
-          FMHA_TRACE(j + 1, 1);
-          tc_fence_after();
-          fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + ((j + 1) & 1) * FM_BN, q_s, kv_s + st * 2 * C::TILE);
-          umma_commit<1>(&s_full[(j + 1) & 1]);
-          FMHA_TRACE(j + 1, 2);
-        }
+        const int it = j + kRP, st = it % ST;
+        mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
+        FMHA_TRACE(j, 1);
+        if (j >= FM_SBUFS)
+          mbar_wait(&pv_done[j % FM_SBUFS], static_cast<uint32_t>(j / FM_SBUFS - 1) & 1u);   // P_{j-3} consumed
+        tc_fence_after();
+        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + (j % FM_SBUFS) * FM_BN, q_s, kv_s + st * 2 * C::TILE);
+        umma_commit<1>(&s_full[j % FM_SBUFS]);
+        umma_commit<1>(&k_empty[st]);
+        FMHA_TRACE(j, 2);
+      }
+    }
+  } else if (warp == FM_PV_WARP) {
+    // ===================== P V issuer (one thread) =====================
+    if (elect_one()) {
+      const uint32_t kv_s = smem_u32(sKV);
+      const uint32_t o_tmem = tmem_base + FM_COL_O;
+      for (int j = 0; j < n_tiles; ++j) {
         const int it = j + kRP, st = it % ST;
         mbar_wait(&v_full[st], static_cast<uint32_t>(it / ST) & 1u);
         FMHA_TRACE(j, 3);
-        mbar_wait(&p_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u);
+        mbar_wait(&p_full[j % FM_SBUFS], static_cast<uint32_t>(j / FM_SBUFS) & 1u);
         FMHA_TRACE(j, 4);
         tc_fence_after();
-        fmha_issue_pv<T, HD>(o_tmem, tmem_base + FM_COL_S + (j & 1) * FM_BN, kv_s + st * 2 * C::TILE + C::TILE, j == 0);
-        umma_commit<1>(&kv_empty[st]);
-        umma_commit<1>(pv_done);
+        fmha_issue_pv<T, HD>(o_tmem, tmem_base + FM_COL_S + (j % FM_SBUFS) * FM_BN, kv_s + st * 2 * C::TILE + C::TILE,
+                             j == 0);
+        umma_commit<1>(&v_empty[st]);
+        umma_commit<1>(&pv_done[j % FM_SBUFS]);
+        FMHA_TRACE(j, 14);
       }
-      // the epilogue needs its own single-phase barrier: after the last tile a softmax thread can be up to TWO
-      // completions behind pv_done (no s_full wait bounds it any more), which a parity wait cannot disambiguate
+      // the epilogue needs its own single-phase barrier: a softmax thread can be several completions behind pv_done
       umma_commit<1>(o_final);
     }
+  }
   } else {
-    // ===================== softmax / correction / epilogue: TPR threads per query row =====================
-    // Softmax warp sw = warp - 2 takes the key columns [CPT * part, CPT * (part + 1)) of every tile, part = sw / 4, for
-    // the 32 rows of TMEM lane quadrant warp % 4 (a warp may only touch that quadrant; warps w, w + 4, ... share it).
-    // With one warp per SM sub-partition the softmax was latency-bound (XU pipe 39 %, tensor pipe 16 - 25 % in the
-    // round-1 captures); TPR warps per sub-partition hide each other's TMEM loads and MUFU latency.  The threads of a
-    // row exchange their partial row maximum through shared memory (one named barrier of 32 * TPR threads per tile),
-    // keep partial row sums that are added once at the end, and split the O columns for the lazy rescale and the final
-    // store.  The scores stay in registers between the max pass and the exp pass, so P (which overwrites the first 64
-    // columns of the S buffer) is only written after ALL threads of the row have read their scores (the barrier).
-    const int part = (warp - 2) >> 2;            // which CPT-column part of the tile
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FM_REGS_SOFTMAX));
+    // ===================== softmax / correction / epilogue: two warps per TMEM lane quadrant =====================
+    // Softmax warps w and w + 4 share the 32 rows of TMEM lane quadrant w % 4 (a warp may only touch that quadrant)
+    // and one SM sub-partition.  Per tile the sub-partition's MUFU is the bound (128 x 128 exponentials at 16 / clk /
+    // SM = 1024 cycles against 512 - 1024 cycles of tcgen05 work), so the two warps must keep it busy in turn:
+    //   ALT  (group g = 0 / 1 takes the tiles j = g, g + 2, ...; one thread owns a whole row of its tiles): while one
+    //        group is in its exponential pass the other loads S of the next tile and finds its row maximum.  The
+    //        reference maximum of a row is handed from tile to tile through shared memory (one float per row, a
+    //        bar.arrive / bar.sync pair of named barriers per tile and quadrant): tile j reads the maximum in use
+    //        after tile j - 1, grows it lazily, publishes it.  Each thread keeps the partial row sum of its own
+    //        tiles relative to the last maximum it saw and converts when that changes; the partial sums are added at
+    //        the end.
+    //   !ALT (both warps work on every tile, 64 key columns each, exchange their partial maxima, one barrier of 64
+    //        threads per tile): both warps are in the same phase at the same time -- kept for the rel-pos variants
+    //        whose per-thread bias registers do not fit beside 128 scores.
+    // The scores stay in registers between the max pass and the exp pass; P (which overwrites the first 64 columns
+    // of the S buffer as 16-bit pairs) is only written after every thread of the row has read its scores.
+    const int grp = warp >> 2;             // which of the two warps of the quadrant
+    const int part = ALT ? 0 : grp;              // which CPT-column part of the tile
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;            // row inside the tile
     const int qrow = m0 + row;
@@ -332,9 +367,13 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     const float sl2 = p.scale_log2;
     float* Ah = tabs + row * pstride;
     float* Aw = Ah + S;
-    float aw[RP == 2 ? CPT : 1];
-    constexpr int kOChunks = HD / 16;            // O columns in chunks of 16: chunk c belongs to part c % TPR
-#define FMHA_ROW_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * TPR) : "memory")
+    float aw[RP == 2 ? 64 : 1];                  // S == 64: the bias of grid column kw = key % 64
+    constexpr int kOChunks = HD / 16;            // O columns in chunks of 16: chunk c belongs to group c % 2
+    constexpr int NH = CPT / 64;                 // 64-column halves (= grid rows when S == 64) per thread and tile
+#define FMHA_ROW_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(64) : "memory")
+    // ALT: barrier 1 + 2 * quad + g is "group g published"; the publisher arrives, the reader syncs
+#define FMHA_PUB_ARRIVE(g) asm volatile("bar.arrive %0, %1;" ::"r"(1 + 2 * quad + (g)), "n"(64) : "memory")
+#define FMHA_PUB_SYNC(g) asm volatile("bar.sync %0, %1;" ::"r"(1 + 2 * quad + (g)), "n"(64) : "memory")
 
     if constexpr (RP != 0) {
       constexpr float kLog2e = 1.4426950408889634f;
@@ -344,13 +383,13 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       mbar_wait(&s_full[1], 0);
       tc_fence_after();
       {
-        // parts [0, TPR/2) turn Q Rh^T into A_h, parts [TPR/2, TPR) turn Q Rw^T into A_w (32-column chunks interleaved)
-        const int tb = part / (TPR / 2), sub_part = part % (TPR / 2);
+        // group 0 turns Q Rh^T into A_h, group 1 turns Q Rw^T into A_w
+        const int tb = grp;
         const uint32_t ts = tmem_base + lane_off + FM_COL_S + tb * FM_BN;
         float* dst = tb ? Aw : Ah;
         const int base = (tb ? qw : qh) + S - 1;   // table column r  ->  index base - r
 #pragma unroll 1
-        for (int c = sub_part; c < 4; c += TPR / 2) {
+        for (int c = 0; c < 4; ++c) {
           if (c * 32 >= 2 * S - 1) break;
           uint32_t r[32];
           tmem_ld_32x32(ts + c * 32, r);
@@ -364,30 +403,35 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       }
       tc_fence_before();
       mbar_arrive(pro_done);
-      FMHA_ROW_SYNC();                           // both tables of the row are complete
+      asm volatile("bar.sync %0, %1;" ::"r"(9 + quad), "n"(64) : "memory");   // both tables of the row are complete
       if constexpr (RP == 2) {
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) aw[i] = Aw[(CPT * part) % 64 + i];   // S == 64: my columns are kw0 .. kw0 + CPT - 1
+        for (int i = 0; i < 64; ++i) aw[i] = Aw[i];   // S == 64: my columns start at a multiple of 64
       }
     }
 
     float m_used = 0.f, l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int buf = j & 1;
+    bool first_mine = true;                      // ALT: l_run is still empty
+    for (int j = ALT ? grp : 0; j < n_tiles; j += ALT ? 2 : 1) {
+      const int buf = j % FM_SBUFS;
       const uint32_t ts = tmem_base + lane_off + FM_COL_S + buf * FM_BN;
       const int key0 = j * FM_BN + CPT * part;   // first key of this thread's part
       const bool need_mask = (j * FM_BN + FM_BN > p.seq_k) || (p.causal && (j * FM_BN + FM_BN - 1 > p.q_pos0 + m0));
-      mbar_wait(&s_full[buf], static_cast<uint32_t>((j >> 1) + kRP) & 1u);
-      if (threadIdx.x == 64) FMHA_TRACE(j, 5);
+      mbar_wait(&s_full[buf], static_cast<uint32_t>(j / FM_SBUFS + (buf < 2 ? kRP : 0)) & 1u);
+      if (lane == 0) FMHA_TRACE(j, 32 + warp);
       tc_fence_after();
       uint32_t r[CPT];
 #pragma unroll
       for (int c = 0; c < CPT / 32; ++c)
         tmem_ld_32x32(ts + CPT * part + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * c]));
       tmem_ld_wait();
-      if (threadIdx.x == 64) FMHA_TRACE(j, 12);
-      float ah = 0.f;
-      if constexpr (RP == 2) ah = Ah[min(2 * j + (CPT * part) / 64, S - 1)];   // S == 64: my part lies in one grid row
+      float ah[NH];                              // S == 64: half h of my part lies in grid row 2 j + ...
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf) ah[hf] = 0.f;
+      if constexpr (RP == 2) {
+#pragma unroll
+        for (int hf = 0; hf < NH; ++hf) ah[hf] = Ah[min(2 * j + (CPT * part) / 64 + hf, S - 1)];
+      }
       const int key_lim = p.causal ? min(p.seq_k, p.q_pos0 + qrow + 1) : p.seq_k;   // keys < key_lim are visible
       int kh0 = 0, kw0 = 0;
       if constexpr (RP == 1) {
@@ -395,22 +439,24 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         kw0 = key0 - kh0 * S;
       }
 
-      // ---- pass 1: my scores in log2 units (in place, bias and mask applied; the per-thread constant ah of the
+      // ---- pass 1: my scores in log2 units (in place, bias and mask applied; the per-half constant ah of the
       //      64 x 64 grid is added later) and their maximum.  Without bias or mask the raw scores stay as they are
       //      and the scale is folded into pass 2. ----
       const bool raw_scores = (RP == 0) && !need_mask;
-      float mx;
-      {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf) {
         float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (raw_scores) {
 #pragma unroll
-          for (int i = 0; i < CPT; i += 2)
+          for (int i = 64 * hf; i < 64 * hf + 64; i += 2)
             mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
         } else if (RP == 2 && !need_mask) {
           const uint64_t sl2v = pk2(sl2, sl2);
 #pragma unroll
-          for (int i = 0; i < CPT; i += 2) {
-            const uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v, pk2(aw[i], aw[i + 1]));
+          for (int i = 64 * hf; i < 64 * hf + 64; i += 2) {
+            const uint64_t x = ffma2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sl2v,
+                                     pk2(aw[i & 63], aw[(i + 1) & 63]));
             float x0, x1;
             upk2(x, x0, x1);
             r[i] = __float_as_uint(x0);
@@ -419,11 +465,17 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
           }
         } else {
           int kh = kh0, kw = kw0;
+          if constexpr (RP == 1) {
+            if (hf == 1) {                        // NH == 2: advance the grid position by 64 keys
+              kw += 64;
+              while (kw >= S) { kw -= S; ++kh; }
+            }
+          }
 #pragma unroll   // fully: r[] must be indexed with compile-time constants to stay in registers
-          for (int i = 0; i < CPT; ++i) {
+          for (int i = 64 * hf; i < 64 * hf + 64; ++i) {
             float x;
             if constexpr (RP == 0) x = __uint_as_float(r[i]) * sl2;
-            else if constexpr (RP == 2) x = fmaf(__uint_as_float(r[i]), sl2, aw[i]);
+            else if constexpr (RP == 2) x = fmaf(__uint_as_float(r[i]), sl2, aw[i & 63]);
             else x = fmaf(__uint_as_float(r[i]), sl2, Ah[min(kh, S - 1)] + Aw[kw]);
             if (key0 + i >= key_lim) x = -INFINITY;
             r[i] = __float_as_uint(x);
@@ -433,79 +485,133 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
             }
           }
         }
-        mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-        mx = raw_scores ? mx * sl2 : mx + ah;   // scale > 0; ah == 0 unless RP == 2
+        const float mh = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        mx = fmaxf(mx, raw_scores ? mh * sl2 : mh + ah[hf]);   // scale > 0; ah == 0 unless RP == 2
       }
-      // ---- the row maximum of the whole tile: exchange with the threads that hold the other columns ----
-      const int xs = kXchDouble ? buf * TPR : 0;
-      if (threadIdx.x == 64) FMHA_TRACE(j, 13);
-      xch[(xs + part) * FM_BM + row] = mx;
-      FMHA_ROW_SYNC();
-#pragma unroll
-      for (int q2 = 0; q2 < TPR; ++q2) mx = fmaxf(mx, xch[(xs + q2) * FM_BM + row]);
-      if constexpr (!kXchDouble) FMHA_ROW_SYNC();   // single slot: read before the next tile's write
-      if (threadIdx.x == 64) FMHA_TRACE(j, 6);
-      if (lane == 0) FMHA_TRACE(j, 24 + warp - 2);
-      fmha_rescale<HD, TPR>(j, mx, m_used, l_run, o_taddr, pv_done, part);
-      if (threadIdx.x == 64) FMHA_TRACE(j, 8);
 
+      if constexpr (!ALT) {
+        // ---- the row maximum of the whole tile: exchange with the thread that holds the other columns ----
+        const int xs = kXchDouble ? (j & 1) * 2 : 0;
+        xch[(xs + part) * FM_BM + row] = mx;
+        FMHA_ROW_SYNC();
+        mx = fmaxf(mx, xch[(xs + (part ^ 1)) * FM_BM + row]);
+        if constexpr (!kXchDouble) FMHA_ROW_SYNC();   // single slot: read before the next tile's write
+        if (lane == 0) FMHA_TRACE(j, 24 + warp);
+        fmha_rescale<HD, 2>(j, mx, m_used, l_run, o_taddr, pv_done, part);
+      } else {
+        // ---- the maximum in use: take it over from tile j - 1 (the other group), grow it lazily, hand it on ----
+        float m_prev = 0.f;
+        if (j > 0) {
+          FMHA_PUB_SYNC(grp ^ 1);
+          m_prev = xch[row];
+        }
+        bool grow = false;
+        float m_new;
+        if (j == 0) {
+          m_new = (mx == -INFINITY) ? 0.f : mx;
+        } else {
+          grow = mx > m_prev + FM_RESCALE_THRESHOLD;
+          m_new = grow ? mx : m_prev;
+        }
+        xch[row] = m_new;
+        FMHA_PUB_ARRIVE(grp);
+        if (lane == 0) FMHA_TRACE(j, 24 + warp);
+        if (!first_mine && m_used != m_new) l_run *= ex2_approx(m_used - m_new);   // my partial sum follows the maximum
+        first_mine = false;
+        m_used = m_new;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? ex2_approx(m_prev - m_new) : 1.f;
+          mbar_wait(&pv_done[(j - 1) % FM_SBUFS], static_cast<uint32_t>((j - 1) / FM_SBUFS) & 1u);  // O holds tiles 0..j-1
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < kOChunks; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(o_taddr + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(o_taddr + c * 16, o);
+          }
+        }
+      }
+
+      if (lane == 0) FMHA_TRACE(j, 40 + warp);
       // ---- pass 2: p = 2^(x - m), partial row sum, P -> TMEM (packed pairs: words [CPT/2 * part, +CPT/2) of the S buffer) ----
+      uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+      auto exp_pair = [&](float x0, float x1, int slot, uint32_t& packed) {
+        float p0, p1;                                               // 2^(-inf) = 0 for masked keys
+        if ((slot & 7) < EMU) {
+          const uint64_t pe = ex2_fma2<std::is_same<T, __half>::value ? 4 : 3>(x0, x1);
+          upk2(pe, p0, p1);
+          sum[slot & 1] = fadd2(sum[slot & 1], pe);
+        } else {
+          p0 = ex2_approx(x0);
+          p1 = ex2_approx(x1);
+          sum[slot & 1] = fadd2(sum[slot & 1], pk2(p0, p1));
+        }
+        packed = pack2<T>(p0, p1);
+      };
       {
         // one FFMA2 per pair either way (x * 1 + off is exactly x + off): a select between an FFMA2 and an FADD2 made
         // the compiler funnel every exponential through the same two temporaries, a serial chain of ~18 cycles a pair
         const float mul = raw_scores ? sl2 : 1.f;
         const uint64_t sl2v = pk2(mul, mul);
-        const float off = ah - m_used;
-        const uint64_t offv = pk2(off, off);
-        uint64_t sum[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
 #pragma unroll
         for (int c = 0; c < CPT / 32; ++c) {
+          const float off = ah[c / 2] - m_used;
+          const uint64_t offv = pk2(off, off);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const int e = c * 32 + i;
-            const uint64_t v2 = pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-            const uint64_t x = ffma2(v2, sl2v, offv);
+            const uint64_t x = ffma2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), sl2v, offv);
             float x0, x1;
             upk2(x, x0, x1);
-            float p0, p1;                                           // 2^(-inf) = 0 for masked keys
-            if (((i >> 1) & 7) < EMU) {
-              const uint64_t pe = ex2_fma2<sizeof(T) == 2 && std::is_same<T, __half>::value ? 4 : 3>(x0, x1);
-              upk2(pe, p0, p1);
-              sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pe);
-            } else {
-              p0 = ex2_approx(x0);
-              p1 = ex2_approx(x1);
-              sum[(i >> 1) & 1] = fadd2(sum[(i >> 1) & 1], pk2(p0, p1));
-            }
-            pk[i >> 1] = pack2<T>(p0, p1);
+            exp_pair(x0, x1, i >> 1, pk[i >> 1]);
           }
           tmem_st_32x16(ts + (CPT / 2) * part + c * 16, pk);
-          if (threadIdx.x == 64) FMHA_TRACE(j, 9 + c);
         }
+      }
+      {
         float s0, s1, s2, s3;
         upk2(sum[0], s0, s1);
         upk2(sum[1], s2, s3);
         l_run += (s0 + s1) + (s2 + s3);
       }
       tmem_st_wait();
-      if (threadIdx.x == 64) FMHA_TRACE(j, 11);
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
-      if (threadIdx.x == 64) FMHA_TRACE(j, 7);
-      if (lane == 0) FMHA_TRACE(j, 16 + warp - 2);
+      if (lane == 0) FMHA_TRACE(j, 16 + warp);
     }
 
-    // ---- epilogue: O / l -> global; the row sum is the sum of the threads' partial sums ----
-    const int ls = kXchDouble ? (n_tiles & 1) * TPR : 0;   // the parity the last tile did not use (its reads may be in flight)
-    xch[(ls + part) * FM_BM + row] = l_run;
-    FMHA_ROW_SYNC();
-    float l_tot = 0.f;
-#pragma unroll
-    for (int q2 = 0; q2 < TPR; ++q2) l_tot += xch[(ls + q2) * FM_BM + row];
+    // ---- epilogue: O / l -> global; the row sum is the sum of the two threads' partial sums ----
+    float inv;
+    if constexpr (!ALT) {
+      const int ls = kXchDouble ? (n_tiles & 1) * 2 : 0;   // the parity the last tile did not use (its reads may be in flight)
+      xch[(ls + part) * FM_BM + row] = l_run;
+      FMHA_ROW_SYNC();
+      const float l_tot = xch[ls * FM_BM + row] + xch[(ls + 1) * FM_BM + row];
+      inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    } else {
+      // the group of the last tile holds the final maximum; the other one converts its partial sum to it
+      const int gl = (n_tiles - 1) & 1;
+      if (grp != gl) {
+        FMHA_PUB_SYNC(gl);
+        const float m_fin = xch[row];
+        xch[FM_BM + row] = first_mine ? 0.f : l_run * ex2_approx(m_used - m_fin);
+        FMHA_PUB_ARRIVE(grp);
+        FMHA_PUB_SYNC(gl);
+        inv = xch[row];
+      } else {
+        FMHA_PUB_SYNC(grp ^ 1);
+        const float l_tot = l_run + xch[FM_BM + row];
+        inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        xch[row] = inv;
+        FMHA_PUB_ARRIVE(grp);
+      }
+    }
     mbar_wait(o_final, 0);
     tc_fence_after();
-    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
     T* orow = nullptr;
     if (qrow < p.seq_q) {
       if (p.o_row_map) {
@@ -517,7 +623,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     }
 #pragma unroll
     for (int c = 0; c < kOChunks; ++c) {
-      if (c % TPR == part) {                     // warp-uniform
+      if (c % 2 == grp) {                        // warp-uniform
         uint32_t r[16];
         tmem_ld_32x16(o_taddr + c * 16, r);
         tmem_ld_wait();
@@ -537,11 +643,13 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       }
     }
 #undef FMHA_ROW_SYNC
+#undef FMHA_PUB_ARRIVE
+#undef FMHA_PUB_SYNC
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == FM_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, FM_TMEM_COLS);
   }
@@ -564,11 +672,11 @@ static int fmha_map(CUtensorMap* main_map, CUtensorMap* tail_map, const void* ba
   return e;
 }
 
-template <typename T, int HD, int RP, int EMU>
+template <typename T, int HD, int RP, int EMU, bool ALT>
 static int fmha_launch_emu(const FmhaMaps& maps, const FmhaParams& p, int batch, int heads, cudaStream_t stream) {
   using C = FmhaCfg<HD>;
   const int smem = C::smem_bytes(RP ? FM_BM * (2 * p.S + 1) : 0);
-  auto kern = fmha_tcgen05_kernel<T, HD, RP, EMU>;
+  auto kern = fmha_tcgen05_kernel<T, HD, RP, EMU, ALT>;
   static SmemOptIn opt_in;   // per device (common.cuh)
   { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
   dim3 grid((p.seq_q + FM_BM - 1) / FM_BM, heads, batch);
@@ -584,11 +692,14 @@ static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int
     const char* e = getenv("ULLAVA_FMHA_EMU");
     g_fmha_emu = e ? atoi(e) : 3;
   }
+  // one thread per row and alternating tiles (ALT) where the scores are all a thread holds: 740 vs 620 TFLOP/s at hd 64,
+  // 1180 vs 1110 at hd 128 (4096 keys).  With the rel-pos bias registers beside them it spills; the two-threads-per-row
+  // form stays for those (SAM global attention: 615 TFLOP/s against 557)
+  constexpr bool kAlt = RP == 0;
   switch (g_fmha_emu) {
-    case 2: return fmha_launch_emu<T, HD, RP, 2>(maps, p, batch, heads, stream);
-    case 4: return fmha_launch_emu<T, HD, RP, 4>(maps, p, batch, heads, stream);
-    case 0: return fmha_launch_emu<T, HD, RP, 0>(maps, p, batch, heads, stream);
-    default: return fmha_launch_emu<T, HD, RP, 3>(maps, p, batch, heads, stream);
+    case 0: return fmha_launch_emu<T, HD, RP, 0, kAlt>(maps, p, batch, heads, stream);
+    case 2: return fmha_launch_emu<T, HD, RP, 2, kAlt>(maps, p, batch, heads, stream);
+    default: return fmha_launch_emu<T, HD, RP, 3, kAlt>(maps, p, batch, heads, stream);
   }
 }
 
