@@ -63,6 +63,13 @@ def main():
             t = buf.cpu().numpy()
             t0 = t[t > 0].min()
             rel = lambda v: [int(x - t0) if x > 0 else None for x in v]
+            if name.startswith("sam_window"):
+                print(name, "per tile: [loads issued, Q/K landed, QK issued, S landed, tables done, pass 1 done, P arrived, "
+                      "P landed, PV issued, O landed, stored]")
+                for tt in range(2):
+                    print(tt, rel(t.reshape(-1)[tt * 16: tt * 16 + 11]))
+                ctx.set_attention_impl(0)
+                continue
             print(name, "per tile: [K issued, K landed, QK issued, V landed, P landed, PV issued]; then per softmax warp 0..7")
             for j in range(4, min(14, (S + 127) // 128)):
                 print(j, rel(t[j][[0, 1, 2, 3, 4, 14]]))

@@ -610,8 +610,6 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         FMHA_PUB_ARRIVE(grp);
       }
     }
-    mbar_wait(o_final, 0);
-    tc_fence_after();
     T* orow = nullptr;
     if (qrow < p.seq_q) {
       if (p.o_row_map) {
@@ -621,24 +619,34 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         orow = static_cast<T*>(p.o) + b * p.o_bs + static_cast<int64_t>(qrow) * p.o_rs + h * p.o_hs;
       }
     }
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    {
+      // this group's chunks (c % 2 == grp): all TMEM loads in flight before the first store
+      constexpr int kMine = (kOChunks + 1) / 2;
+      uint32_t r[kMine * 16];
 #pragma unroll
-    for (int c = 0; c < kOChunks; ++c) {
-      if (c % 2 == grp) {                        // warp-uniform
-        uint32_t r[16];
-        tmem_ld_32x16(o_taddr + c * 16, r);
-        tmem_ld_wait();
-        if (orow) {
-          uint4 w0, w1;
-          w0.x = pack2<T>(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-          w0.y = pack2<T>(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-          w0.z = pack2<T>(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-          w0.w = pack2<T>(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-          w1.x = pack2<T>(__uint_as_float(r[8]) * inv, __uint_as_float(r[9]) * inv);
-          w1.y = pack2<T>(__uint_as_float(r[10]) * inv, __uint_as_float(r[11]) * inv);
-          w1.z = pack2<T>(__uint_as_float(r[12]) * inv, __uint_as_float(r[13]) * inv);
-          w1.w = pack2<T>(__uint_as_float(r[14]) * inv, __uint_as_float(r[15]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 16) = w0;
-          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = w1;
+      for (int i = 0; i < kMine; ++i) {
+        const int c = 2 * i + grp;
+        if (c < kOChunks) tmem_ld_32x16(o_taddr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&r[i * 16]));
+      }
+      tmem_ld_wait();
+      if (orow) {
+#pragma unroll
+        for (int i = 0; i < kMine; ++i) {
+          const int c = 2 * i + grp;
+          if (c < kOChunks) {
+#pragma unroll
+            for (int hv = 0; hv < 2; ++hv) {
+              const uint32_t* v = &r[i * 16 + hv * 8];
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+              w.y = pack2<T>(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+              w.z = pack2<T>(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+              w.w = pack2<T>(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+              *reinterpret_cast<uint4*>(orow + c * 16 + hv * 8) = w;
+            }
+          }
         }
       }
     }
