@@ -379,6 +379,48 @@ def test_flash_attention_rescale_growing_maximum(ctx):
     _check(out, _attn_ref(q, k, v, False, 0, D ** -0.5), torch.bfloat16, "growing-max attention")
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("D", [64, 80, 128])
+@pytest.mark.parametrize("Sk", [100, 200, 300, 500, 897, 2048])
+def test_flash_attention_maximum_handed_from_tile_to_tile(ctx, dtype, D, Sk):
+    """The two softmax warpgroups take alternating key tiles and hand the row maximum on (fmha_sm100.cu, ALT): keys whose
+    scores climb by ~12 log2 units per tile force the lazy rescale on (nearly) every tile, in both groups; every row
+    also has tiles whose scores lie far below the maximum in use (partial sums converted late), and 1 ... 16 tiles cover
+    'the other group never ran' and both parities of the last tile."""
+    B, H, Sq = 2, 3, 200
+    g = torch.Generator(device="cuda").manual_seed(43 + Sk + D)
+    q = torch.randn((B, Sq, H, D), generator=g, device="cuda")
+    k = torch.randn((B, Sk, H, D), generator=g, device="cuda")
+    v = torch.randn((B, Sk, H, D), generator=g, device="cuda")
+    # one strong common direction: q.k grows with the key index for half of the rows and falls for the other half
+    u = torch.randn((D,), generator=g, device="cuda")
+    u = u / u.norm()
+    ramp = torch.linspace(0.0, 1.0, Sk, device="cuda") * (Sk / 128.0) * 12.0 * 0.6931 * D ** 0.5
+    sign = torch.where(torch.arange(Sq, device="cuda") % 2 == 0, 1.0, -1.0)
+    q = (q + sign[None, :, None, None] * 1.0 * u).to(dtype)
+    k = (k + ramp[None, :, None, None] * u).to(dtype)
+    v = v.to(dtype)
+    ctx.set_attention_impl(2)
+    try:
+        out = ctx.attention(q, k, v, causal=False, q_pos0=0)
+    finally:
+        ctx.set_attention_impl(0)
+    ref = _attn_ref(q, k, v, False, 0, D ** -0.5)
+    assert torch.isfinite(out.float()).all()
+    _check(out, ref, dtype, f"handed-on maximum {Sk, D}")
+
+
+@pytest.mark.parametrize("D,Sk,causal", [(64, 4096, False), (128, 1664, True), (80, 1000, False)])
+def test_flash_attention_is_bit_reproducible(ctx, D, Sk, causal):
+    """The pipeline has nine asynchronous parties per CTA (TMA, two MMA issuers, eight softmax warps); a missed
+    dependency shows up as run-to-run differences long before it shows up as a tolerance failure."""
+    qkv = _rand((2, Sk, 3, 4, D), torch.bfloat16, seed=49)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    first = ctx.attention(q, k, v, causal=causal).clone()
+    for _ in range(12):
+        assert torch.equal(ctx.attention(q, k, v, causal=causal), first)
+
+
 def _relpos_ref(q, k, v, rel_h, rel_w, S, scale):
     """segment_anything/modeling/image_encoder.py:196-260 + add_decomposed_rel_pos (:355-392), fp32."""
     qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))           # [B, H, N, D]
@@ -423,6 +465,18 @@ def test_attention_relpos(ctx, dtype, impl, packed_tables, B, H, S, D):
     exp = torch.zeros_like(scat)
     exp[rows[keep].long()] = out.reshape(B * N, H, D)[keep]
     assert torch.equal(scat, exp)
+
+
+@pytest.mark.parametrize("S", [14, 64])
+def test_attention_relpos_is_bit_reproducible(ctx, S):
+    N, D = S * S, 80
+    qkv = _rand((3, N, 3, 4, D), torch.bfloat16, seed=50)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    both = _rand((2 * (2 * S - 1), D), torch.bfloat16, scale=0.5, seed=51)
+    rel_h, rel_w = both[:2 * S - 1], both[2 * S - 1:]
+    first = ctx.attention_relpos(q, k, v, rel_h, rel_w, S).clone()
+    for _ in range(12):
+        assert torch.equal(ctx.attention_relpos(q, k, v, rel_h, rel_w, S), first)
 
 
 @pytest.mark.parametrize("dtype", DT)
