@@ -8,21 +8,29 @@
 //   * SAM ViT-H windowed (14x14) and global (64x64) attention with decomposed relative-position bias,
 //     hd 80                                               segment_anything/modeling/image_encoder.py:196-260,355-392
 //
-// One CTA = one 128-row query tile of one (batch, head).  64 + 128 * TPR threads (TPR = 4; 2 for hd 128):
-//   warp 0      TMA producer: Q once, then K/V tiles of 128 keys through a STAGES-deep ring
-//               (cp.async.bulk.tensor.4d over the strided [d, token, head, batch] view, SWIZZLE_128B slabs of
-//               64 columns plus, for hd 80, one SWIZZLE_32B slab of 16 columns);
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
-//                 S_j   = Q K_j^T        (SS form: A = Q smem K-major, B = K smem K-major, N = 128)
-//                 O    += P_j V_j        (TS form: A = P_j in TMEM, B = V smem MN-major, N = hd)
-//               S is double buffered in TMEM (2 x 128 columns) so QK^T of tile j+1 runs under the softmax of tile j;
-//               P_j overwrites the first 64 columns of its own S buffer as packed 16-bit pairs;
-//   warps 2..   softmax: TPR threads per query row (warps w, w + 4, ... share a TMEM lane quadrant and take 128 / TPR key
-//               columns of every tile each; no shuffles, one named barrier of 32 * TPR threads per tile to exchange the
-//               partial row maximum).  The scores stay in registers between the max pass and the exp pass (one
-//               MUFU.EX2 per score); the row sum is kept as TPR partial sums, P is stored to TMEM.  O lives in TMEM for the whole CTA; it is only rescaled when the running maximum grew by
-//               more than 2^8 ("lazy rescale" - the stale maximum is used consistently for P and the row sum, so the
-//               result is exact), which after the first tiles practically never happens.
+// One CTA = one 128-row query tile of one (batch, head), 384 threads in three warpgroups:
+//   warps 0-7   softmax, two warps per TMEM lane quadrant (w and w + 4; registers raised to 232 with setmaxnreg):
+//                 without bias the two take ALTERNATING key tiles, one thread per row (the row maximum in use is handed
+//                 from tile to tile through shared memory, partial row sums are added at the end), so one warp's
+//                 exponential pass runs beside the other's TMEM load + maximum pass;
+//                 with the rel-pos bias both work on every tile, 64 key columns each (the bias registers do not fit
+//                 beside 128 scores), and exchange partial maxima through one 64-thread named barrier per tile.
+//               The scores stay in registers between the max pass and the exp pass; 3 of every 8 pairs of exponentials
+//               are computed on the FMA pipe (the MUFU, 16 ex2 / clk / SM, is the pipe that bounds a tile), the row sum
+//               is kept as partial sums, P is stored to TMEM.  O lives in TMEM for the whole CTA; it is only rescaled
+//               when the running maximum grew by more than 2^8 ("lazy rescale" - the stale maximum is used consistently
+//               for P and the row sum, so the result is exact), which after the first tiles practically never happens;
+//   warp 8      TMA producer: Q once, then K / V tiles of 128 keys through a STAGES-deep ring whose K and V slots are
+//               freed separately (cp.async.bulk.tensor.4d over the strided [d, token, head, batch] view, SWIZZLE_128B
+//               slabs of 64 columns plus, for hd 80, one SWIZZLE_32B slab of 16 columns);
+//   warp 9      TMEM allocator + Q K^T issuer:  S_j = Q K_j^T   (SS form, N = 128) into buffer j % 3 as soon as
+//               P_{j-3} V_{j-3} has freed it, i.e. up to three tiles ahead of the softmax;
+//   warp 10     P V issuer:  O += P_j V_j   (TS form: A = P_j in TMEM, B = V smem MN-major, N = hd); P_j overwrites the
+//               first 64 columns of its own S buffer as packed 16-bit pairs.
+//               (Two issuing threads: one thread stalls on its uniform registers until the tensor pipe has taken its
+//               instructions over, and spent ~1300 cycles a tile on 512 cycles of tensor work.  Both issue under
+//               elect.sync -- under `lane == 0` the compiler wraps every tcgen05.mma in a broadcast loop.)
+//   warp 11     idle (its registers go to the softmax warpgroups).
 // Rel-pos bias: the prologue runs Q Rh^T and Q Rw^T through the same MMA path into the two S buffers; each softmax
 // thread turns its two rows into per-row tables A_h[kh], A_w[kw] (x log2 e, fp32, shared memory), so that in the
 // main loop bias(q, k) = A_h[kh(k)] + A_w[kw(k)].  For the 64x64 global grid a key tile is exactly two grid rows:
@@ -34,11 +42,7 @@ namespace ullava {
 
 static constexpr int FM_BM = 128;       // query rows per CTA (= TMEM lanes)
 static constexpr int FM_BN = 128;       // keys per tile
-// Softmax threads per query row: the 128 key columns of a tile are split among TPR threads of TPR different warps that
-// share a TMEM lane quadrant (warps w, w + 4, ...).  Measured on the path's shapes (tools/bench_attn.py, B200): TPR = 2 is
-// 5 - 11 % faster than one thread per row (CLIP 0.174 -> 0.166 ms, LLaMA prefill 0.312 -> 0.291 ms, SAM global 1.66 ->
-// 1.50 ms per 8 images); TPR = 4 is no faster (1.55 ms) -- per tile the kernel is bound by the S -> softmax -> P -> PV
-// latency chain, not by softmax issue slots (profiles/r02_ncu_fmha.md).
+// Softmax warps per TMEM lane quadrant (warps w, w + 4): two.  Four were no faster (profiles/r02_ncu_fmha.md).
 static constexpr int fm_tpr(int hd) { return 2 + 0 * hd; }
 // Warps 0-7 softmax (two warpgroups), warp 8 TMA producer, warps 9 / 10 Q K^T / P V issuers, warp 11 idle: the third warpgroup
 // hands its registers to the softmax warpgroups (setmaxnreg 40 / 232), whose threads hold 128 scores each.
@@ -692,23 +696,19 @@ static int fmha_launch_emu(const FmhaMaps& maps, const FmhaParams& p, int batch,
   return check_cuda(cudaGetLastError(), "fmha_tcgen05 launch");
 }
 
-static int g_fmha_emu = -1;   // sweep knob (ULLAVA_FMHA_EMU), -1 = default
+// Of every 8 pairs of exponentials, FM_EX2_FMA run on the FMA pipe (ex2_fma2, common.cuh).  Swept with -DFM_EX2_FMA=n
+// (tools/bench_attn.py, B200): 0 / 2 / 3 / 4 -> 4096 x hd 64: 723 / 735 / 741 / 718 TFLOP/s, SAM global 574 / 600 / 617 /
+// 590, CLIP 295 / 304 / 312 / 300.
+#ifndef FM_EX2_FMA
+#define FM_EX2_FMA 3
+#endif
 
 template <typename T, int HD, int RP>
 static int fmha_launch(const FmhaMaps& maps, const FmhaParams& p, int batch, int heads, cudaStream_t stream) {
-  if (g_fmha_emu < 0) {
-    const char* e = getenv("ULLAVA_FMHA_EMU");
-    g_fmha_emu = e ? atoi(e) : 3;
-  }
   // one thread per row and alternating tiles (ALT) where the scores are all a thread holds: 740 vs 620 TFLOP/s at hd 64,
   // 1180 vs 1110 at hd 128 (4096 keys).  With the rel-pos bias registers beside them it spills; the two-threads-per-row
   // form stays for those (SAM global attention: 615 TFLOP/s against 557)
-  constexpr bool kAlt = RP == 0;
-  switch (g_fmha_emu) {
-    case 0: return fmha_launch_emu<T, HD, RP, 0, kAlt>(maps, p, batch, heads, stream);
-    case 2: return fmha_launch_emu<T, HD, RP, 2, kAlt>(maps, p, batch, heads, stream);
-    default: return fmha_launch_emu<T, HD, RP, 3, kAlt>(maps, p, batch, heads, stream);
-  }
+  return fmha_launch_emu<T, HD, RP, FM_EX2_FMA, RP == 0>(maps, p, batch, heads, stream);
 }
 
 bool fmha_supported(const AttnArgs& a, bool relpos, int S) {
