@@ -61,6 +61,8 @@ def main():
                   ("sam_fc1_b32", 131072, 5120, 1280, native.EPI_GELU), ("sam_fc2_b32", 131072, 1280, 5120, native.EPI_NONE)]
     if os.environ.get("SHAPES") == "large":
         shapes = [s for s in shapes if s[1] > 32]
+    if os.environ.get("EPI_NONE"):   # same shapes without their activation: what the epilogue costs
+        shapes = [(n, M, N, K, native.EPI_NONE) for n, M, N, K, e in shapes if e != native.EPI_SILU_MUL]
     for name, M, N, K, epi in shapes:
         ncopies = max(2, int(160e6 // (N * K * 2)) + 1) if M <= 32 else 2
         a = torch.randn((M, K), device="cuda", dtype=dt)

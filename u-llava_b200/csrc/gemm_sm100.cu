@@ -521,23 +521,34 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row = m_blk * kPairBM + static_cast<int>(rank) * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        float v[32];
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
+      // This warp's chunks c = half, half + 2, ...: the TMEM load of the next chunk is in flight while the current one
+      // goes through the activation and the stores, and the accumulator is handed back to the MMA thread as soon as
+      // the LAST load has landed in registers -- not after the last store (with K = 1024 / 1280 a tile's main loop
+      // is barely longer than its epilogue, so every cycle the accumulator is held stalls the tensor pipe).
+      // tools/bench_gemm.py SHAPES=b32: +1 ... +3.6 % per shape (SAM qkv 1373 -> 1423, LLaMA gate/up 1621 -> 1680 TFLOP/s);
+      // neutral inside the power-capped step (same-box A/B: 709.8 / 711.3 vs 708.8 / 712.8 ms).
+      constexpr int kChunks = BN / 64;
+      uint32_t rn[32];
+      tmem_ld_32x32(taddr + half * 32, rn);
+#pragma unroll 1   // one copy of the activation code: unrolled four times the GELU epilogue ran 12 % slower
+      for (int i = 0; i < kChunks; ++i) {
+        const int c = half + 2 * i;
         tmem_ld_wait();
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(rn[k]);
+        if (i + 1 < kChunks) {
+          tmem_ld_32x32(taddr + (c + 2) * 32, rn);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+            else mbar_arrive_cluster(&tmem_empty[acc], 0);
+          }
+        }
         const int n0 = n_blk * BN + c * 32;
         if (row_ok && n0 < p.N) epilogue_store<T, EPI, 32>(v, p, bias, resid, false, 0, row, n0);
-        __syncwarp();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(&tmem_empty[acc]);
-        else mbar_arrive_cluster(&tmem_empty[acc], 0);
       }
       if (++acc == 2) {
         acc = 0;
