@@ -69,11 +69,13 @@ struct FmhaParams {
   int seq_q, seq_k, causal, q_pos0;
   float scale_log2;
   int S;  // rel-pos grid side (RP != 0)
+  int n_qt, heads, n_items;   // work items = (query tile, head, batch), query tile fastest
+  int sms;                    // host side only: CTAs of the persistent launch
   long long* trace;  // debug (ullava_debug_fmha_trace): clock64 stamps of CTA (0, 0, 0), [tile < 64][48], else NULL
 };
 #define FMHA_TRACE(tile, slot)                                                                      \
   do {                                                                                              \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 64)            \
+    if (p.trace && blockIdx.x == 0 && ic == 0 && (tile) < 64)                                       \
       p.trace[(tile) * 48 + (slot)] = clock64();                                                     \
   } while (0)
 
@@ -85,7 +87,7 @@ struct FmhaCfg {
   static constexpr int TAIL_BYTES = 128 * TAIL * 2;
   static constexpr int TILE = NS * SLAB + TAIL_BYTES;     // one Q / K / V tile
   static constexpr int STAGES = HD == 64 ? 4 : 3;
-  static constexpr int BAR_BYTES = (1 + 4 * STAGES + 3 * FM_SBUFS + 1 + 1) * 8 + 16;
+  static constexpr int BAR_BYTES = (1 + 4 * STAGES + 3 * FM_SBUFS + 1 + 1 + 2) * 8 + 16;
   static_assert(TAIL == 0 || TAIL == 16, "head_dim must be 64, 80 or 128");
   static constexpr int smem_bytes(int table_floats) {
     return 1024 + TILE * (1 + 2 * STAGES) + (table_floats + fm_xch_floats(HD)) * 4 + BAR_BYTES;
@@ -135,7 +137,7 @@ __device__ __forceinline__ void fmha_issue_pv(uint32_t o_tmem, uint32_t p_tmem, 
 // The TPR threads of a row take the same decision (same mx, same history); thread `part` rescales the O chunks c with
 // c % TPR == part.
 template <int HD, int TPR>
-__device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, float& l_run, uint32_t o_taddr,
+__device__ __forceinline__ void fmha_rescale(int j, int g, float mx, float& m_used, float& l_run, uint32_t o_taddr,
                                              uint64_t* pv_done, int part) {
   bool grow;
   float alpha = 1.f;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, flo
   if (__any_sync(0xffffffffu, grow)) {
     // O holds tiles 0..j-1.  One barrier per S buffer: Q K^T runs FM_SBUFS tiles ahead, so S_j having landed only
     // proves P V of tile j - FM_SBUFS complete, and a single barrier's parity could be two completions behind
-    mbar_wait(&pv_done[(j - 1) % FM_SBUFS], static_cast<uint32_t>((j - 1) / FM_SBUFS) & 1u);
+    mbar_wait(&pv_done[(g - 1) % FM_SBUFS], static_cast<uint32_t>((g - 1) / FM_SBUFS) & 1u);   // g = running tile index
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < HD / 16; ++c) {
@@ -167,6 +169,26 @@ __device__ __forceinline__ void fmha_rescale(int j, float mx, float& m_used, flo
       }
     }
   }
+}
+
+// A CTA works through the items blockIdx.x, blockIdx.x + gridDim.x, ... (one item per CTA for the rel-pos variants); the
+// pipelines run on across items: the K / V ring and the three S buffers are indexed by running tile counters, so the
+// next item's Q / K / V loads and first Q K^T run under the current item's last tiles and its epilogue.
+struct FmItem {
+  int m0, h, b, n_tiles;
+};
+__device__ __forceinline__ FmItem fm_item(const FmhaParams& p, int item) {
+  FmItem w;
+  const int x = item % p.n_qt;
+  const int rest = item / p.n_qt;
+  w.h = rest % p.heads;
+  w.b = rest / p.heads;
+  const int qt = p.causal ? (p.n_qt - 1 - x) : x;   // heavy tiles first
+  w.m0 = qt * FM_BM;
+  int k_end = p.seq_k;
+  if (p.causal) k_end = min(k_end, p.q_pos0 + w.m0 + FM_BM);
+  w.n_tiles = (k_end + FM_BN - 1) / FM_BN;
+  return w;
 }
 
 // RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
@@ -200,18 +222,12 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   uint64_t* pv_done = p_full + FM_SBUFS;
   uint64_t* pro_done = pv_done + FM_SBUFS;
   uint64_t* o_final = pro_done + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
+  uint64_t* q_free = o_final + 1;    // the item's last Q K^T has completed: the Q tile may be overwritten
+  uint64_t* o_free = q_free + 1;     // the item's O has been read back: the next item's P V may overwrite it
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_qt = gridDim.x;
-  const int qt = p.causal ? (n_qt - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);  // heavy tiles first
-  const int m0 = qt * FM_BM;
-  const int h = blockIdx.y, b = blockIdx.z;
-
-  int k_end = p.seq_k;
-  if (p.causal) k_end = min(k_end, p.q_pos0 + m0 + FM_BM);
-  const int n_tiles = (k_end + FM_BN - 1) / FM_BN;
   constexpr int kRP = RP ? 1 : 0;
 
   if (warp == FM_TMA_WARP && lane == 0) {
@@ -232,6 +248,8 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     for (int i = 0; i < FM_SBUFS; ++i) mbar_init(&pv_done[i], 1);
     mbar_init(pro_done, 128 * TPR);
     mbar_init(o_final, 1);
+    mbar_init(q_free, 1);
+    mbar_init(o_free, 128 * TPR);
     fence_mbar_init();
   }
   if (warp == FM_MMA_WARP) tmem_alloc<1>(tmem_ptr, FM_TMEM_COLS);
@@ -245,44 +263,51 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
   if (warp == FM_TMA_WARP) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(q_full, C::TILE);
+      int kv_base = kRP;
+      for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+        const FmItem w = fm_item(p, item);
+        const int m0 = w.m0, h = w.h, b = w.b, n_tiles = w.n_tiles;
+        if (ic > 0) mbar_wait(q_free, static_cast<uint32_t>(ic - 1) & 1u);
+        mbar_expect_tx(q_full, C::TILE);
 #pragma unroll
-      for (int s = 0; s < C::NS; ++s) tma_load_4d(sQ + s * C::SLAB, &maps.q, q_full, s * 64, m0, h, b);
-      if constexpr (C::TAIL != 0) tma_load_4d(sQ + C::NS * C::SLAB, &maps.qt, q_full, C::NS * 64, m0, h, b);
-      if constexpr (RP != 0) {
-        // pipeline item 0: the two rel-pos tables take the place of a K and a V tile (rows >= 2S-1 are zero-filled)
-        uint8_t* sk = sKV;
-        uint8_t* sv = sk + C::TILE;
-        mbar_expect_tx(&k_full[0], C::TILE);
+        for (int s = 0; s < C::NS; ++s) tma_load_4d(sQ + s * C::SLAB, &maps.q, q_full, s * 64, m0, h, b);
+        if constexpr (C::TAIL != 0) tma_load_4d(sQ + C::NS * C::SLAB, &maps.qt, q_full, C::NS * 64, m0, h, b);
+        if constexpr (RP != 0) {
+          // pipeline slot 0: the two rel-pos tables take the place of a K and a V tile (rows >= 2S-1 are zero-filled)
+          uint8_t* sk = sKV;
+          uint8_t* sv = sk + C::TILE;
+          mbar_expect_tx(&k_full[0], C::TILE);
 #pragma unroll
-        for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.rh, &k_full[0], s * 64, 0, 0, 0);
-        if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.rht, &k_full[0], C::NS * 64, 0, 0, 0);
-        mbar_expect_tx(&v_full[0], C::TILE);
+          for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.rh, &k_full[0], s * 64, 0, 0, 0);
+          if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.rht, &k_full[0], C::NS * 64, 0, 0, 0);
+          mbar_expect_tx(&v_full[0], C::TILE);
 #pragma unroll
-        for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.rw, &v_full[0], s * 64, 0, 0, 0);
-        if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.rwt, &v_full[0], C::NS * 64, 0, 0, 0);
-      }
-      // K runs one tile ahead of V: a K slot is free again once its QK^T has completed, a V slot once its P V has
-      auto load_k = [&](int j) {
-        const int it = j + kRP, st = it % ST;
-        mbar_wait(&k_empty[st], (static_cast<uint32_t>(it / ST) & 1u) ^ 1u);
-        FMHA_TRACE(j, 0);
-        uint8_t* sk = sKV + st * 2 * C::TILE;
-        mbar_expect_tx(&k_full[st], C::TILE);
+          for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.rw, &v_full[0], s * 64, 0, 0, 0);
+          if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.rwt, &v_full[0], C::NS * 64, 0, 0, 0);
+        }
+        // K runs one tile ahead of V: a K slot is free again once its QK^T has completed, a V slot once its P V has
+        auto load_k = [&](int j) {
+          const int it = kv_base + j, st = it % ST;
+          mbar_wait(&k_empty[st], (static_cast<uint32_t>(it / ST) & 1u) ^ 1u);
+          FMHA_TRACE(j, 0);
+          uint8_t* sk = sKV + st * 2 * C::TILE;
+          mbar_expect_tx(&k_full[st], C::TILE);
 #pragma unroll
-        for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.k, &k_full[st], s * 64, j * FM_BN, h, b);
-        if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.kt, &k_full[st], C::NS * 64, j * FM_BN, h, b);
-      };
-      load_k(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) load_k(j + 1);
-        const int it = j + kRP, st = it % ST;
-        mbar_wait(&v_empty[st], (static_cast<uint32_t>(it / ST) & 1u) ^ 1u);
-        uint8_t* sv = sKV + st * 2 * C::TILE + C::TILE;
-        mbar_expect_tx(&v_full[st], C::TILE);
+          for (int s = 0; s < C::NS; ++s) tma_load_4d(sk + s * C::SLAB, &maps.k, &k_full[st], s * 64, j * FM_BN, h, b);
+          if constexpr (C::TAIL != 0) tma_load_4d(sk + C::NS * C::SLAB, &maps.kt, &k_full[st], C::NS * 64, j * FM_BN, h, b);
+        };
+        load_k(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          if (j + 1 < n_tiles) load_k(j + 1);
+          const int it = kv_base + j, st = it % ST;
+          mbar_wait(&v_empty[st], (static_cast<uint32_t>(it / ST) & 1u) ^ 1u);
+          uint8_t* sv = sKV + st * 2 * C::TILE + C::TILE;
+          mbar_expect_tx(&v_full[st], C::TILE);
 #pragma unroll
-        for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.v, &v_full[st], s * 64, j * FM_BN, h, b);
-        if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.vt, &v_full[st], C::NS * 64, j * FM_BN, h, b);
+          for (int s = 0; s < C::NS; ++s) tma_load_4d(sv + s * C::SLAB, &maps.v, &v_full[st], s * 64, j * FM_BN, h, b);
+          if constexpr (C::TAIL != 0) tma_load_4d(sv + C::NS * C::SLAB, &maps.vt, &v_full[st], C::NS * 64, j * FM_BN, h, b);
+        }
+        kv_base += n_tiles;
       }
     }
   } else if (warp == FM_MMA_WARP) {
@@ -290,35 +315,43 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     if (elect_one()) {
       const uint32_t q_s = smem_u32(sQ);
       const uint32_t kv_s = smem_u32(sKV);
-      mbar_wait(q_full, 0);
-      if constexpr (RP != 0) {
-        mbar_wait(&k_full[0], 0);
-        mbar_wait(&v_full[0], 0);
-        tc_fence_after();
-        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S, q_s, kv_s);                       // Ph = Q Rh^T
-        umma_commit<1>(&s_full[0]);
-        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + FM_BN, q_s, kv_s + C::TILE);     // Pw = Q Rw^T
-        umma_commit<1>(&s_full[1]);
-        umma_commit<1>(&k_empty[0]);
-        umma_commit<1>(&v_empty[0]);
-        mbar_wait(pro_done, 0);  // softmax threads have moved both tables out of TMEM
-      }
-      // S_j goes to buffer j % 3 as soon as P_{j-3} V_{j-3} has completed (pv_done of that buffer), so Q K^T runs up
-      // to three tiles ahead of the softmax and a group finds its next S_{j+2} complete when it hands in P_j.
-      // Q K^T and P V are issued by two different warps: the issuing thread stalls on its uniform registers until
-      // the tensor pipe has taken the instructions over, and one thread doing both spent ~1300 cycles per tile on
-      // 512 cycles of tensor work.
-      for (int j = 0; j < n_tiles; ++j) {
-        const int it = j + kRP, st = it % ST;
-        mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
-        FMHA_TRACE(j, 1);
-        if (j >= FM_SBUFS)
-          mbar_wait(&pv_done[j % FM_SBUFS], static_cast<uint32_t>(j / FM_SBUFS - 1) & 1u);   // P_{j-3} consumed
-        tc_fence_after();
-        fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + (j % FM_SBUFS) * FM_BN, q_s, kv_s + st * 2 * C::TILE);
-        umma_commit<1>(&s_full[j % FM_SBUFS]);
-        umma_commit<1>(&k_empty[st]);
-        FMHA_TRACE(j, 2);
+      int kv_base = kRP, g_base = 0;
+      for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+        const int n_tiles = fm_item(p, item).n_tiles;
+        mbar_wait(q_full, static_cast<uint32_t>(ic) & 1u);
+        if constexpr (RP != 0) {
+          mbar_wait(&k_full[0], 0);
+          mbar_wait(&v_full[0], 0);
+          tc_fence_after();
+          fmha_issue_qk<T, HD>(tmem_base + FM_COL_S, q_s, kv_s);                       // Ph = Q Rh^T
+          umma_commit<1>(&s_full[0]);
+          fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + FM_BN, q_s, kv_s + C::TILE);     // Pw = Q Rw^T
+          umma_commit<1>(&s_full[1]);
+          umma_commit<1>(&k_empty[0]);
+          umma_commit<1>(&v_empty[0]);
+          mbar_wait(pro_done, 0);  // softmax threads have moved both tables out of TMEM
+        }
+        // S of the g-th tile this CTA processes goes to buffer g % 3 as soon as P V of tile g - 3 has completed (pv_done
+        // of that buffer), so Q K^T runs up to three tiles ahead of the softmax -- across item boundaries too -- and a
+        // softmax group finds its next S complete when it hands in P.
+        // Q K^T and P V are issued by two different warps: the issuing thread stalls on its uniform registers until
+        // the tensor pipe has taken the instructions over, and one thread doing both spent ~1300 cycles per tile on
+        // 512 cycles of tensor work.
+        for (int j = 0; j < n_tiles; ++j) {
+          const int it = kv_base + j, st = it % ST;
+          const int g = g_base + j, sb = g % FM_SBUFS;
+          mbar_wait(&k_full[st], static_cast<uint32_t>(it / ST) & 1u);
+          FMHA_TRACE(j, 1);
+          if (g >= FM_SBUFS) mbar_wait(&pv_done[sb], static_cast<uint32_t>(g / FM_SBUFS - 1) & 1u);   // P of tile g - 3 consumed
+          tc_fence_after();
+          fmha_issue_qk<T, HD>(tmem_base + FM_COL_S + sb * FM_BN, q_s, kv_s + st * 2 * C::TILE);
+          umma_commit<1>(&s_full[sb]);
+          umma_commit<1>(&k_empty[st]);
+          FMHA_TRACE(j, 2);
+        }
+        umma_commit<1>(q_free);
+        kv_base += n_tiles;
+        g_base += n_tiles;
       }
     }
   } else if (warp == FM_PV_WARP) {
@@ -326,21 +359,28 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     if (elect_one()) {
       const uint32_t kv_s = smem_u32(sKV);
       const uint32_t o_tmem = tmem_base + FM_COL_O;
-      for (int j = 0; j < n_tiles; ++j) {
-        const int it = j + kRP, st = it % ST;
-        mbar_wait(&v_full[st], static_cast<uint32_t>(it / ST) & 1u);
-        FMHA_TRACE(j, 3);
-        mbar_wait(&p_full[j % FM_SBUFS], static_cast<uint32_t>(j / FM_SBUFS) & 1u);
-        FMHA_TRACE(j, 4);
-        tc_fence_after();
-        fmha_issue_pv<T, HD>(o_tmem, tmem_base + FM_COL_S + (j % FM_SBUFS) * FM_BN, kv_s + st * 2 * C::TILE + C::TILE,
-                             j == 0);
-        umma_commit<1>(&v_empty[st]);
-        umma_commit<1>(&pv_done[j % FM_SBUFS]);
-        FMHA_TRACE(j, 14);
+      int kv_base = kRP, g_base = 0;
+      for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+        const int n_tiles = fm_item(p, item).n_tiles;
+        if (ic > 0) mbar_wait(o_free, static_cast<uint32_t>(ic - 1) & 1u);   // the previous item's O is in registers
+        for (int j = 0; j < n_tiles; ++j) {
+          const int it = kv_base + j, st = it % ST;
+          const int g = g_base + j, sb = g % FM_SBUFS;
+          mbar_wait(&v_full[st], static_cast<uint32_t>(it / ST) & 1u);
+          FMHA_TRACE(j, 3);
+          mbar_wait(&p_full[sb], static_cast<uint32_t>(g / FM_SBUFS) & 1u);
+          FMHA_TRACE(j, 4);
+          tc_fence_after();
+          fmha_issue_pv<T, HD>(o_tmem, tmem_base + FM_COL_S + sb * FM_BN, kv_s + st * 2 * C::TILE + C::TILE, j == 0);
+          umma_commit<1>(&v_empty[st]);
+          umma_commit<1>(&pv_done[sb]);
+          FMHA_TRACE(j, 14);
+        }
+        // the epilogue needs its own barrier: a softmax thread can be several completions behind pv_done
+        umma_commit<1>(o_final);
+        kv_base += n_tiles;
+        g_base += n_tiles;
       }
-      // the epilogue needs its own single-phase barrier: a softmax thread can be several completions behind pv_done
-      umma_commit<1>(o_final);
     }
   }
   } else {
@@ -365,7 +405,6 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     const int part = ALT ? 0 : grp;              // which CPT-column part of the tile
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;            // row inside the tile
-    const int qrow = m0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t o_taddr = tmem_base + lane_off + FM_COL_O;
     const float sl2 = p.scale_log2;
@@ -379,6 +418,11 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
 #define FMHA_PUB_ARRIVE(g) asm volatile("bar.arrive %0, %1;" ::"r"(1 + 2 * quad + (g)), "n"(64) : "memory")
 #define FMHA_PUB_SYNC(g) asm volatile("bar.sync %0, %1;" ::"r"(1 + 2 * quad + (g)), "n"(64) : "memory")
 
+    int g_base = 0;                              // tiles this CTA has processed before the current item
+    for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+    const FmItem w = fm_item(p, item);
+    const int m0 = w.m0, h = w.h, b = w.b, n_tiles = w.n_tiles;
+    const int qrow = m0 + row;
     if constexpr (RP != 0) {
       constexpr float kLog2e = 1.4426950408889634f;
       const int qr = min(qrow, p.seq_q - 1);
@@ -416,12 +460,14 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
 
     float m_used = 0.f, l_run = 0.f;
     bool first_mine = true;                      // ALT: l_run is still empty
-    for (int j = ALT ? grp : 0; j < n_tiles; j += ALT ? 2 : 1) {
-      const int buf = j % FM_SBUFS;
+    // ALT: the groups alternate on the CTA's running tile count, so the alternation carries on across items
+    for (int j = ALT ? ((grp ^ g_base) & 1) : 0; j < n_tiles; j += ALT ? 2 : 1) {
+      const int g = g_base + j;                  // running tile index: S buffer and barrier phases
+      const int buf = g % FM_SBUFS;
       const uint32_t ts = tmem_base + lane_off + FM_COL_S + buf * FM_BN;
       const int key0 = j * FM_BN + CPT * part;   // first key of this thread's part
       const bool need_mask = (j * FM_BN + FM_BN > p.seq_k) || (p.causal && (j * FM_BN + FM_BN - 1 > p.q_pos0 + m0));
-      mbar_wait(&s_full[buf], static_cast<uint32_t>(j / FM_SBUFS + (buf < 2 ? kRP : 0)) & 1u);
+      mbar_wait(&s_full[buf], static_cast<uint32_t>(g / FM_SBUFS + (buf < 2 ? kRP : 0)) & 1u);
       if (lane == 0) FMHA_TRACE(j, 32 + warp);
       tc_fence_after();
       uint32_t r[CPT];
@@ -501,7 +547,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         mx = fmaxf(mx, xch[(xs + (part ^ 1)) * FM_BM + row]);
         if constexpr (!kXchDouble) FMHA_ROW_SYNC();   // single slot: read before the next tile's write
         if (lane == 0) FMHA_TRACE(j, 24 + warp);
-        fmha_rescale<HD, 2>(j, mx, m_used, l_run, o_taddr, pv_done, part);
+        fmha_rescale<HD, 2>(j, g, mx, m_used, l_run, o_taddr, pv_done, part);
       } else {
         // ---- the maximum in use: take it over from tile j - 1 (the other group), grow it lazily, hand it on ----
         float m_prev = 0.f;
@@ -525,7 +571,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         m_used = m_new;
         if (__any_sync(0xffffffffu, grow)) {
           const float alpha = grow ? ex2_approx(m_prev - m_new) : 1.f;
-          mbar_wait(&pv_done[(j - 1) % FM_SBUFS], static_cast<uint32_t>((j - 1) / FM_SBUFS) & 1u);  // O holds tiles 0..j-1
+          mbar_wait(&pv_done[(g - 1) % FM_SBUFS], static_cast<uint32_t>((g - 1) / FM_SBUFS) & 1u);  // O holds tiles 0..j-1
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < kOChunks; ++c) {
@@ -598,19 +644,19 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
     } else {
       // the group of the last tile holds the final maximum; the other one converts its partial sum to it
-      const int gl = (n_tiles - 1) & 1;
+      const int gl = (g_base + n_tiles - 1) & 1;
       if (grp != gl) {
         FMHA_PUB_SYNC(gl);
         const float m_fin = xch[row];
         xch[FM_BM + row] = first_mine ? 0.f : l_run * ex2_approx(m_used - m_fin);
         FMHA_PUB_ARRIVE(grp);
         FMHA_PUB_SYNC(gl);
-        inv = xch[row];
+        inv = xch[FM_BM + row];
       } else {
         FMHA_PUB_SYNC(grp ^ 1);
         const float l_tot = l_run + xch[FM_BM + row];
         inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-        xch[row] = inv;
+        xch[FM_BM + row] = inv;   // not the hand-over slot: the next item's first tile may write that one any time
         FMHA_PUB_ARRIVE(grp);
       }
     }
@@ -623,7 +669,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         orow = static_cast<T*>(p.o) + b * p.o_bs + static_cast<int64_t>(qrow) * p.o_rs + h * p.o_hs;
       }
     }
-    mbar_wait(o_final, 0);
+    mbar_wait(o_final, static_cast<uint32_t>(ic) & 1u);
     tc_fence_after();
     {
       // this group's chunks (c % 2 == grp): all TMEM loads in flight before the first store
@@ -635,6 +681,8 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         if (c < kOChunks) tmem_ld_32x16(o_taddr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&r[i * 16]));
       }
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);                       // O is in registers: the next item's P V may start
       if (orow) {
 #pragma unroll
         for (int i = 0; i < kMine; ++i) {
@@ -654,6 +702,8 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
         }
       }
     }
+    g_base += n_tiles;
+    }   // items
 #undef FMHA_ROW_SYNC
 #undef FMHA_PUB_ARRIVE
 #undef FMHA_PUB_SYNC
@@ -691,7 +741,9 @@ static int fmha_launch_emu(const FmhaMaps& maps, const FmhaParams& p, int batch,
   auto kern = fmha_tcgen05_kernel<T, HD, RP, EMU, ALT>;
   static SmemOptIn opt_in;   // per device (common.cuh)
   { const int _st = ensure_dynamic_smem(kern, smem, opt_in); if (_st != OK) return _st; }
-  dim3 grid((p.seq_q + FM_BM - 1) / FM_BM, heads, batch);
+  // bias-free: one CTA per SM works through the items; rel-pos: one item per CTA (its table prologue runs once)
+  const int grid = (RP == 0 && p.n_items > p.sms) ? p.sms : p.n_items;
+  (void)batch; (void)heads;
   kern<<<grid, fm_threads(HD), smem, stream>>>(maps, p);
   return check_cuda(cudaGetLastError(), "fmha_tcgen05 launch");
 }
@@ -741,6 +793,10 @@ int fmha_run(Context* ctx, const AttnArgs& a, const void* rel_h, const void* rel
   p.seq_q = a.seq_q; p.seq_k = a.seq_k; p.causal = a.causal; p.q_pos0 = a.q_pos0;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.S = S;
+  p.n_qt = (a.seq_q + FM_BM - 1) / FM_BM;
+  p.heads = a.heads;
+  p.n_items = p.n_qt * a.heads * a.batch;
+  p.sms = ctx->sm_count;
   p.trace = static_cast<long long*>(ctx->fmha_trace);
   int st = ERR_UNSUPPORTED;
 #define ULLAVA_FMHA(TT)                                                                                   \
