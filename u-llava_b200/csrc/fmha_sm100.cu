@@ -8,7 +8,9 @@
 //   * SAM ViT-H windowed (14x14) and global (64x64) attention with decomposed relative-position bias,
 //     hd 80                                               segment_anything/modeling/image_encoder.py:196-260,355-392
 //
-// One CTA = one 128-row query tile of one (batch, head), 384 threads in three warpgroups:
+// Work item = one 128-row query tile of one (batch, head).  Without bias the kernel is persistent: one CTA per SM works
+// through the items blockIdx.x, blockIdx.x + gridDim.x, ... and all pipelines run on across items (fm_item below); with the
+// rel-pos bias one CTA per item.  384 threads in three warpgroups:
 //   warps 0-7   softmax, two warps per TMEM lane quadrant (w and w + 4; registers raised to 232 with setmaxnreg):
 //                 without bias the two take ALTERNATING key tiles, one thread per row (the row maximum in use is handed
 //                 from tile to tile through shared memory, partial row sums are added at the end), so one warp's
