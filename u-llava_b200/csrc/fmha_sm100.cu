@@ -194,6 +194,7 @@ __device__ __forceinline__ FmItem fm_item(const FmhaParams& p, int item) {
 }
 
 // RP: 0 = no bias (causal allowed), 1 = rel-pos bias on a generic S x S grid, 2 = rel-pos bias, S == 64
+// (RP != 0: one item per CTA -- the item loops below then have a static trip count of one and carry no state)
 // EMU: of every 8 pairs of exponentials, EMU are computed on the FMA pipe (ex2_fma2) and 8 - EMU on the MUFU
 template <typename T, int HD, int RP, int EMU, bool ALT>
 __global__ void __launch_bounds__(fm_threads(HD), 1)
@@ -266,7 +267,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int kv_base = kRP;
-      for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+      for (int item = blockIdx.x, ic = 0; RP != 0 ? ic < 1 : item < p.n_items; item += gridDim.x, ++ic) {
         const FmItem w = fm_item(p, item);
         const int m0 = w.m0, h = w.h, b = w.b, n_tiles = w.n_tiles;
         if (ic > 0) mbar_wait(q_free, static_cast<uint32_t>(ic - 1) & 1u);
@@ -318,7 +319,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       const uint32_t q_s = smem_u32(sQ);
       const uint32_t kv_s = smem_u32(sKV);
       int kv_base = kRP, g_base = 0;
-      for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+      for (int item = blockIdx.x, ic = 0; RP != 0 ? ic < 1 : item < p.n_items; item += gridDim.x, ++ic) {
         const int n_tiles = fm_item(p, item).n_tiles;
         mbar_wait(q_full, static_cast<uint32_t>(ic) & 1u);
         if constexpr (RP != 0) {
@@ -362,7 +363,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
       const uint32_t kv_s = smem_u32(sKV);
       const uint32_t o_tmem = tmem_base + FM_COL_O;
       int kv_base = kRP, g_base = 0;
-      for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+      for (int item = blockIdx.x, ic = 0; RP != 0 ? ic < 1 : item < p.n_items; item += gridDim.x, ++ic) {
         const int n_tiles = fm_item(p, item).n_tiles;
         if (ic > 0) mbar_wait(o_free, static_cast<uint32_t>(ic - 1) & 1u);   // the previous item's O is in registers
         for (int j = 0; j < n_tiles; ++j) {
@@ -421,7 +422,7 @@ fmha_tcgen05_kernel(const __grid_constant__ FmhaMaps maps, const FmhaParams p) {
 #define FMHA_PUB_SYNC(g) asm volatile("bar.sync %0, %1;" ::"r"(1 + 2 * quad + (g)), "n"(64) : "memory")
 
     int g_base = 0;                              // tiles this CTA has processed before the current item
-    for (int item = blockIdx.x, ic = 0; item < p.n_items; item += gridDim.x, ++ic) {
+    for (int item = blockIdx.x, ic = 0; RP != 0 ? ic < 1 : item < p.n_items; item += gridDim.x, ++ic) {
     const FmItem w = fm_item(p, item);
     const int m0 = w.m0, h = w.h, b = w.b, n_tiles = w.n_tiles;
     const int qrow = m0 + row;
