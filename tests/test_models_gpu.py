@@ -381,6 +381,44 @@ def test_llama_layer_full_width(ctx, dtype):
     assert (two.float() - final.float()).abs().max().item() < tol(dtype, 3e-2)
 
 
+@pytest.mark.parametrize("dtype", DT)
+def test_llama_prefill_rope_in_the_qkv_epilogue_equals_the_separate_pass(ctx, dtype):
+    """At LLaMA-7B geometry with enough rows for the CTA-pair GEMM, RoPE and the KV-cache write run in the epilogue of
+    the qkv projection (gemm_sm100.cu EPI_QKV_ROPE; hf:models/llama/modeling_llama.py:137-168, 240-262).  One sample at
+    a time (608 rows: below the pair kernel's threshold) takes the separate rope_kvcache pass: same arithmetic, so the
+    hidden states and the cache rows must agree to the last bit or two."""
+    from transformers import LlamaConfig, LlamaModel
+    from models.engine import LlamaStack
+    _, meta = load_golden("llama_layer_full")
+    lc = LlamaConfig(vocab_size=64, hidden_size=4096, intermediate_size=11008, num_hidden_layers=1,
+                     num_attention_heads=32, num_key_value_heads=32, rms_norm_eps=1e-6)
+    mod = LlamaModel(lc).eval()
+    mod.load_state_dict(synth_state_dict(meta["shapes"], meta["seed"]), strict=True)
+    mod = mod.cuda().to(dtype)
+    head = torch.nn.Linear(4096, 64, bias=False).cuda().to(dtype)
+    stack = LlamaStack(mod, head)
+    B, L = 5, 608
+    x = torch.stack([synth_normal("llama_x", (L, 4096), seed=3 + i) for i in range(B)]).cuda().to(dtype)
+    cache = stack.new_cache(B, L + 8)
+    fused, _ = stack.run(ctx, x.view(B * L, 4096).clone(), cache, B, L)
+    for i in range(B):
+        ci = stack.new_cache(1, L + 8)
+        one, _ = stack.run(ctx, x[i].clone(), ci, 1, L)
+        # the cache rows are the epilogue's direct output: at most the last bit (FMA contraction may differ)
+        for got, ref in ((cache.k, ci.k), (cache.v, ci.v)):
+            d = (got[0, i, :, :L].float() - ref[0, 0, :, :L].float()).abs()
+            assert d.max().item() <= tol(dtype, 4e-3) and (d > 0).float().mean().item() < 0.02
+        # ... which the rest of the layer (softmax, two more GEMMs) turns into a few ulps of the hidden state
+        assert (one.float() - fused.view(B, L, 4096)[i].float()).abs().max().item() <= tol(dtype, 1.5e-2)
+    # chunked prefill deep into the cache (pos0 > 0) through the fused epilogue == one shot
+    cache2 = stack.new_cache(B, L + 8)
+    fa, _ = stack.run(ctx, x[:, :320].reshape(B * 320, 4096).clone(), cache2, B, 320)
+    fb, _ = stack.run(ctx, x[:, 320:].reshape(B * 288, 4096).clone(), cache2, B, 288)
+    two = torch.cat([fa.view(B, 320, 4096), fb.view(B, 288, 4096)], 1)
+    assert (two.float() - fused.view(B, L, 4096).float()).abs().max().item() < tol(dtype, 3e-2)
+    assert (cache2.k[0, :, :, :L].float() - cache.k[0, :, :, :L].float()).abs().max().item() <= tol(dtype, 4e-3)
+
+
 def test_right_padding_and_text_only_rows(ctx):
     """Batches mixing image rows and text-only rows (reference :213-220) and right padding."""
     dtype = torch.bfloat16

@@ -51,6 +51,7 @@ struct GemmKernelParams {
   int splits;         // >1: D is an fp32 workspace [splits][M][N], epilogue deferred
   int group_m;        // rasterisation group: M tiles swept together over N (their A panel stays L2 resident)
   uint64_t hint_a, hint_b;  // L2 eviction priority of the A / B tile loads (CTA-pair kernel)
+  RopeFuse rope;            // EPI_QKV_ROPE only
 };
 
 template <int BN, int STAGES>
@@ -405,6 +406,66 @@ struct PairSmem {
   static constexpr int kTotal = kBarOffset + (2 * kPairStages + 4) * 8 + 16 + 1024;
 };
 
+// EPI_QKV_ROPE: the prefill qkv projection of LLaMA (hf:models/llama/modeling_llama.py:137-168, 240-262) with RoPE and
+// the KV-cache write in the epilogue instead of a separate pass over q / k / v (rope_kvcache_kernel, elementwise.cu).
+// `lo` / `hi` are the fp32 accumulators of one row for head dims [d0, d0 + 32) and [d0 + 64, d0 + 96) of one head (d0 =
+// 0 or 32): exactly a rotation pair.  Same arithmetic as the separate kernel: the projection is rounded to the 16-bit
+// type first (that is what the kernel read back), the rotation is fp32, one rounding at the end.  q goes to D (the
+// packed qkv buffer the attention kernel reads), rotated k and v go straight to their cache rows.
+template <typename T>
+__device__ __forceinline__ void rope_pair_store(const uint32_t (&lo)[32], const uint32_t (&hi)[32],
+                                                const GemmKernelParams& p, int row, int n0) {
+  const RopeFuse& r = p.rope;
+  const int hidden = r.heads * 128;
+  const int region = n0 / hidden;                 // 0 = q, 1 = k, 2 = v
+  const int col = n0 - region * hidden;
+  const int head = col >> 7, d0 = col & 127;
+  const int b = row / r.seq, t = row - b * r.seq, pos = r.pos0 + t;
+  T* dst;
+  if (region == 0) {
+    dst = reinterpret_cast<T*>(p.D) + static_cast<int64_t>(row) * p.ldd + n0;
+  } else {
+    dst = reinterpret_cast<T*>(region == 1 ? r.k_cache : r.v_cache) + b * r.cache_bs + head * r.cache_hs +
+          static_cast<int64_t>(pos) * 128 + d0;
+  }
+  if (region == 2) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      uint4 w0, w1;
+      w0.x = pack2<T>(__uint_as_float(lo[k]), __uint_as_float(lo[k + 1]));
+      w0.y = pack2<T>(__uint_as_float(lo[k + 2]), __uint_as_float(lo[k + 3]));
+      w0.z = pack2<T>(__uint_as_float(lo[k + 4]), __uint_as_float(lo[k + 5]));
+      w0.w = pack2<T>(__uint_as_float(lo[k + 6]), __uint_as_float(lo[k + 7]));
+      w1.x = pack2<T>(__uint_as_float(hi[k]), __uint_as_float(hi[k + 1]));
+      w1.y = pack2<T>(__uint_as_float(hi[k + 2]), __uint_as_float(hi[k + 3]));
+      w1.z = pack2<T>(__uint_as_float(hi[k + 4]), __uint_as_float(hi[k + 5]));
+      w1.w = pack2<T>(__uint_as_float(hi[k + 6]), __uint_as_float(hi[k + 7]));
+      *reinterpret_cast<uint4*>(dst + k) = w0;
+      *reinterpret_cast<uint4*>(dst + 64 + k) = w1;
+    }
+    return;
+  }
+  const float* cs = r.cos_t + static_cast<int64_t>(pos) * 64 + d0;
+  const float* sn = r.sin_t + static_cast<int64_t>(pos) * 64 + d0;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const float4 c0 = *reinterpret_cast<const float4*>(cs + k), c1 = *reinterpret_cast<const float4*>(cs + k + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(sn + k), s1 = *reinterpret_cast<const float4*>(sn + k + 4);
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t ol[4], ou[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = unpack2<T>(pack2<T>(__uint_as_float(lo[k + 2 * e]), __uint_as_float(lo[k + 2 * e + 1])));
+      const float2 c = unpack2<T>(pack2<T>(__uint_as_float(hi[k + 2 * e]), __uint_as_float(hi[k + 2 * e + 1])));
+      ol[e] = pack2<T>(a.x * cc[2 * e] - c.x * ss[2 * e], a.y * cc[2 * e + 1] - c.y * ss[2 * e + 1]);
+      ou[e] = pack2<T>(c.x * cc[2 * e] + a.x * ss[2 * e], c.y * cc[2 * e + 1] + a.y * ss[2 * e + 1]);
+    }
+    *reinterpret_cast<uint4*>(dst + k) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<uint4*>(dst + 64 + k) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+  }
+}
+
 template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -527,6 +588,26 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // is barely longer than its epilogue, so every cycle the accumulator is held stalls the tensor pipe).
       // tools/bench_gemm.py SHAPES=b32: +1 ... +3.6 % per shape (SAM qkv 1373 -> 1423, LLaMA gate/up 1621 -> 1680 TFLOP/s);
       // neutral inside the power-capped step (same-box A/B: 709.8 / 711.3 vs 708.8 / 712.8 ms).
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        // chunks (c, c + 2) are the two halves of a rotation pair: this warp takes c = half and c = half + 4
+#pragma unroll 1
+        for (int pr = 0; pr < 2; ++pr) {
+          const int c = half + 4 * pr;
+          uint32_t lo[32], hi[32];
+          tmem_ld_32x32(taddr + c * 32, lo);
+          tmem_ld_32x32(taddr + (c + 2) * 32, hi);
+          tmem_ld_wait();
+          if (pr == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+              else mbar_arrive_cluster(&tmem_empty[acc], 0);
+            }
+          }
+          if (row_ok) rope_pair_store<T>(lo, hi, p, row, n_blk * BN + c * 32);
+        }
+      } else {
       constexpr int kChunks = BN / 64;
       uint32_t rn[32];
       tmem_ld_32x32(taddr + half * 32, rn);
@@ -549,6 +630,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         const int n0 = n_blk * BN + c * 32;
         if (row_ok && n0 < p.N) epilogue_store<T, EPI, 32>(v, p, bias, resid, false, 0, row, n0);
+      }
       }
       if (++acc == 2) {
         acc = 0;
@@ -698,6 +780,7 @@ static int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb
     case EPI_GELU: return launch_pair<T, EPI_GELU>(ta, tb, p, grid, stream);
     case EPI_QUICK_GELU: return launch_pair<T, EPI_QUICK_GELU>(ta, tb, p, grid, stream);
     case EPI_SILU_MUL: return launch_pair<T, EPI_SILU_MUL>(ta, tb, p, grid, stream);
+    case EPI_QKV_ROPE: return launch_pair<T, EPI_QKV_ROPE>(ta, tb, p, grid, stream);
     default: set_last_error("gemm: unknown epilogue %d", epi); return ERR_BAD_ARG;
   }
 }
@@ -724,7 +807,16 @@ static int pick_bn_large(int N) {
   return 16;
 }
 
+// Large products run on CTA pairs (256 x 256 tile per two SMs) when there are enough pair tiles to fill the machine.
+bool gemm_pair_eligible(const Context* ctx, int M, int N) {
+  const int sms = ctx->sm_count;
+  return ctx->gemm_pair != 0 && M > 32 && N >= 256 &&
+         static_cast<long long>((M + kPairBM - 1) / kPairBM) * ((N + kPairBN - 1) / kPairBN) >= 2ll * (sms / 2);
+}
+
 int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
+  const RopeFuse* rope = ctx->rope_fuse;   // one-shot: whatever happens below, it never outlives this call
+  ctx->rope_fuse = nullptr;
   ULLAVA_REQUIRE(a.A && a.B && a.D, "gemm: null operand");
   ULLAVA_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   ULLAVA_REQUIRE(a.dtype == DT_BF16 || a.dtype == DT_F16, "gemm: dtype must be bf16/f16");
@@ -781,12 +873,18 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
     set_last_error("gemm: force_splits does not apply to the weight-streaming (M <= 32) path");
     return ERR_BAD_ARG;
   }
+  if (swap && rope) {
+    set_last_error("gemm: the fused RoPE epilogue does not apply to the weight-streaming (M <= 32) path");
+    return ERR_BAD_ARG;
+  }
   if (!swap) {
     ctx->next_w = nullptr;  // the next-weight hint only applies to the weight-streaming kernel
     // CTA-pair kernel (256 x 256 tile per two SMs) for the large products: enough pair tiles to fill the machine
-    const bool pair_ok = !a.force_bn && a.force_splits <= 1 && ctx->gemm_pair != 0 && a.N >= 256 &&
-                         static_cast<long long>((a.M + kPairBM - 1) / kPairBM) * ((a.N + kPairBN - 1) / kPairBN) >=
-                             2ll * (sms / 2);
+    const bool pair_ok = !a.force_bn && a.force_splits <= 1 && gemm_pair_eligible(ctx, a.M, a.N);
+    if (rope && (!pair_ok || a.epilogue != EPI_NONE || a.bias || a.residual || a.out_f32 || a.N != 3 * rope->heads * 128)) {
+      set_last_error("gemm: the fused RoPE epilogue needs the CTA-pair kernel and a plain [rows, 3 * heads * 128] product");
+      return ERR_BAD_ARG;
+    }
     if (pair_ok) {
       p.M = a.M; p.N = a.N; p.K = a.K;
       p.num_m = (a.M + kPairBM - 1) / kPairBM;
@@ -801,8 +899,13 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
       if (st) return st;
       const int tiles = p.num_m * p.num_n;
       const int grid = 2 * (tiles < sms / 2 ? tiles : sms / 2);
-      st = (a.dtype == DT_BF16) ? launch_pair_epi<__nv_bfloat16>(a.epilogue, ta, tb, p, grid, stream)
-                                : launch_pair_epi<__half>(a.epilogue, ta, tb, p, grid, stream);
+      int epi = a.epilogue;
+      if (rope) {
+        p.rope = *rope;
+        epi = EPI_QKV_ROPE;
+      }
+      st = (a.dtype == DT_BF16) ? launch_pair_epi<__nv_bfloat16>(epi, ta, tb, p, grid, stream)
+                                : launch_pair_epi<__half>(epi, ta, tb, p, grid, stream);
       if (st) return st;
       ctx->launches += 1;
       return OK;

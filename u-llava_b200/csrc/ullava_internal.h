@@ -13,6 +13,8 @@ struct ullava_prof_rec {
   int launches;
 };
 
+namespace ullava { struct RopeFuse; }
+
 struct ullava_ctx {
   int device = 0;
   int device_sm_count = 148;  // SMs of the device
@@ -34,6 +36,7 @@ struct ullava_ctx {
   int gemm_hints = 0; // L2 eviction-priority hints on the large-M GEMM operand loads (ULLAVA_GEMM_HINTS=1): measured
                       // counter-productive on B200, see gemm_sm100.cu
   int group_m = 0;    // 0 = default rasterisation group of the large-M GEMM; ULLAVA_GROUP_M overrides at create (tuning)
+  const ullava::RopeFuse* rope_fuse = nullptr;   // see RopeFuse
   void* fmha_trace = nullptr;   // debug: clock64 stamps of CTA (0,0,0) of the next fmha_tcgen05 launches
   void* chain_trace = nullptr;  // debug: globaltimer stamps of the next chain kernels (ullava_debug_chain_trace)
   int attn_impl = 0;  // 0 = pick per shape, 1 = warp-level mma.sync kernels only, 2 = tcgen05/TMEM wherever compiled
@@ -46,6 +49,19 @@ namespace ullava {
 
 using Context = ::ullava_ctx;
 using GemmArgs = ::ullava_gemm_args;
+
+// RoPE + KV-cache scatter fused into the epilogue of the prefill qkv GEMM (gemm_sm100.cu, CTA-pair kernel): set on the
+// context right before that ullava_gemm-shaped call, consumed (and cleared) by gemm_run.  head_dim 128 only.
+struct RopeFuse {
+  const float* cos_t;   // [max_pos][64] fp32
+  const float* sin_t;
+  void* k_cache;        // [batch][heads][max_seq][128], strides in elements
+  void* v_cache;
+  int64_t cache_bs, cache_hs;
+  int seq, pos0, heads;
+};
+constexpr int EPI_QKV_ROPE = 100;   // internal epilogue code of that GEMM
+bool gemm_pair_eligible(const struct ::ullava_ctx* ctx, int M, int N);
 using AttnArgs = ::ullava_attn_args;
 
 enum Epilogue : int {
