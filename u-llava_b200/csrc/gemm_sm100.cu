@@ -586,8 +586,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // goes through the activation and the stores, and the accumulator is handed back to the MMA thread as soon as
       // the LAST load has landed in registers -- not after the last store (with K = 1024 / 1280 a tile's main loop
       // is barely longer than its epilogue, so every cycle the accumulator is held stalls the tensor pipe).
-      // tools/bench_gemm.py SHAPES=b32: +1 ... +3.6 % per shape (SAM qkv 1373 -> 1423, LLaMA gate/up 1621 -> 1680 TFLOP/s);
-      // neutral inside the power-capped step (same-box A/B: 709.8 / 711.3 vs 708.8 / 712.8 ms).
+      // Same-box A/B against load -> wait -> activation -> stores per chunk (tools/bench_gemm.py SHAPES=b32, and the
+      // whole step): within +-2 % per shape either way, i.e. neutral at the power cap -- kept for the early release.
       if constexpr (EPI == EPI_QKV_ROPE) {
         // chunks (c, c + 2) are the two halves of a rotation pair: this warp takes c = half and c = half + 4
 #pragma unroll 1
