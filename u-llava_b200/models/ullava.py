@@ -230,7 +230,8 @@ class UllavaForCausalLM(PreTrainedModel):
     def _blocks_under_decode(self, enc, batch: int, max_new_tokens: int, sms_lane: int) -> int:
         """How many encoder blocks fit under the decode steps.  Decode step: the 16-bit LLaMA weights + the KV rows
         stream once per token at ~4.5 TB/s (+ ~10 % on the smaller lane); encoder block on the lane: its GEMM /
-        attention FLOPs at ~8 TFLOP/s per SM (tools/bench_overlap.py: ViT-H, B = 32, 60 SMs -> 11.5 ms per block).
+        attention FLOPs at ~9 TFLOP/s per SM (tools/bench_overlap.py: ViT-H, B = 32, 60 SMs -> 10.5 ms per block with the
+        round-2 attention kernels; bench.py --overlap-blocks 28 / 30 / 32 on one box: 695 / 687 / 688 ms per step).
         A block too many costs more (it runs on a fraction of the machine while the rest idles) than a block too few
         (it runs at full speed afterwards), hence the 0.9."""
         c = self.llm.config
@@ -241,7 +242,7 @@ class UllavaForCausalLM(PreTrainedModel):
         n_tok = (enc.img_size // enc.patch_size) ** 2
         d = enc.embed_dim
         flop_block = batch * n_tok * (24.0 * d * d + 4.0 * d * min(n_tok, max(enc.window_size, 1) ** 2 * 4))
-        t_block = flop_block / (8.0e12 * max(sms_lane, 1))
+        t_block = flop_block / (9.0e12 * max(sms_lane, 1))
         return max(1, min(enc.depth, int(0.9 * t_decode / max(t_block, 1e-9))))
 
     def evaluate(self, images_sam, images, input_ids, raw_size_list, resize_list, max_new_tokens=32, temperature=0.2,
