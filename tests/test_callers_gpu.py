@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 import torch
 
-import native
 from oracle import callers_oracle as O
 from tests.util_models import build_tiny_core, load_golden, oracle_inputs_core
 

@@ -9,7 +9,6 @@ take minutes: size-independent properties of the product path, plus the oracle o
   c4  full u-LLaVA-7B pipeline, batch 8, 64 greedy tokens + masks: run-to-run determinism (bit-identical ids and mask
       logits), batch invariance of the token ids, mask logits of batch-8 and batch-2 runs equal up to 16-bit rounding.
 Synthetic weights of the real architecture (bench.build_model, seed 0), the bench's synthetic inputs."""
-import numpy as np
 import pytest
 import torch
 

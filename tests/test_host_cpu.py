@@ -334,7 +334,7 @@ def test_lora_adapters_are_folded_into_packed_weights():
     import torch
     from transformers import LlamaConfig, LlamaModel
     from models.engine import LlamaStack, effective_weight
-    from tests.util_models import LoraLinearStub, inject_lora
+    from tests.util_models import inject_lora
     torch.manual_seed(0)
     lc = LlamaConfig(vocab_size=64, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
                      num_key_value_heads=2)

@@ -1,6 +1,5 @@
 """GPU parity of every primitive kernel behind the C ABI against a plain torch fp32 reference of the
 same op (floating-point kernels; tolerances written next to each check)."""
-import math
 
 import pytest
 import torch

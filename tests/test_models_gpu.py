@@ -15,7 +15,7 @@ import native
 from oracle import ullava_oracle as O
 from oracle.synth import subsample, synth_normal, synth_state_dict
 from tests import configs as C
-from tests.util_models import (build_tiny_core, build_tiny_full, core_cfg, greedy_walk, iou, load_golden,
+from tests.util_models import (build_tiny_core, build_tiny_full, greedy_walk, iou, load_golden,
                                oracle_inputs_core, oracle_inputs_full)
 
 pytestmark = pytest.mark.gpu
