@@ -409,6 +409,28 @@ def test_flash_attention_maximum_handed_from_tile_to_tile(ctx, dtype, D, Sk):
     _check(out, ref, dtype, f"handed-on maximum {Sk, D}")
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,S,D,causal", [
+    (7, 9, 577, 64, False),      # 315 items of 5 tiles on 148 persistent CTAs: every CTA crosses item boundaries
+    (3, 16, 1400, 128, True),    # causal: items of 1 ... 11 tiles, odd and even tile counts follow each other
+    (2, 3, 700, 80, False),      # fewer items than SMs: one item per CTA through the same loop
+    (5, 31, 130, 64, True),      # two-tile items whose second tile is almost empty
+])
+def test_flash_attention_persistent_items(ctx, dtype, B, H, S, D, causal):
+    """The bias-free kernels run one CTA per SM over (query tile, head, batch) items with the K / V ring, the S buffers
+    and the softmax alternation carried across items (fmha_sm100.cu, fm_item): check the item boundaries."""
+    qkv = _rand((B, S, 3, H, D), dtype, seed=52)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    ctx.set_attention_impl(2)
+    try:
+        out = ctx.attention(q, k, v, causal=causal)
+        again = ctx.attention(q, k, v, causal=causal)
+    finally:
+        ctx.set_attention_impl(0)
+    _check(out, _attn_ref(q, k, v, causal, 0, D ** -0.5), dtype, f"persistent attention {B,H,S,D,causal}")
+    assert torch.equal(out, again)
+
+
 @pytest.mark.parametrize("D,Sk,causal", [(64, 4096, False), (128, 1664, True), (80, 1000, False)])
 def test_flash_attention_is_bit_reproducible(ctx, D, Sk, causal):
     """The pipeline has nine asynchronous parties per CTA (TMA, two MMA issuers, eight softmax warps); a missed
