@@ -52,6 +52,7 @@ struct GemmKernelParams {
   int group_m;        // rasterisation group: M tiles swept together over N (their A panel stays L2 resident)
   uint64_t hint_a, hint_b;  // L2 eviction priority of the A / B tile loads (CTA-pair kernel)
   RopeFuse rope;            // EPI_QKV_ROPE only
+  int tma_store;            // CTA-pair kernel: D leaves through shared memory + cp.async.bulk.tensor (16-bit outputs)
 };
 
 template <int BN, int STAGES>
@@ -403,7 +404,11 @@ struct PairSmem {
   static constexpr int kBBytes = (kPairBN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kPairStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * kPairStages + 4) * 8 + 16 + 1024;
+  // epilogue staging for the TMA store: 8 warps x 2 buffers x (32 rows x 64 B), SWIZZLE_64B
+  static constexpr int kStoreOffset = kBarOffset + 1024;
+  static constexpr int kStoreBytes = kEpiWarps * 2 * 2048;
+  static constexpr int kTotal = kStoreOffset + kStoreBytes + 1024;
+  static_assert((2 * kPairStages + 4) * 8 + 16 <= 1024, "barrier block");
 };
 
 // EPI_QKV_ROPE: the prefill qkv projection of LLaMA (hf:models/llama/modeling_llama.py:137-168, 240-262) with RoPE and
@@ -466,10 +471,78 @@ __device__ __forceinline__ void rope_pair_store(const uint32_t (&lo)[32], const 
   }
 }
 
+// Epilogue of one 32-row x 32-column chunk through shared memory and a TMA store (16-bit D, no SiLU-mul): bias,
+// activation and residual in registers like epilogue_store, then each lane writes its row's 64 bytes into a
+// SWIZZLE_64B staging tile (16-byte chunk k of row r at chunk k ^ ((r >> 1) & 3): conflict-free), and one lane issues
+// cp.async.bulk.tensor for the whole tile -- full 64-byte row segments instead of four 16-byte stores per lane, and
+// rows / columns beyond M / N are clipped by the tensor map.  The whole warp calls this.
+template <typename T, int EPI>
+__device__ __forceinline__ void epilogue_tma_store(float (&v)[32], const GemmKernelParams& p, const T* bias,
+                                                   const T* resid, int row, bool row_ok, int row0, int n0,
+                                                   uint8_t* stage, const CUtensorMap* tmD, int lane) {
+  const bool full_chunk = (n0 + 32 <= p.N);
+  if (bias != nullptr) {
+    if (full_chunk && ((reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 b = *reinterpret_cast<const uint4*>(bias + n0 + i);
+        float2 f;
+        f = unpack2<T>(b.x); v[i] += f.x; v[i + 1] += f.y;
+        f = unpack2<T>(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+        f = unpack2<T>(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+        f = unpack2<T>(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += T16<T>::to_f(bias[n0 + i]);
+    }
+  }
+  if constexpr (EPI != EPI_NONE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = apply_act<EPI>(v[i]);
+  }
+  if (resid != nullptr && row_ok) {
+    const T* rr = resid + static_cast<int64_t>(row) * p.ldr + n0;
+    if (full_chunk && ((reinterpret_cast<uintptr_t>(rr) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 b = *reinterpret_cast<const uint4*>(rr + i);
+        float2 f;
+        f = unpack2<T>(b.x); v[i] += f.x; v[i + 1] += f.y;
+        f = unpack2<T>(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+        f = unpack2<T>(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+        f = unpack2<T>(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += T16<T>::to_f(rr[i]);
+    }
+  }
+  uint8_t* my = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 w;
+    w.x = pack2<T>(v[8 * k], v[8 * k + 1]);
+    w.y = pack2<T>(v[8 * k + 2], v[8 * k + 3]);
+    w.z = pack2<T>(v[8 * k + 4], v[8 * k + 5]);
+    w.w = pack2<T>(v[8 * k + 6], v[8 * k + 7]);
+    *reinterpret_cast<uint4*>(my + ((k ^ sw) << 4)) = w;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(tmD, stage, n0, row0, 0, 0);
+    tma_store_commit();
+  }
+}
+
 template <typename T, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmKernelParams p) {
+                         const __grid_constant__ CUtensorMap tmD, const GemmKernelParams p) {
   using S = PairSmem;
   constexpr int STAGES = kPairStages;
   constexpr int BN = kPairBN;
@@ -482,6 +555,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* store_stage = smem + S::kStoreOffset;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -629,6 +703,18 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         const int n0 = n_blk * BN + c * 32;
+        if constexpr (EPI != EPI_SILU_MUL) {
+          if (p.tma_store) {
+            if (n0 < p.N) {
+              // staging buffer i & 1 of this warp: the store issued from it two chunks ago must have read it
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+              epilogue_tma_store<T, EPI>(v, p, bias, resid, row, row_ok, row - lane, n0,
+                                         store_stage + ((warp - kEpiWarp0) * 2 + (i & 1)) * 2048, &tmD, lane);
+            }
+            continue;
+          }
+        }
         if (row_ok && n0 < p.N) epilogue_store<T, EPI, 32>(v, p, bias, resid, false, 0, row, n0);
       }
       }
@@ -637,6 +723,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         acc_phase ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait<0>();   // this thread's bulk stores have completed before the CTA may exit
   }
 
   tc_fence_before();
@@ -762,25 +849,25 @@ static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const
 }
 
 template <typename T, int EPI>
-static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
-                       cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmKernelParams& p,
+                       int grid, cudaStream_t stream) {
   auto kern = gemm_tcgen05_pair_kernel<T, EPI>;
   static SmemOptIn opt_in;   // per device (common.cuh)
   { const int _st = ensure_dynamic_smem(kern, PairSmem::kTotal, opt_in); if (_st != OK) return _st; }
-  kern<<<grid, kGemmThreads, PairSmem::kTotal, stream>>>(ta, tb, p);   // __cluster_dims__(2, 1, 1): grid is even
+  kern<<<grid, kGemmThreads, PairSmem::kTotal, stream>>>(ta, tb, td, p);   // __cluster_dims__(2, 1, 1): grid is even
   return check_cuda(cudaGetLastError(), "gemm_tcgen05_pair_kernel launch");
 }
 
 template <typename T>
-static int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, int grid,
-                           cudaStream_t stream) {
+static int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
+                           const GemmKernelParams& p, int grid, cudaStream_t stream) {
   switch (epi) {
-    case EPI_NONE: return launch_pair<T, EPI_NONE>(ta, tb, p, grid, stream);
-    case EPI_RELU: return launch_pair<T, EPI_RELU>(ta, tb, p, grid, stream);
-    case EPI_GELU: return launch_pair<T, EPI_GELU>(ta, tb, p, grid, stream);
-    case EPI_QUICK_GELU: return launch_pair<T, EPI_QUICK_GELU>(ta, tb, p, grid, stream);
-    case EPI_SILU_MUL: return launch_pair<T, EPI_SILU_MUL>(ta, tb, p, grid, stream);
-    case EPI_QKV_ROPE: return launch_pair<T, EPI_QKV_ROPE>(ta, tb, p, grid, stream);
+    case EPI_NONE: return launch_pair<T, EPI_NONE>(ta, tb, td, p, grid, stream);
+    case EPI_RELU: return launch_pair<T, EPI_RELU>(ta, tb, td, p, grid, stream);
+    case EPI_GELU: return launch_pair<T, EPI_GELU>(ta, tb, td, p, grid, stream);
+    case EPI_QUICK_GELU: return launch_pair<T, EPI_QUICK_GELU>(ta, tb, td, p, grid, stream);
+    case EPI_SILU_MUL: return launch_pair<T, EPI_SILU_MUL>(ta, tb, td, p, grid, stream);
+    case EPI_QKV_ROPE: return launch_pair<T, EPI_QKV_ROPE>(ta, tb, td, p, grid, stream);
     default: set_last_error("gemm: unknown epilogue %d", epi); return ERR_BAD_ARG;
   }
 }
@@ -904,8 +991,20 @@ int gemm_run(Context* ctx, const GemmArgs& a, cudaStream_t stream) {
         p.rope = *rope;
         epi = EPI_QKV_ROPE;
       }
-      st = (a.dtype == DT_BF16) ? launch_pair_epi<__nv_bfloat16>(epi, ta, tb, p, grid, stream)
-                                : launch_pair_epi<__half>(epi, ta, tb, p, grid, stream);
+      // D through shared memory + TMA store whenever it is a plain 16-bit matrix the tensor map can describe
+      CUtensorMap td = ta;
+      p.tma_store = 0;
+      if (!rope && !a.out_f32 && a.epilogue != EPI_SILU_MUL && ctx->gemm_tma_store != 0 && (a.ldd % 8) == 0 &&
+          (reinterpret_cast<uintptr_t>(a.D) & 15) == 0) {
+        const uint64_t dd[4] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.M), 1, 1};
+        const uint64_t ds[3] = {static_cast<uint64_t>(a.ldd) * 2, static_cast<uint64_t>(a.ldd) * 2 * a.M,
+                                static_cast<uint64_t>(a.ldd) * 2 * a.M};
+        st = encode_tmap_4d(&td, a.D, dd, ds, 32, 32, 64);
+        if (st) return st;
+        p.tma_store = 1;
+      }
+      st = (a.dtype == DT_BF16) ? launch_pair_epi<__nv_bfloat16>(epi, ta, tb, td, p, grid, stream)
+                                : launch_pair_epi<__half>(epi, ta, tb, td, p, grid, stream);
       if (st) return st;
       ctx->launches += 1;
       return OK;

@@ -153,6 +153,7 @@ int ullava_create(int device, ullava_ctx** out) {
   }
   if (const char* e = getenv("ULLAVA_GEMM_PAIR")) c->gemm_pair = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("ULLAVA_GEMM_HINTS")) c->gemm_hints = atoi(e) != 0 ? 1 : 0;
+  if (const char* e = getenv("ULLAVA_GEMM_TMA_STORE")) c->gemm_tma_store = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("ULLAVA_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0 && v <= 1024) c->group_m = v;

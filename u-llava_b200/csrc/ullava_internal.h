@@ -33,6 +33,7 @@ struct ullava_ctx {
   int64_t next_ldb = 0;
   int prefetch_units = 12;  // 16 KB tiles per SM pulled into L2 (0 = off); ULLAVA_PREFETCH_UNITS overrides at create
   int gemm_pair = 1;  // large-M GEMMs on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles); ULLAVA_GEMM_PAIR=0 turns it off
+  int gemm_tma_store = 1;  // CTA-pair GEMM: 16-bit D leaves through shared memory + cp.async.bulk.tensor (ULLAVA_GEMM_TMA_STORE=0: direct stores)
   int gemm_hints = 0; // L2 eviction-priority hints on the large-M GEMM operand loads (ULLAVA_GEMM_HINTS=1): measured
                       // counter-productive on B200, see gemm_sm100.cu
   int group_m = 0;    // 0 = default rasterisation group of the large-M GEMM; ULLAVA_GROUP_M overrides at create (tuning)
