@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ULLAVA_ABI_VERSION 3
+#define ULLAVA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ULLAVA_API __attribute__((visibility("default")))

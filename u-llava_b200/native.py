@@ -20,7 +20,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libullava_sm100.so")
 
-ABI_VERSION = 3   # ULLAVA_ABI_VERSION of include/ullava_sm100.h (struct layouts and signatures mirrored below)
+ABI_VERSION = 4   # ULLAVA_ABI_VERSION of include/ullava_sm100.h (struct layouts and signatures mirrored below)
 BF16, F16, F32 = 0, 1, 2
 EPI_NONE, EPI_RELU, EPI_GELU, EPI_QUICK_GELU, EPI_SILU_MUL = 0, 1, 2, 3, 4
 SAM_N_WEIGHTS = 121
